@@ -1,0 +1,304 @@
+"""ctypes binding of libcgsvmc.so (include/cgsvmc.h) for torch CUDA tensors.
+
+torch is used for device memory and streams only; the signatures that cross
+the boundary are plain pointers and sizes.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libcgsvmc.so')
+
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
+ANSATZ_KINDS = {'fully_connected': 1, 'rbm': 2, 'conv_1d': 3, 'conv_2d': 4}
+ACTIVATIONS = {'relu': 0, 'tanh': 1, 'sigmoid': 2, 'identity': 3, 'cos': 4,
+               'exp': 5, 'tan': 6}
+
+EXPORTS = [
+    'cgsvmc_version', 'cgsvmc_last_error', 'cgsvmc_ansatz_create',
+    'cgsvmc_ansatz_destroy', 'cgsvmc_ansatz_num_params',
+    'cgsvmc_ansatz_bind_params', 'cgsvmc_ham_create', 'cgsvmc_ham_destroy',
+    'cgsvmc_pack_configs', 'cgsvmc_unpack_configs', 'cgsvmc_random_configs',
+    'cgsvmc_log_amp', 'cgsvmc_mc_steps', 'cgsvmc_mc_step_replay',
+    'cgsvmc_flip_enum', 'cgsvmc_local_energy', 'cgsvmc_weighted_grad_sum',
+    'cgsvmc_energy_stats',
+]
+
+
+class AnsatzDesc(ctypes.Structure):
+  _fields_ = [(n, ctypes.c_int32) for n in (
+      'kind', 'n_sites', 'num_layers', 'layer_size', 'num_filters',
+      'kernel_size', 'size_x', 'size_y', 'nonlinearity')]
+
+
+class NativeError(RuntimeError):
+  pass
+
+
+_lib = None
+
+
+def load():
+  """Loads the shared library (once).  Raises if it has not been built."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise NativeError(
+        'libcgsvmc.so is missing (%s): run `python __graft_entry__.py` to '
+        'build the CUDA library; there is no CPU fallback.' % LIB_PATH)
+  lib = ctypes.CDLL(LIB_PATH)
+  vp, i32, i64, u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64
+  lib.cgsvmc_version.restype = ctypes.c_int
+  lib.cgsvmc_last_error.restype = ctypes.c_char_p
+  lib.cgsvmc_ansatz_create.argtypes = [ctypes.POINTER(AnsatzDesc), ctypes.POINTER(vp)]
+  lib.cgsvmc_ansatz_destroy.argtypes = [vp]
+  lib.cgsvmc_ansatz_num_params.argtypes = [vp]
+  lib.cgsvmc_ansatz_num_params.restype = i64
+  lib.cgsvmc_ansatz_bind_params.argtypes = [vp, vp]
+  lib.cgsvmc_ham_create.argtypes = [vp, vp, vp, i32, i32, ctypes.POINTER(vp)]
+  lib.cgsvmc_ham_destroy.argtypes = [vp]
+  lib.cgsvmc_pack_configs.argtypes = [vp, i64, i32, vp, vp]
+  lib.cgsvmc_unpack_configs.argtypes = [vp, i64, i32, vp, vp]
+  lib.cgsvmc_random_configs.argtypes = [vp, i64, i32, u64, u64, vp]
+  lib.cgsvmc_log_amp.argtypes = [vp, vp, i64, vp, vp]
+  lib.cgsvmc_mc_steps.argtypes = [vp, vp, i64, i32, u64, u64, u64, vp, vp, vp]
+  lib.cgsvmc_mc_step_replay.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
+  lib.cgsvmc_flip_enum.argtypes = [vp, vp, i64, vp, vp, vp]
+  lib.cgsvmc_local_energy.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp]
+  lib.cgsvmc_weighted_grad_sum.argtypes = [vp, vp, vp, i64, i32, vp, vp]
+  lib.cgsvmc_energy_stats.argtypes = [vp, i64, vp, vp]
+  for name in EXPORTS:
+    fn = getattr(lib, name)
+    if name not in ('cgsvmc_last_error', 'cgsvmc_ansatz_num_params'):
+      fn.restype = ctypes.c_int
+  _lib = lib
+  return lib
+
+
+def check(rc):
+  """Maps a status code to the exception the reference raises for the same
+  condition (ValueError for shape / registry errors)."""
+  if rc == OK:
+    return
+  msg = load().cgsvmc_last_error().decode('utf-8', 'replace')
+  if rc == ERR_INVALID:
+    raise ValueError(msg)
+  if rc == ERR_UNSUPPORTED:
+    raise NotImplementedError(msg)
+  raise NativeError('cgsvmc error %d: %s' % (rc, msg))
+
+
+def require_cuda():
+  if not torch.cuda.is_available():
+    raise NativeError('no CUDA device: cgs_vmc_b200 has no CPU fallback')
+
+
+def _ptr(t):
+  return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+  return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def n_words(n_sites):
+  return (n_sites + 63) // 64
+
+
+def _want(t, dtype, shape=None, name='tensor'):
+  if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+    raise ValueError('%s must be a contiguous CUDA tensor of dtype %s' % (name, dtype))
+  if shape is not None and tuple(t.shape) != tuple(shape):
+    raise ValueError('%s has shape %s, expected %s' % (name, tuple(t.shape), tuple(shape)))
+
+
+class Ansatz:
+  """Owns a cgsvmc_ansatz handle and the flat float32 parameter buffer."""
+
+  def __init__(self, kind, n_sites, num_layers=0, layer_size=0, num_filters=0,
+               kernel_size=0, size_x=1, size_y=1, nonlinearity='relu',
+               device='cuda'):
+    require_cuda()
+    lib = load()
+    if kind not in ANSATZ_KINDS:
+      raise ValueError('Provided wavefunction_type is not registered.')
+    if nonlinearity not in ACTIVATIONS:
+      raise ValueError('unknown nonlinearity %r' % (nonlinearity,))
+    self.kind, self.n_sites = kind, n_sites
+    self.device = torch.device(device)
+    desc = AnsatzDesc(ANSATZ_KINDS[kind], n_sites, num_layers, layer_size,
+                      num_filters, kernel_size, size_x, size_y,
+                      ACTIVATIONS[nonlinearity])
+    self.desc = desc
+    handle = ctypes.c_void_p()
+    with torch.cuda.device(self.device):
+      check(lib.cgsvmc_ansatz_create(ctypes.byref(desc), ctypes.byref(handle)))
+    self._handle = handle
+    self.num_params = int(lib.cgsvmc_ansatz_num_params(handle))
+    self.params = torch.zeros(self.num_params, dtype=torch.float32, device=self.device)
+    check(lib.cgsvmc_ansatz_bind_params(handle, _ptr(self.params)))
+
+  def set_params(self, flat):
+    """Copies a flat parameter vector (layout of include/cgsvmc.h) in place."""
+    flat = torch.as_tensor(flat, dtype=torch.float32).reshape(-1)
+    if flat.numel() != self.num_params:
+      raise ValueError('expected %d parameters, got %d' % (self.num_params, flat.numel()))
+    self.params.copy_(flat.to(self.device))
+
+  def close(self):
+    if getattr(self, '_handle', None) is not None and _lib is not None:
+      _lib.cgsvmc_ansatz_destroy(self._handle)
+      self._handle = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:   # interpreter shutdown
+      pass
+
+  # ---- compute entry points -------------------------------------------
+  def log_amp(self, packed, out=None):
+    b = packed.shape[0]
+    _want(packed, torch.int64, (b, n_words(self.n_sites)), 'packed')
+    if out is None:
+      out = torch.empty(b, dtype=torch.float32, device=packed.device)
+    check(load().cgsvmc_log_amp(self._handle, _ptr(packed), b, _ptr(out), _stream()))
+    return out
+
+  def mc_steps(self, packed, n_steps, seed, walker_id0=0, step0=0,
+               accept_count=None, log_amp_out=None):
+    b = packed.shape[0]
+    _want(packed, torch.int64, (b, n_words(self.n_sites)), 'packed')
+    if accept_count is not None:
+      _want(accept_count, torch.int64, (1,), 'accept_count')
+    if log_amp_out is not None:
+      _want(log_amp_out, torch.float32, (b,), 'log_amp_out')
+    check(load().cgsvmc_mc_steps(self._handle, _ptr(packed), b, int(n_steps),
+                                 int(seed), int(walker_id0), int(step0),
+                                 _ptr(accept_count), _ptr(log_amp_out), _stream()))
+
+  def mc_step_replay(self, packed, u_sites, u_acc):
+    b = packed.shape[0]
+    _want(packed, torch.int64, (b, n_words(self.n_sites)), 'packed')
+    _want(u_sites, torch.float32, (b, self.n_sites), 'u_sites')
+    _want(u_acc, torch.float32, (b,), 'u_acc')
+    dev = packed.device
+    down = torch.empty(b, dtype=torch.int32, device=dev)
+    up = torch.empty(b, dtype=torch.int32, device=dev)
+    log_ratio = torch.empty(b, dtype=torch.float32, device=dev)
+    accept = torch.empty(b, dtype=torch.uint8, device=dev)
+    check(load().cgsvmc_mc_step_replay(self._handle, _ptr(packed), b, _ptr(u_sites),
+                                       _ptr(u_acc), _ptr(down), _ptr(up),
+                                       _ptr(log_ratio), _ptr(accept), _stream()))
+    return down, up, log_ratio, accept
+
+  def local_energy(self, ham, packed, want_parts=False):
+    b = packed.shape[0]
+    _want(packed, torch.int64, (b, n_words(self.n_sites)), 'packed')
+    dev = packed.device
+    e = torch.empty(b, dtype=torch.float32, device=dev)
+    z = torch.empty(b, dtype=torch.float32, device=dev)
+    diag = torch.empty(b, dtype=torch.float32, device=dev) if want_parts else None
+    off = torch.empty(b, dtype=torch.float32, device=dev) if want_parts else None
+    check(load().cgsvmc_local_energy(self._handle, ham._handle, _ptr(packed), b,
+                                     _ptr(e), _ptr(z), _ptr(diag), _ptr(off), _stream()))
+    return (e, z, diag, off) if want_parts else (e, z)
+
+  def weighted_grad_sum(self, packed, weights, out=None):
+    b = packed.shape[0]
+    _want(packed, torch.int64, (b, n_words(self.n_sites)), 'packed')
+    if weights.dim() == 1:
+      weights = weights.reshape(1, -1)
+    k = weights.shape[0]
+    _want(weights, torch.float32, (k, b), 'weights')
+    if out is None:
+      out = torch.zeros(k, self.num_params, dtype=torch.float32, device=packed.device)
+    else:
+      _want(out, torch.float32, (k, self.num_params), 'out')
+    check(load().cgsvmc_weighted_grad_sum(self._handle, _ptr(packed), _ptr(weights),
+                                          b, k, _ptr(out), _stream()))
+    return out
+
+
+class Hamiltonian:
+  """Owns a cgsvmc_ham handle (bond table on the device)."""
+
+  def __init__(self, bonds_ij, jx, jz, n_sites, device='cuda'):
+    require_cuda()
+    lib = load()
+    ij = np.ascontiguousarray(np.asarray(bonds_ij, dtype=np.int32).reshape(-1, 2))
+    n_bonds = ij.shape[0]
+    jx = np.ascontiguousarray(np.broadcast_to(np.asarray(jx, dtype=np.float32), (n_bonds,)))
+    jz = np.ascontiguousarray(np.broadcast_to(np.asarray(jz, dtype=np.float32), (n_bonds,)))
+    self.n_bonds, self.n_sites = n_bonds, n_sites
+    self.bonds_ij, self.jx, self.jz = ij, jx, jz
+    handle = ctypes.c_void_p()
+    with torch.cuda.device(torch.device(device)):
+      check(lib.cgsvmc_ham_create(ij.ctypes.data_as(ctypes.c_void_p),
+                                  jx.ctypes.data_as(ctypes.c_void_p),
+                                  jz.ctypes.data_as(ctypes.c_void_p),
+                                  n_bonds, n_sites, ctypes.byref(handle)))
+    self._handle = handle
+
+  def close(self):
+    if getattr(self, '_handle', None) is not None and _lib is not None:
+      _lib.cgsvmc_ham_destroy(self._handle)
+      self._handle = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+  def flip_enum(self, packed, want_flipped=True):
+    b, w = packed.shape
+    _want(packed, torch.int64, (b, n_words(self.n_sites)), 'packed')
+    dev = packed.device
+    mask = torch.empty(b, (self.n_bonds + 31) // 32, dtype=torch.int32, device=dev)
+    flipped = torch.empty(b, self.n_bonds, w, dtype=torch.int64, device=dev) \
+        if want_flipped else None
+    check(load().cgsvmc_flip_enum(self._handle, _ptr(packed), b, _ptr(flipped),
+                                  _ptr(mask), _stream()))
+    return mask, flipped
+
+
+def pack_configs(configs):
+  """float32 [B, N] of +-1 (CUDA) -> int64-viewed uint64 [B, W]."""
+  require_cuda()
+  b, n = configs.shape
+  _want(configs, torch.float32, (b, n), 'configs')
+  packed = torch.empty(b, n_words(n), dtype=torch.int64, device=configs.device)
+  check(load().cgsvmc_pack_configs(_ptr(configs), b, n, _ptr(packed), _stream()))
+  return packed
+
+
+def unpack_configs(packed, n_sites, out=None):
+  require_cuda()
+  b = packed.shape[0]
+  _want(packed, torch.int64, (b, n_words(n_sites)), 'packed')
+  if out is None:
+    out = torch.empty(b, n_sites, dtype=torch.float32, device=packed.device)
+  check(load().cgsvmc_unpack_configs(_ptr(packed), b, n_sites, _ptr(out), _stream()))
+  return out
+
+
+def random_configs(batch_size, n_sites, seed, walker_id0=0, device='cuda'):
+  require_cuda()
+  packed = torch.empty(batch_size, n_words(n_sites), dtype=torch.int64, device=device)
+  check(load().cgsvmc_random_configs(_ptr(packed), batch_size, n_sites, int(seed),
+                                     int(walker_id0), _stream()))
+  return packed
+
+
+def energy_stats(e_loc, stats=None):
+  require_cuda()
+  _want(e_loc, torch.float32, None, 'e_loc')
+  if stats is None:
+    stats = torch.zeros(4, dtype=torch.float64, device=e_loc.device)
+  check(load().cgsvmc_energy_stats(_ptr(e_loc), e_loc.numel(), _ptr(stats), _stream()))
+  return stats

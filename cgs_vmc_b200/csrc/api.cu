@@ -1,0 +1,300 @@
+// extern "C" entry points of include/cgsvmc.h: argument checking, handle
+// management and dispatch to the kernel launchers.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "internal.h"
+
+namespace cgsvmc {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t err, const char* what) {
+  if (err == cudaSuccess) return CGSVMC_OK;
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(err);
+  return CGSVMC_ERR_CUDA;
+}
+
+int ensure_scratch(cgsvmc_ansatz* a, size_t bytes) {
+  if (bytes <= a->scratch_bytes) return CGSVMC_OK;
+  if (a->scratch != nullptr) {
+    // earlier launches may still read the old buffer
+    if (int rc = cuda_fail(cudaDeviceSynchronize(), "scratch sync")) return rc;
+    cudaFree(a->scratch);
+    a->scratch = nullptr;
+    a->scratch_bytes = 0;
+  }
+  if (int rc = cuda_fail(cudaMalloc(&a->scratch, bytes), "scratch alloc")) return rc;
+  a->scratch_bytes = bytes;
+  return CGSVMC_OK;
+}
+
+namespace {
+
+int invalid(const char* msg) {
+  set_error(msg);
+  return CGSVMC_ERR_INVALID;
+}
+
+// Tensor sizes of the flat parameter layout (see cgsvmc.h).
+bool layout(const cgsvmc_ansatz_desc& d, std::vector<int64_t>* sizes) {
+  sizes->clear();
+  const int64_t N = d.n_sites;
+  switch (d.kind) {
+    case CGSVMC_ANSATZ_FULLY_CONNECTED: {
+      int64_t n_in = N;
+      for (int l = 0; l < d.num_layers; ++l) {
+        sizes->push_back(n_in * d.layer_size);
+        sizes->push_back(d.layer_size);
+        n_in = d.layer_size;
+      }
+      sizes->push_back(n_in);
+      sizes->push_back(1);
+      return true;
+    }
+    case CGSVMC_ANSATZ_RBM: {
+      sizes->push_back(N);
+      sizes->push_back(1);
+      int64_t n_in = N;
+      for (int l = 0; l < d.num_layers; ++l) {
+        sizes->push_back(n_in * d.layer_size);
+        sizes->push_back(d.layer_size);
+        n_in = d.layer_size;
+      }
+      sizes->push_back(n_in * d.layer_size);
+      sizes->push_back(d.layer_size);
+      return true;
+    }
+    case CGSVMC_ANSATZ_CONV_1D:
+    case CGSVMC_ANSATZ_CONV_2D: {
+      int64_t c_in = 1;
+      const int64_t taps = d.kind == CGSVMC_ANSATZ_CONV_1D ? d.kernel_size
+                                                           : (int64_t)d.kernel_size * d.kernel_size;
+      for (int l = 0; l < d.num_layers; ++l) {
+        sizes->push_back(taps * c_in * d.num_filters);
+        sizes->push_back(d.num_filters);
+        c_in = d.num_filters;
+      }
+      return true;
+    }
+    default:
+      return false;
+  }
+}
+
+int check_ready(const cgsvmc_ansatz* a) {
+  if (a == nullptr) return invalid("ansatz handle is NULL");
+  if (a->params == nullptr) return invalid("no parameters bound: call cgsvmc_ansatz_bind_params first");
+  return CGSVMC_OK;
+}
+
+}  // namespace
+}  // namespace cgsvmc
+
+using namespace cgsvmc;
+
+extern "C" {
+
+int cgsvmc_version(void) { return CGSVMC_VERSION; }
+
+const char* cgsvmc_last_error(void) { return g_last_error.c_str(); }
+
+int cgsvmc_ansatz_create(const cgsvmc_ansatz_desc* desc, cgsvmc_ansatz** out) {
+  if (desc == nullptr || out == nullptr) return invalid("ansatz_create: NULL argument");
+  *out = nullptr;
+  const cgsvmc_ansatz_desc& d = *desc;
+  std::vector<int64_t> sizes;
+  if (!layout(d, &sizes)) return invalid("Provided wavefunction_type is not registered.");
+  if (d.n_sites < 2 || d.n_sites > CGSVMC_MAX_SITES)
+    return invalid("ansatz_create: n_sites must be in [2, 256]");
+  if (d.num_layers < 0) return invalid("ansatz_create: num_layers < 0");
+  if (d.kind == CGSVMC_ANSATZ_FULLY_CONNECTED || d.kind == CGSVMC_ANSATZ_RBM) {
+    if (d.layer_size < 1) return invalid("ansatz_create: layer_size < 1");
+  } else {
+    if (d.num_layers < 1 || d.num_filters < 1 || d.kernel_size < 1)
+      return invalid("ansatz_create: conv needs num_layers, num_filters, kernel_size >= 1");
+    if (d.kind == CGSVMC_ANSATZ_CONV_2D && (int64_t)d.size_x * d.size_y != d.n_sites)
+      return invalid("ansatz_create: size_x * size_y must equal n_sites");
+  }
+  if (d.nonlinearity < CGSVMC_ACT_RELU || d.nonlinearity > CGSVMC_ACT_TAN)
+    return invalid("ansatz_create: unknown nonlinearity");
+  cgsvmc_ansatz* a = new (std::nothrow) cgsvmc_ansatz();
+  if (a == nullptr) return invalid("ansatz_create: out of host memory");
+  a->desc = d;
+  a->sizes = sizes;
+  int64_t off = 0;
+  for (int64_t s : sizes) { a->offsets.push_back(off); off += s; }
+  a->n_params = off;
+  cudaError_t e = cudaGetDevice(&a->device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&a->num_sms, cudaDevAttrMultiProcessorCount, a->device);
+  if (e == cudaSuccess)
+    e = cudaDeviceGetAttribute(&a->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, a->device);
+  if (e != cudaSuccess) {
+    delete a;
+    return cuda_fail(e, "ansatz_create: device query");
+  }
+  *out = a;
+  return CGSVMC_OK;
+}
+
+int cgsvmc_ansatz_destroy(cgsvmc_ansatz* a) {
+  if (a == nullptr) return CGSVMC_OK;
+  if (a->scratch != nullptr) cudaFree(a->scratch);
+  delete a;
+  return CGSVMC_OK;
+}
+
+int64_t cgsvmc_ansatz_num_params(const cgsvmc_ansatz* a) { return a == nullptr ? -1 : a->n_params; }
+
+int cgsvmc_ansatz_bind_params(cgsvmc_ansatz* a, const float* params_dev) {
+  if (a == nullptr || params_dev == nullptr) return invalid("bind_params: NULL argument");
+  a->params = params_dev;
+  return CGSVMC_OK;
+}
+
+int cgsvmc_ham_create(const int32_t* ij_host, const float* jx_host, const float* jz_host,
+                      int32_t n_bonds, int32_t n_sites, cgsvmc_ham** out) {
+  if (out == nullptr) return invalid("ham_create: NULL out");
+  *out = nullptr;
+  if (n_bonds < 0 || (n_bonds > 0 && (ij_host == nullptr || jx_host == nullptr || jz_host == nullptr)))
+    return invalid("ham_create: NULL bond arrays");
+  if (n_sites < 2 || n_sites > CGSVMC_MAX_SITES) return invalid("ham_create: n_sites must be in [2, 256]");
+  for (int k = 0; k < 2 * n_bonds; ++k)
+    if (ij_host[k] < 0 || ij_host[k] >= n_sites) return invalid("ham_create: bond site index out of range");
+  for (int k = 0; k < n_bonds; ++k)
+    if (ij_host[2 * k] == ij_host[2 * k + 1]) return invalid("ham_create: bond connects a site to itself");
+  cgsvmc_ham* h = new (std::nothrow) cgsvmc_ham();
+  if (h == nullptr) return invalid("ham_create: out of host memory");
+  h->n_bonds = n_bonds;
+  h->n_sites = n_sites;
+  const size_t nb = (size_t)std::max(n_bonds, 1);
+  cudaError_t e = cudaMalloc(&h->ij, nb * sizeof(int2));
+  if (e == cudaSuccess) e = cudaMalloc(&h->jx, nb * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&h->jz, nb * sizeof(float));
+  if (e == cudaSuccess && n_bonds > 0) {
+    e = cudaMemcpy(h->ij, ij_host, (size_t)n_bonds * sizeof(int2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->jx, jx_host, (size_t)n_bonds * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->jz, jz_host, (size_t)n_bonds * sizeof(float), cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) {
+    cgsvmc_ham_destroy(h);
+    return cuda_fail(e, "ham_create");
+  }
+  *out = h;
+  return CGSVMC_OK;
+}
+
+int cgsvmc_ham_destroy(cgsvmc_ham* h) {
+  if (h == nullptr) return CGSVMC_OK;
+  if (h->ij) cudaFree(h->ij);
+  if (h->jx) cudaFree(h->jx);
+  if (h->jz) cudaFree(h->jz);
+  delete h;
+  return CGSVMC_OK;
+}
+
+int cgsvmc_pack_configs(const float* configs, int64_t B, int32_t N, uint64_t* packed, void* stream) {
+  if (B < 0 || N < 1 || N > CGSVMC_MAX_SITES) return invalid("pack_configs: bad shape");
+  if (B > 0 && (configs == nullptr || packed == nullptr)) return invalid("pack_configs: NULL buffer");
+  return launch_pack(configs, B, N, packed, (cudaStream_t)stream);
+}
+
+int cgsvmc_unpack_configs(const uint64_t* packed, int64_t B, int32_t N, float* configs, void* stream) {
+  if (B < 0 || N < 1 || N > CGSVMC_MAX_SITES) return invalid("unpack_configs: bad shape");
+  if (B > 0 && (configs == nullptr || packed == nullptr)) return invalid("unpack_configs: NULL buffer");
+  return launch_unpack(packed, B, N, configs, (cudaStream_t)stream);
+}
+
+int cgsvmc_random_configs(uint64_t* packed, int64_t B, int32_t N, uint64_t seed, uint64_t walker_id0,
+                          void* stream) {
+  if (B < 0 || N < 2 || N > CGSVMC_MAX_SITES) return invalid("random_configs: bad shape");
+  if (B > 0 && packed == nullptr) return invalid("random_configs: NULL buffer");
+  return launch_random_configs(packed, B, N, seed, walker_id0, (cudaStream_t)stream);
+}
+
+int cgsvmc_log_amp(const cgsvmc_ansatz* a, const uint64_t* packed, int64_t B, float* log_amp,
+                   void* stream) {
+  if (int rc = check_ready(a)) return rc;
+  if (B < 0) return invalid("log_amp: n_walkers < 0");
+  if (B == 0) return CGSVMC_OK;
+  if (packed == nullptr || log_amp == nullptr) return invalid("log_amp: NULL buffer");
+  if (rbm_fast_supported(a)) return rbm_log_amp(a, packed, B, log_amp, (cudaStream_t)stream);
+  return net_log_amp(a, packed, B, log_amp, (cudaStream_t)stream);
+}
+
+int cgsvmc_mc_steps(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int32_t n_steps,
+                    uint64_t seed, uint64_t walker_id0, uint64_t step0,
+                    unsigned long long* accept_count, float* log_amp_out, void* stream) {
+  if (int rc = check_ready(a)) return rc;
+  if (B < 0 || n_steps < 0) return invalid("mc_steps: negative size");
+  if (B == 0) return CGSVMC_OK;
+  if (packed == nullptr) return invalid("mc_steps: NULL configs");
+  if (rbm_fast_supported(a))
+    return rbm_mc_steps(a, packed, B, n_steps, seed, walker_id0, step0, accept_count, log_amp_out,
+                        (cudaStream_t)stream);
+  return net_mc_steps(a, packed, B, n_steps, seed, walker_id0, step0, accept_count, log_amp_out,
+                      (cudaStream_t)stream);
+}
+
+int cgsvmc_mc_step_replay(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, const float* u_sites,
+                          const float* u_acc, int32_t* down_site, int32_t* up_site,
+                          float* log_ratio, uint8_t* accept_mask, void* stream) {
+  if (int rc = check_ready(a)) return rc;
+  if (B < 0) return invalid("mc_step_replay: n_walkers < 0");
+  if (B == 0) return CGSVMC_OK;
+  if (packed == nullptr || u_sites == nullptr || u_acc == nullptr)
+    return invalid("mc_step_replay: NULL buffer");
+  if (rbm_fast_supported(a))
+    return rbm_mc_replay(a, packed, B, u_sites, u_acc, down_site, up_site, log_ratio, accept_mask,
+                         (cudaStream_t)stream);
+  return net_mc_replay(a, packed, B, u_sites, u_acc, down_site, up_site, log_ratio, accept_mask,
+                       (cudaStream_t)stream);
+}
+
+int cgsvmc_flip_enum(const cgsvmc_ham* h, const uint64_t* packed, int64_t B, uint64_t* flipped,
+                     uint32_t* active_mask, void* stream) {
+  if (h == nullptr) return invalid("flip_enum: NULL hamiltonian");
+  if (B < 0) return invalid("flip_enum: n_walkers < 0");
+  if (B > 0 && packed == nullptr) return invalid("flip_enum: NULL configs");
+  return launch_flip_enum(h, packed, B, flipped, active_mask, (cudaStream_t)stream);
+}
+
+int cgsvmc_local_energy(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed,
+                        int64_t B, float* e_loc, float* log_amp_out, float* diag_out,
+                        float* offdiag_ratio_out, void* stream) {
+  if (int rc = check_ready(a)) return rc;
+  if (h == nullptr) return invalid("local_energy: NULL hamiltonian");
+  if (h->n_sites != a->desc.n_sites) return invalid("local_energy: hamiltonian and ansatz n_sites differ");
+  if (B < 0) return invalid("local_energy: n_walkers < 0");
+  if (B == 0) return CGSVMC_OK;
+  if (packed == nullptr || e_loc == nullptr) return invalid("local_energy: NULL buffer");
+  if (rbm_fast_supported(a))
+    return rbm_local_energy(a, h, packed, B, e_loc, log_amp_out, diag_out, offdiag_ratio_out,
+                            (cudaStream_t)stream);
+  return net_local_energy(a, h, packed, B, e_loc, log_amp_out, diag_out, offdiag_ratio_out,
+                          (cudaStream_t)stream);
+}
+
+int cgsvmc_weighted_grad_sum(const cgsvmc_ansatz* a, const uint64_t* packed, const float* weights,
+                             int64_t B, int32_t K, float* out, void* stream) {
+  if (int rc = check_ready(a)) return rc;
+  if (B < 0) return invalid("weighted_grad_sum: n_walkers < 0");
+  if (K < 1 || K > 4) return invalid("weighted_grad_sum: n_weights must be in 1..4");
+  if (B == 0) return CGSVMC_OK;
+  if (packed == nullptr || weights == nullptr || out == nullptr)
+    return invalid("weighted_grad_sum: NULL buffer");
+  cgsvmc_ansatz* am = const_cast<cgsvmc_ansatz*>(a);   // scratch growth only
+  if (rbm_fast_supported(a)) return rbm_grad(am, packed, weights, B, K, out, (cudaStream_t)stream);
+  return net_grad(am, packed, weights, B, K, out, (cudaStream_t)stream);
+}
+
+int cgsvmc_energy_stats(const float* e_loc, int64_t B, double* stats, void* stream) {
+  if (B < 0) return invalid("energy_stats: n_walkers < 0");
+  if (B > 0 && (e_loc == nullptr || stats == nullptr)) return invalid("energy_stats: NULL buffer");
+  return launch_energy_stats(e_loc, B, stats, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+// Internal (C++) side of the C-ABI: handle layouts and kernel launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/cgsvmc.h"
+
+#ifndef CGSVMC_MAX_SITES
+#define CGSVMC_MAX_WORDS 4      // 64-bit words per walker: n_sites <= 256
+#define CGSVMC_MAX_SITES 256
+#endif
+
+struct cgsvmc_ansatz {
+  cgsvmc_ansatz_desc desc;
+  int64_t n_params = 0;
+  const float* params = nullptr;   // borrowed device buffer, flat layout
+  std::vector<int64_t> offsets;    // offset of every tensor of the flat layout
+  std::vector<int64_t> sizes;
+  int device = 0;
+  int num_sms = 148;
+  int max_smem_optin = 0;          // bytes
+  float* scratch = nullptr;        // owned device scratch (gradient partials ...)
+  size_t scratch_bytes = 0;
+};
+
+struct cgsvmc_ham {
+  int32_t n_bonds = 0;
+  int32_t n_sites = 0;
+  int2* ij = nullptr;    // device [n_bonds]
+  float* jx = nullptr;   // device [n_bonds]
+  float* jz = nullptr;   // device [n_bonds]
+};
+
+namespace cgsvmc {
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t err, const char* what);
+// Grows ansatz->scratch to at least `bytes` (stream-ordered free/alloc is not
+// needed: growth only happens on the first call of a given size).
+int ensure_scratch(cgsvmc_ansatz* a, size_t bytes);
+
+inline int n_words(int n_sites) { return (n_sites + 63) / 64; }
+
+// ---- utility kernels (util_kernels.cu) ----
+int launch_pack(const float* configs, int64_t B, int N, uint64_t* packed, cudaStream_t s);
+int launch_unpack(const uint64_t* packed, int64_t B, int N, float* configs, cudaStream_t s);
+int launch_random_configs(uint64_t* packed, int64_t B, int N, uint64_t seed, uint64_t walker0,
+                          cudaStream_t s);
+int launch_flip_enum(const cgsvmc_ham* h, const uint64_t* packed, int64_t B, uint64_t* flipped,
+                     uint32_t* mask, cudaStream_t s);
+int launch_energy_stats(const float* e, int64_t B, double* stats, cudaStream_t s);
+int launch_reduce_partials(const float* partials, int n_parts, int64_t n, float* out,
+                           cudaStream_t s);
+
+// ---- pure RBM (num_layers == 0) fast path (rbm.cu) ----
+bool rbm_fast_supported(const cgsvmc_ansatz* a);
+int rbm_log_amp(const cgsvmc_ansatz* a, const uint64_t* packed, int64_t B, float* out,
+                cudaStream_t s);
+int rbm_mc_steps(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int n_steps, uint64_t seed,
+                 uint64_t walker0, uint64_t step0, unsigned long long* accept_count,
+                 float* log_amp_out, cudaStream_t s);
+int rbm_mc_replay(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, const float* u_sites,
+                  const float* u_acc, int32_t* down, int32_t* up, float* log_ratio,
+                  uint8_t* accept, cudaStream_t s);
+int rbm_local_energy(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed,
+                     int64_t B, float* e_loc, float* log_amp_out, float* diag_out,
+                     float* off_out, cudaStream_t s);
+int rbm_grad(cgsvmc_ansatz* a, const uint64_t* packed, const float* weights, int64_t B, int K,
+             float* out, cudaStream_t s);
+
+// ---- generic tile networks: fc, rbm with hidden layers, conv (net.cu) ----
+int net_log_amp(const cgsvmc_ansatz* a, const uint64_t* packed, int64_t B, float* out,
+                cudaStream_t s);
+int net_mc_steps(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int n_steps, uint64_t seed,
+                 uint64_t walker0, uint64_t step0, unsigned long long* accept_count,
+                 float* log_amp_out, cudaStream_t s);
+int net_mc_replay(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, const float* u_sites,
+                  const float* u_acc, int32_t* down, int32_t* up, float* log_ratio,
+                  uint8_t* accept, cudaStream_t s);
+int net_local_energy(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed,
+                     int64_t B, float* e_loc, float* log_amp_out, float* diag_out,
+                     float* off_out, cudaStream_t s);
+int net_grad(cgsvmc_ansatz* a, const uint64_t* packed, const float* weights, int64_t B, int K,
+             float* out, cudaStream_t s);
+
+}  // namespace cgsvmc

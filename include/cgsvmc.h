@@ -1,0 +1,206 @@
+/*
+ * cgsvmc.h -- C-ABI of the B200-native variational-Monte-Carlo hot path.
+ *
+ * The reference (ClarkResearchGroup/cgs-vmc) has no FFI: its hot path is a
+ * pure-Python object protocol on top of TensorFlow 1.x ops.  Each entry point
+ * below replaces one group of those ops; the comment above it cites the
+ * reference interface it stands in for (paths relative to cgs_vmc/ in the
+ * reference tree).  INTEGRATION.md shows the ctypes binding a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *  - plain C: opaque handles, raw pointers, sizes.  No C++/torch types.
+ *  - every `*_dev` / unqualified data pointer is a DEVICE pointer borrowed for
+ *    the duration of the stream-ordered call; `*_host` pointers are host
+ *    memory read synchronously during the call.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ *    stream).  Calls enqueue work and return; they never synchronise.
+ *  - return value: CGSVMC_OK or a negative error code; the message is kept in
+ *    a thread-local string returned by cgsvmc_last_error().
+ *  - handles are not thread-safe: one handle per (device, host thread).
+ *
+ * Walker configuration layout ("packed"): W = ceil(N / 64) uint64 words per
+ * walker, row-major [B, W]; site i is bit (i & 63) of word (i >> 6);
+ * bit = 1 <=> spin +1, bit = 0 <=> spin -1; unused high bits are zero.
+ * cgsvmc_pack_configs / cgsvmc_unpack_configs convert from / to the
+ * reference's float32 [B, N] tensor of +-1 (graph_builders.py:92-125).
+ *
+ * Amplitudes: all entry points work with z(sigma) = log psi(sigma) + shift,
+ * i.e. the tensor the reference hands to add_exp_normalization + tf.exp
+ * (wavefunctions.py:206-232); psi = exp(z - exp_norm_shift) is formed by the
+ * host wrapper.  The in-scope ansaetze (output_activation = exp) are positive.
+ *
+ * Flat parameter layout (float32, row-major, Sonnet shapes):
+ *   fully_connected : W_1[in,out], b_1[out], ..., W_L, b_L, W_out[in,1], b_out[1]
+ *   rbm             : a[N], a0[1], (W_l, b_l) hidden layers ..., W[in,H], c[H]
+ *   conv_1d         : per layer w[k, cin, cout], b[cout]
+ *   conv_2d         : per layer w[k, k, cin, cout], b[cout]
+ */
+#ifndef CGSVMC_H_
+#define CGSVMC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGSVMC_VERSION 100 /* major * 10000 + minor * 100 + patch */
+
+#define CGSVMC_OK 0
+#define CGSVMC_ERR_INVALID (-1)     /* bad argument / shape mismatch */
+#define CGSVMC_ERR_CUDA (-2)        /* CUDA runtime error */
+#define CGSVMC_ERR_UNSUPPORTED (-3) /* valid request outside the built path */
+
+/* wavefunctions.WAVEFUNCTION_TYPES keys (wavefunctions.py:1199-1211) */
+#define CGSVMC_ANSATZ_FULLY_CONNECTED 1
+#define CGSVMC_ANSATZ_RBM 2
+#define CGSVMC_ANSATZ_CONV_1D 3
+#define CGSVMC_ANSATZ_CONV_2D 4
+
+/* layers.NONLINEARITIES keys (layers.py:13-21) */
+#define CGSVMC_ACT_RELU 0
+#define CGSVMC_ACT_TANH 1
+#define CGSVMC_ACT_SIGMOID 2
+#define CGSVMC_ACT_IDENTITY 3
+#define CGSVMC_ACT_COS 4
+#define CGSVMC_ACT_EXP 5
+#define CGSVMC_ACT_TAN 6
+
+typedef struct cgsvmc_ansatz cgsvmc_ansatz;
+typedef struct cgsvmc_ham cgsvmc_ham;
+
+/* Mirrors the hparams consumed by <Ansatz>.from_hparams
+ * (wavefunctions.py:373-388, 438-452, 512-528, 597-615). */
+typedef struct cgsvmc_ansatz_desc {
+  int32_t kind;         /* CGSVMC_ANSATZ_*                                   */
+  int32_t n_sites;      /* hparams.num_sites                                 */
+  int32_t num_layers;   /* num_fc_layers (fc, rbm) / num_conv_layers (conv)  */
+  int32_t layer_size;   /* fc_layer_size                                     */
+  int32_t num_filters;  /* num_conv_filters                                  */
+  int32_t kernel_size;  /* kernel_size                                       */
+  int32_t size_x;       /* conv_2d: hparams.size_x                           */
+  int32_t size_y;       /* conv_2d: hparams.size_y                           */
+  int32_t nonlinearity; /* CGSVMC_ACT_* for hidden activations               */
+} cgsvmc_ansatz_desc;
+
+int cgsvmc_version(void);
+const char* cgsvmc_last_error(void);
+
+/* ---- handles ---------------------------------------------------------- */
+
+/* Replaces wavefunctions.build_wavefunction / <Ansatz>.__init__
+ * (wavefunctions.py:1157-1196).  Unknown kind -> CGSVMC_ERR_INVALID (the
+ * reference raises ValueError, wavefunctions.py:1196). */
+int cgsvmc_ansatz_create(const cgsvmc_ansatz_desc* desc, cgsvmc_ansatz** out);
+int cgsvmc_ansatz_destroy(cgsvmc_ansatz* ansatz);
+/* Number of float32 parameters P of the flat layout above
+ * (len of get_trainable_variables flattened, wavefunctions.py:167-175). */
+int64_t cgsvmc_ansatz_num_params(const cgsvmc_ansatz* ansatz);
+/* Borrows a device buffer of P floats; it must stay valid until the next bind
+ * or destroy.  The library only reads it. */
+int cgsvmc_ansatz_bind_params(cgsvmc_ansatz* ansatz, const float* params_dev);
+
+/* Replaces HeisenbergHamiltonian.__init__ (operators.py:212-225), with one
+ * (j_x, j_z) per bond as in HeisenbergBond.__init__ (operators.py:131-135).
+ * ij_host: int32 [n_bonds, 2]; jx_host, jz_host: float32 [n_bonds]; bonds may
+ * repeat (list semantics). */
+int cgsvmc_ham_create(const int32_t* ij_host, const float* jx_host,
+                      const float* jz_host, int32_t n_bonds, int32_t n_sites,
+                      cgsvmc_ham** out);
+int cgsvmc_ham_destroy(cgsvmc_ham* ham);
+
+/* ---- walker state ----------------------------------------------------- */
+
+/* float32 [B, N] of +-1 (graph_builders.get_configs variable,
+ * graph_builders.py:92-125) <-> packed uint64 [B, W]. */
+int cgsvmc_pack_configs(const float* configs, int64_t n_walkers,
+                        int32_t n_sites, uint64_t* packed, void* stream);
+int cgsvmc_unpack_configs(const uint64_t* packed, int64_t n_walkers,
+                          int32_t n_sites, float* configs, void* stream);
+/* Replaces utils.random_configurations (utils.py:169-192): uniformly random
+ * configurations with n_sites / 2 spins down, Philox keyed by
+ * (seed, walker_id0 + b). */
+int cgsvmc_random_configs(uint64_t* packed, int64_t n_walkers, int32_t n_sites,
+                          uint64_t seed, uint64_t walker_id0, void* stream);
+
+/* ---- amplitudes ------------------------------------------------------- */
+
+/* Replaces Wavefunction.__call__ / _build (wavefunctions.py:47-59, 355-371,
+ * 419-436, 495-510, 578-595): z[b] = log psi(sigma_b) + shift. */
+int cgsvmc_log_amp(const cgsvmc_ansatz* ansatz, const uint64_t* packed,
+                   int64_t n_walkers, float* log_amp, void* stream);
+
+/* ---- Metropolis sampler ----------------------------------------------- */
+
+/* Replaces n_steps consecutive session.run(mc_step) of
+ * graph_builders.build_monte_carlo_sampling (graph_builders.py:38-89;
+ * loops at training.py:608-609, 616-617, 208-210, evaluation.py:143-149):
+ * per walker and step, draw a uniformly random up site and a uniformly random
+ * down site, exchange them, accept iff |psi'/psi|^2 > u (strict).  Randomness
+ * is Philox4x32-10 with key = seed and counter = (step0 + s, walker_id0 + b),
+ * so trajectories do not depend on how walkers are sharded over devices.
+ * accept_count (uint64, device) is incremented by the number of accepted
+ * moves (acceptance_count, graph_builders.py:86); log_amp_out (nullable)
+ * receives z of the final configurations. */
+int cgsvmc_mc_steps(const cgsvmc_ansatz* ansatz, uint64_t* packed_inout,
+                    int64_t n_walkers, int32_t n_steps, uint64_t seed,
+                    uint64_t walker_id0, uint64_t step0,
+                    unsigned long long* accept_count, float* log_amp_out,
+                    void* stream);
+
+/* One step in REPLAY mode (tests): consumes caller-supplied uniforms exactly
+ * like graph_builders.py:59-79 -- u_sites float32 [B, N] (argmin / argmax of
+ * sigma * u with first-occurrence ties), u_acc float32 [B] (accept iff
+ * ratio > sqrt(u)).  Outputs (all nullable): down_site / up_site int32 [B],
+ * log_ratio float32 [B] = z' - z, accept_mask uint8 [B]. */
+int cgsvmc_mc_step_replay(const cgsvmc_ansatz* ansatz, uint64_t* packed_inout,
+                          int64_t n_walkers, const float* u_sites,
+                          const float* u_acc, int32_t* down_site,
+                          int32_t* up_site, float* log_ratio,
+                          uint8_t* accept_mask, void* stream);
+
+/* ---- Hamiltonian ------------------------------------------------------ */
+
+/* Parity hook for the integer part of HeisenbergBond.build
+ * (operators.py:154-167): flipped uint64 [B, n_bonds, W] = configuration with
+ * the bond's two spins exchanged, active_mask uint32 [B, ceil(n_bonds / 32)]
+ * with bit (k & 31) of word (k >> 5) set iff bond k is antiparallel. */
+int cgsvmc_flip_enum(const cgsvmc_ham* ham, const uint64_t* packed,
+                     int64_t n_walkers, uint64_t* flipped,
+                     uint32_t* active_mask, void* stream);
+
+/* Replaces HeisenbergHamiltonian.local_value (operators.py:249-259):
+ * e_loc[b] = sum_k jz_k/4 s_i s_j + jx_k/2 [s_i != s_j] psi(flip_k)/psi.
+ * Nullable extra outputs: log_amp_out[b] = z(sigma_b); diag_out[b] and
+ * offdiag_ratio_out[b] are the two terms of Operator.build
+ * (operators.py:227-247) with the off-diagonal one divided by psi, so that
+ * apply_in_place (operators.py:261-271) = (diag + offdiag_ratio) * psi. */
+int cgsvmc_local_energy(const cgsvmc_ansatz* ansatz, const cgsvmc_ham* ham,
+                        const uint64_t* packed, int64_t n_walkers,
+                        float* e_loc, float* log_amp_out, float* diag_out,
+                        float* offdiag_ratio_out, void* stream);
+
+/* ---- estimators ------------------------------------------------------- */
+
+/* Replaces the two tf.gradients + accumulators of
+ * EnergyGradientOptimizer.build_opt_ops (training.py:545-558) and the
+ * gradient of the SWO loss (training.py:169-175): for k < n_weights
+ *   out[k, :] += sum_b weights[k, b] * d z_b / d params      (flat layout)
+ * weights float32 [n_weights, B] (n_weights <= 4), out float32 [n_weights, P]
+ * ACCUMULATED into (zero it to start an epoch, training.py:568).  The
+ * reduction order is fixed (deterministic for a given B). */
+int cgsvmc_weighted_grad_sum(const cgsvmc_ansatz* ansatz,
+                             const uint64_t* packed, const float* weights,
+                             int64_t n_walkers, int32_t n_weights, float* out,
+                             void* stream);
+
+/* Replaces tf.metrics.mean(local_energy) bookkeeping (training.py:555):
+ * stats (double [4], device) += { sum e, sum e^2, B, 0 }. */
+int cgsvmc_energy_stats(const float* e_loc, int64_t n_walkers, double* stats,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGSVMC_H_ */
