@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the VMC hot path (BASELINE.json metric: walker-steps/sec and
+E_loc evals/sec), workload C2 = 6x6 Heisenberg, RBM (H = 144), 8192 walkers
+per GPU.
+
+A "step" is one batch iteration of EnergyGradientOptimizer.run_optimization_epoch
+(training.py:614-617): `accumulate_gradients` (local energy of every walker,
+the two gradient sums, energy statistics) followed by one Monte-Carlo sweep
+(num_monte_carlo_sweeps * num_sites = 36 Metropolis steps per walker).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints one JSON line (see DESIGN.md section "Measurement" for every field).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOAD = 'C2: 6x6 square-lattice Heisenberg (72 NN bonds, jx=-1, jz=1), rbm H=144, 8192 walkers/GPU'
+N_SITES, SIZE, HIDDEN, WALKERS = 36, 6, 144, 8192
+SWEEP_STEPS = N_SITES            # num_monte_carlo_sweeps (1) * num_sites
+SEED = 0xC65
+L2_FLUSH_BYTES = 256 << 20
+
+
+def parse_args():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=200)
+  ap.add_argument('--warmup', type=int, default=20)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--walkers', type=int, default=WALKERS, help='walkers per GPU')
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  return ap.parse_args()
+
+
+def peaks():
+  path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    p = json.load(open(path))
+    return dict(hbm_gbs=p['hbm_gbs'], sm_max_mhz=p.get('sm_max_mhz', 1965.0), source='measured')
+  return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source='fallback')
+
+
+def problem():
+  """Synthetic inputs of SURVEY.md 8(d): Sonnet-default weights (seed 1234),
+  NN bonds with (jx, jz) = (-1, 1)."""
+  from oracle import ansatz as oansatz
+  from oracle import lattices
+  spec = oansatz.AnsatzSpec('rbm', N_SITES, num_layers=0, layer_size=HIDDEN,
+                            size_x=SIZE, size_y=SIZE)
+  flat = oansatz.flatten(oansatz.init_params(spec, seed=1234)).float()
+  ij, jx, jz = lattices.heisenberg_couplings(lattices.square_nn_bonds(SIZE), -1.0, 1.0)
+  return spec, flat, ij, jx, jz
+
+
+# ----------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------
+class ClockSampler:
+  """Samples SM clock and throttle reasons through NVML from a background
+  thread while the timed region runs (the region lasts milliseconds, far below
+  nvidia-smi's own start-up time, so the CLI loop of the profiling recipe
+  cannot be used here; the NVML fields are the same ones it prints)."""
+
+  def __init__(self, index, period_s=0.002):
+    import threading
+    self.samples, self.max_mhz, self.reasons = [], None, set()
+    self._stop = threading.Event()
+    self._thread = None
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self._nv = pynvml
+      self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+    except Exception:   # NVML unavailable: report nulls
+      self._nv = None
+      return
+    self._period = period_s
+    self._thread = threading.Thread(target=self._run, daemon=True)
+    self._thread.start()
+
+  def _run(self):
+    nv = self._nv
+    names = {
+        'hw_slowdown': nv.nvmlClocksThrottleReasonHwSlowdown,
+        'hw_thermal_slowdown': nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+        'sw_thermal_slowdown': nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+        'sw_power_cap': nv.nvmlClocksThrottleReasonSwPowerCap,
+    }
+    while not self._stop.is_set():
+      try:
+        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for k, bit in names.items():
+          if mask & bit:
+            self.reasons.add(k)
+      except Exception:
+        pass
+      self._stop.wait(self._period)
+
+  def stop(self):
+    if self._thread is not None:
+      self._stop.set()
+      self._thread.join(timeout=2)
+    sm = float(np.median(self.samples)) if self.samples else None
+    return dict(sm_mhz=sm, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                samples=len(self.samples))
+
+
+# ----------------------------------------------------------------------------
+# CPU arm: the reference-equivalent op sequence on the host cores
+# ----------------------------------------------------------------------------
+def cpu_arm(walkers, steps, warmup):
+  from oracle import bits, cpu_baseline
+  spec, flat, ij, jx, jz = problem()
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  cfg = bits.random_sz0_configs(N_SITES, walkers, np.random.default_rng(1234))
+  vmc = cpu_baseline.ReferenceEquivalentVMC(spec, flat, ij, jx, jz, cfg, seed=SEED)
+  times = cpu_baseline.time_steps(vmc, SWEEP_STEPS, steps, warmup)
+  t = float(np.mean(times))
+  return dict(walker_steps_per_sec=walkers * SWEEP_STEPS / t, eloc_evals_per_sec=walkers / t,
+              ms_per_step=t * 1e3, cores=cores, walkers=walkers, steps=steps)
+
+
+def run_reference(args, rank):
+  """--impl reference: the reference's CPU implementation of the same step.
+  TensorFlow 1.x / Sonnet v1 are not installable in this image, so this is
+  the op-for-op torch-CPU restatement (oracle/cpu_baseline.py, kind "port").
+  Under torchrun only rank 0 works."""
+  if rank != 0:
+    return
+  r = cpu_arm(args.walkers, args.steps, args.warmup)
+  line = {
+      'impl': 'reference', 'metric': 'walker_steps_per_sec', 'value': r['walker_steps_per_sec'],
+      'unit': 'walker-steps/s', 'eloc_evals_per_sec': r['eloc_evals_per_sec'],
+      'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': WORKLOAD, 'walkers_per_gpu': args.walkers,
+                 'mc_steps_per_step': SWEEP_STEPS, 'n_bonds': 72},
+      'cpu_baseline': {'value': r['walker_steps_per_sec'], 'unit': 'walker-steps/s',
+                       'cores': r['cores'], 'kind': 'port',
+                       'sample': '%d full steps of the same workload (%d walkers) on the host, '
+                                 'torch-CPU float32 restatement of the TF graph' % (args.steps, args.walkers)},
+      'e2e': {'value': r['walker_steps_per_sec'], 'unit': 'walker-steps/s',
+              'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+  }
+  print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+  import torch.distributed as dist
+  from cgs_vmc_b200 import _native, engine
+  _native.require_cuda()
+  torch.cuda.set_device(local_rank)
+  dev = torch.device('cuda', local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  spec, flat, ij, jx, jz = problem()
+  B = args.walkers
+  ansatz = _native.Ansatz('rbm', N_SITES, num_layers=0, layer_size=HIDDEN, device=dev)
+  ansatz.set_params(flat)
+  ham = _native.Hamiltonian(ij, jx, jz, N_SITES, device=dev)
+  state = engine.WalkerState(B, N_SITES, seed=SEED, walker_id0=rank * B, device=dev)
+  sums = engine.EnergyGradientSums(ansatz, B, device=dev)
+  P = ansatz.num_params
+  payload = torch.zeros(2 * P + 4, dtype=torch.float32, device=dev)   # all-reduce buffer
+  flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+  state.mc_steps(ansatz, 20 * N_SITES)                                 # equilibrate
+
+  launches = [0]
+  ev = lambda: torch.cuda.Event(enable_timing=True)
+
+  def step(events=None):
+    """accumulate_gradients + one sweep (+ the packed all-reduce when sharded)."""
+    if events: events[0].record()
+    lib = _native.load()
+    e_row = sums.weights[1]
+    _native.check(lib.cgsvmc_local_energy(
+        ansatz._handle, ham._handle, _native._ptr(state.packed), B, _native._ptr(e_row),
+        _native._ptr(sums.log_amp), None, None, _native._stream()))
+    if events: events[1].record()
+    ansatz.weighted_grad_sum(state.packed, sums.weights, out=sums.sums)
+    _native.energy_stats(e_row, sums.stats)
+    if events: events[2].record()
+    state.mc_steps(ansatz, SWEEP_STEPS)
+    if events: events[3].record()
+    launches[0] += 5   # local_energy, grad, reduce_partials, energy_stats, mc
+    if world > 1:
+      payload[:2 * P].copy_(sums.sums.reshape(-1))
+      payload[2 * P:].copy_(sums.stats.float())
+      dist.all_reduce(payload)
+
+  for _ in range(max(args.warmup, 3)):
+    step()
+    flush.zero_()
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+
+  # ---- timed region: K steps, device-resident inputs -----------------------
+  clock = ClockSampler(local_rank) if rank == 0 else None
+  launches[0] = 0
+  marks = [[ev() for _ in range(5)] for _ in range(args.steps)]
+  torch.cuda.synchronize()
+  wall0 = time.perf_counter()
+  for k in range(args.steps):
+    step(marks[k])
+    marks[k][4].record()
+    flush.zero_()                      # L2 flush, outside the per-step event pair
+  torch.cuda.synchronize()
+  wall = time.perf_counter() - wall0
+  if world > 1:
+    dist.barrier()
+  clocks = clock.stop() if clock else None
+  n_launch = launches[0]
+  t_step = np.array([m[0].elapsed_time(m[4]) for m in marks]) * 1e-3
+  t_eloc = np.array([m[0].elapsed_time(m[1]) for m in marks]) * 1e-3
+  t_grad = np.array([m[1].elapsed_time(m[2]) for m in marks]) * 1e-3
+  t_mc = np.array([m[2].elapsed_time(m[3]) for m in marks]) * 1e-3
+  total = torch.tensor([t_step.sum()], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(total, op=dist.ReduceOp.MAX)
+  total_s = float(total.item())
+
+  # ---- e2e: the same step through host buffers -----------------------------
+  host_cfg = torch.empty(B, N_SITES, dtype=torch.float32).pin_memory()
+  host_cfg.copy_(state.configs().cpu())
+  host_stats = torch.empty(4, dtype=torch.float64).pin_memory()
+  dev_cfg = torch.empty(B, N_SITES, dtype=torch.float32, device=dev)
+
+  def e2e_step():
+    dev_cfg.copy_(host_cfg, non_blocking=True)                    # H2D inputs
+    state.packed = _native.pack_configs(dev_cfg)
+    step()
+    _native.unpack_configs(state.packed, N_SITES, out=dev_cfg)
+    host_cfg.copy_(dev_cfg, non_blocking=True)                    # D2H state
+    host_stats.copy_(sums.stats, non_blocking=True)               # D2H result
+    torch.cuda.current_stream().synchronize()
+
+  for _ in range(3):
+    e2e_step()
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  e0, e1 = ev(), ev()
+  e0.record()
+  for _ in range(args.steps):
+    e2e_step()
+  e1.record()
+  torch.cuda.synchronize()
+  e2e_total = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
+  e2e_s = float(e2e_total.item())
+
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+
+  # ---- bookkeeping ----------------------------------------------------------
+  pk = peaks()
+  n_act = float(np.mean(__import__('oracle').hamiltonian.n_active(
+      state.configs().cpu().numpy(), ij)))
+  walkers_total = B * world
+  value = walkers_total * SWEEP_STEPS * args.steps / total_s
+  eloc_rate = walkers_total * args.steps / total_s
+  # dominant kernel = the one with the largest share of the step
+  shares = {'rbm_local_energy_kernel': float(t_eloc.mean()),
+            'rbm_mc_kernel': float(t_mc.mean()), 'rbm_grad_kernel+reduce+stats': float(t_grad.mean())}
+  dominant = max(('rbm_local_energy_kernel', 'rbm_mc_kernel'), key=lambda k: shares[k])
+  H = HIDDEN
+  f_inc_flop, f_inc_mufu = 4 * H + 4, 2 * H
+  f_fwd = 2 * N_SITES * H + 2 * N_SITES + 6 * H               # 10,440 + lncosh arithmetic
+  if dominant == 'rbm_mc_kernel':
+    units = B * SWEEP_STEPS
+    flop = units * f_inc_flop + B * f_fwd
+    mufu = units * f_inc_mufu + B * 2 * H
+    bytes_alg = B * (2 * 8 + 8)
+    t_k = float(t_mc.mean())
+  else:
+    flop = B * (f_fwd + n_act * f_inc_flop)
+    mufu = B * (2 * H + n_act * f_inc_mufu)
+    bytes_alg = B * (8 + 8)
+    t_k = float(t_eloc.mean())
+  f_hz = pk['sm_max_mhz'] * 1e6
+  fp32_peak = 148 * 128 * 2 * f_hz / 1e12                      # TFLOP/s, derived
+  mufu_peak = 148 * 16 * f_hz / 1e12                           # T transcendental/s, derived
+  roofline = {
+      'kernel': dominant, 'bound': 'mufu',
+      'achieved': mufu / t_k / 1e12, 'peak': mufu_peak, 'unit': 'Ttranscendental/s',
+      'frac': mufu / t_k / 1e12 / mufu_peak, 'traffic': None,
+      'peak_source': 'derived: 148 SM x 16 MUFU/clk x sm_max_mhz (%s); state is SM-resident '
+                     'so neither HBM nor the tensor pipe bounds this kernel (SURVEY.md 8(d))' % pk['source'],
+      'fp32': {'achieved': flop / t_k / 1e12, 'peak': fp32_peak, 'unit': 'TFLOP/s',
+               'frac': flop / t_k / 1e12 / fp32_peak},
+      'hbm': {'achieved': bytes_alg / t_k / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+              'frac': bytes_alg / t_k / 1e9 / pk['hbm_gbs'], 'peak_source': pk['source']},
+      'kernel_ms': t_k * 1e3, 'n_active_bonds_mean': n_act,
+  }
+  line = {
+      'metric': 'walker_steps_per_sec', 'value': value, 'unit': 'walker-steps/s',
+      'eloc_evals_per_sec': eloc_rate,
+      'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+      'ms_per_step': total_s / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': WORKLOAD, 'walkers_per_gpu': B, 'mc_steps_per_step': SWEEP_STEPS,
+                 'n_bonds': 72, 'n_params': P,
+                 'l2': 'flushed: %d MiB memset between steps, outside the per-step CUDA-event pairs' % (L2_FLUSH_BYTES >> 20),
+                 'parallelism': 'walkers sharded, params replicated' + (
+                     ', all-reduce of [2P+4] floats per step' if world > 1 else '')},
+      'kernel_ms': {k: v * 1e3 for k, v in shares.items()},
+      'kernel_rates': {'sampler_walker_steps_per_sec': B * SWEEP_STEPS / float(t_mc.mean()),
+                       'eloc_evals_per_sec': B / float(t_eloc.mean())},
+      'roofline': roofline,
+      'e2e': {'value': walkers_total * SWEEP_STEPS * args.steps / e2e_s, 'unit': 'walker-steps/s',
+              'eloc_evals_per_sec': walkers_total * args.steps / e2e_s,
+              'ms_per_step': e2e_s / args.steps * 1e3,
+              'h2d_bytes_per_step': B * N_SITES * 4, 'd2h_bytes_per_step': B * N_SITES * 4 + 32},
+      'gpu_launches': n_launch,
+      'clocks': clocks,
+      'wall_s_timed_region': wall,
+  }
+  if world == 1 and not args.no_cpu_baseline:
+    c = cpu_arm(B, 3, 1)
+    line['cpu_baseline'] = {
+        'value': c['walker_steps_per_sec'], 'unit': 'walker-steps/s',
+        'eloc_evals_per_sec': c['eloc_evals_per_sec'], 'cores': c['cores'], 'kind': 'port',
+        'ms_per_step': c['ms_per_step'],
+        'sample': '3 full steps (after 1 warm-up) of the same workload at the full %d walkers: '
+                  'reference-equivalent torch-CPU float32 op sequence (TF1 not installable)' % B}
+  print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  args = parse_args()
+  rank = int(os.environ.get('RANK', '0'))
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if args.impl == 'reference':
+    run_reference(args, rank)
+  else:
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+  main()

@@ -1,0 +1,90 @@
+"""Device-resident state of one walker shard and the per-batch estimator pass.
+
+This is the host-side glue under the reference-shaped API (graph_builders,
+operators, training): it owns the torch buffers and calls the C-ABI.  Nothing
+here computes on the CPU.
+"""
+import torch
+
+from . import _native
+
+
+class WalkerState:
+  """The `configs` variable of graph_builders.get_configs
+  (graph_builders.py:92-125), kept bit-packed on the device, plus the Philox
+  stream position.  `walker_id0` is the global id of the first walker of this
+  shard, so trajectories do not depend on the sharding."""
+
+  def __init__(self, batch_size, n_sites, seed=0xC65, walker_id0=0, device='cuda',
+               packed=None):
+    self.batch_size, self.n_sites = batch_size, n_sites
+    self.seed, self.walker_id0 = int(seed), int(walker_id0)
+    self.step = 0
+    if packed is None:
+      packed = _native.random_configs(batch_size, n_sites, self.seed, self.walker_id0,
+                                      device=device)
+    self.packed = packed
+    self.accept_count = torch.zeros(1, dtype=torch.int64, device=packed.device)
+    self.proposed = 0
+
+  def configs(self):
+    """float32 [B, N] of +-1: the reference's view of the state."""
+    return _native.unpack_configs(self.packed, self.n_sites)
+
+  def set_configs(self, configs):
+    if tuple(configs.shape) != (self.batch_size, self.n_sites):
+      raise ValueError('Size of existing variable does not match.')   # graph_builders.py:118
+    self.packed = _native.pack_configs(configs.to(self.packed.device, torch.float32).contiguous())
+
+  def mc_steps(self, ansatz, n_steps, log_amp_out=None):
+    """n_steps x session.run(mc_step) (graph_builders.py:38-89) in one launch."""
+    ansatz.mc_steps(self.packed, n_steps, self.seed, self.walker_id0, self.step,
+                    self.accept_count, log_amp_out)
+    self.step += int(n_steps)
+    self.proposed += int(n_steps) * self.batch_size
+
+
+class EnergyGradientSums:
+  """The local-variable accumulators of training.py:550-568 as one packed
+  float buffer [2, P] (sum_b O_b | sum_b E_b O_b) plus float64 energy
+  statistics [sum E, sum E^2, n, 0]; this is also the all-reduce payload of
+  the walker-sharded run."""
+
+  def __init__(self, ansatz, batch_size, device='cuda'):
+    self.ansatz = ansatz
+    self.sums = torch.zeros(2, ansatz.num_params, dtype=torch.float32, device=device)
+    self.stats = torch.zeros(4, dtype=torch.float64, device=device)
+    self.weights = torch.ones(2, batch_size, dtype=torch.float32, device=device)
+    self.log_amp = torch.empty(batch_size, dtype=torch.float32, device=device)
+    self.n_batches = 0
+
+  def reset(self):
+    """session.run(reset_gradients), training.py:568."""
+    self.sums.zero_()
+    self.stats.zero_()
+    self.n_batches = 0
+
+  def accumulate(self, ham, packed):
+    """session.run(accumulate_gradients), training.py:539-558 for one batch:
+    E_loc (written straight into the weight row), then S = [sum O, sum E O]
+    and the energy statistics."""
+    lib = _native.load()
+    b = packed.shape[0]
+    e_row = self.weights[1]
+    _native.check(lib.cgsvmc_local_energy(
+        self.ansatz._handle, ham._handle, _native._ptr(packed), b, _native._ptr(e_row),
+        _native._ptr(self.log_amp), None, None, _native._stream()))
+    self.ansatz.weighted_grad_sum(packed, self.weights, out=self.sums)
+    _native.energy_stats(e_row, self.stats)
+    self.n_batches += 1
+    return e_row
+
+  def mean_energy(self):
+    s = self.stats
+    return s[0] / s[2]
+
+  def gradient(self, n_batches=None):
+    """mean_batches(sum E O) - mean(E) * mean_batches(sum O), training.py:562-564
+    (B times the covariance: tf.gradients sums over the batch)."""
+    nb = float(self.n_batches if n_batches is None else n_batches)
+    return self.sums[1] / nb - self.mean_energy().float() * self.sums[0] / nb
