@@ -126,14 +126,27 @@ __global__ void energy_stats_kernel(const float* __restrict__ e, int64_t B, doub
   }
 }
 
-// out[n] += sum_p partials[p][n]   (fixed order => deterministic)
+// out[n] += sum_p partials[p][n]   (fixed order => deterministic).  A block
+// reduces 32 consecutive outputs; its 8 warps each take every 8th partial
+// (coalesced 128-byte reads), then the 8 slices are added in a fixed order.
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_parts, int64_t n,
                                        float* __restrict__ out) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  __shared__ float sh[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t i0 = (int64_t)blockIdx.x * 32; i0 < n; i0 += (int64_t)gridDim.x * 32) {
+    const int64_t i = i0 + lane;
     float acc = 0.f;
-    for (int p = 0; p < n_parts; ++p) acc += partials[(int64_t)p * n + i];
-    out[i] += acc;
+    if (i < n)
+      for (int p = warp; p < n_parts; p += 8) acc += partials[(int64_t)p * n + i];
+    sh[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && i < n) {
+      float total = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) total += sh[w][lane];
+      out[i] += total;
+    }
+    __syncthreads();
   }
 }
 
@@ -182,7 +195,7 @@ int launch_energy_stats(const float* e, int64_t B, double* stats, cudaStream_t s
 
 int launch_reduce_partials(const float* partials, int n_parts, int64_t n, float* out,
                            cudaStream_t s) {
-  reduce_partials_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(partials, n_parts, n, out);
+  reduce_partials_kernel<<<blocks_for(n, 32), kThreads, 0, s>>>(partials, n_parts, n, out);
   return cuda_fail(cudaGetLastError(), "reduce_partials launch");
 }
 

@@ -1,0 +1,292 @@
+"""-m gpu parity tests of the generic tile networks (fully_connected, rbm with
+hidden layers, conv_1d, conv_2d) through the C-ABI, against the oracle and the
+golden vectors recorded from the reference."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import ansatz as oansatz
+from oracle import bits, estimators, hamiltonian, lattices, philox, sampler
+
+pytestmark = pytest.mark.gpu
+F64 = torch.float64
+
+NET_GOLDEN = ['fc_chain20', 'fc_chain8_small', 'rbm_chain12_hidden', 'conv1d_chain12_k3',
+              'conv1d_chain12_k4', 'conv2d_6x6_k3', 'conv2d_4x4_k2', 'conv2d_4x6_k3',
+              'conv2d_10x10']
+
+NET_SHAPES = [
+    oansatz.AnsatzSpec('fully_connected', 20, num_layers=3, layer_size=80),          # C1
+    oansatz.AnsatzSpec('fully_connected', 36, num_layers=1, layer_size=200),
+    oansatz.AnsatzSpec('fully_connected', 70, num_layers=2, layer_size=33, nonlinearity='tanh'),
+    oansatz.AnsatzSpec('fully_connected', 12, num_layers=0, layer_size=5),
+    oansatz.AnsatzSpec('rbm', 36, num_layers=2, layer_size=48),
+    oansatz.AnsatzSpec('rbm', 100, num_layers=1, layer_size=130, nonlinearity='sigmoid'),
+    oansatz.AnsatzSpec('conv_2d', 100, num_layers=5, num_filters=16, kernel_size=5,
+                       size_x=10, size_y=10),                                         # C3
+    oansatz.AnsatzSpec('conv_2d', 36, num_layers=3, num_filters=8, kernel_size=3,
+                       size_x=6, size_y=6, nonlinearity='tanh'),
+    oansatz.AnsatzSpec('conv_2d', 256, num_layers=2, num_filters=16, kernel_size=4,
+                       size_x=16, size_y=16),
+    oansatz.AnsatzSpec('conv_2d', 24, num_layers=2, num_filters=5, kernel_size=2,
+                       size_x=4, size_y=6),
+    oansatz.AnsatzSpec('conv_1d', 20, num_layers=3, num_filters=6, kernel_size=5),
+    oansatz.AnsatzSpec('conv_1d', 70, num_layers=2, num_filters=16, kernel_size=6),
+]
+
+
+def _id(s):
+  return '%s_N%d_L%d' % (s.kind, s.n_sites, s.num_layers)
+
+
+@pytest.fixture(scope='module')
+def native():
+  from cgs_vmc_b200 import _native
+  _native.load()
+  return _native
+
+
+def _setup(spec, seed, batch, bias=0.1):
+  from gpu_util import make_native
+  params = oansatz.init_params(spec, seed=seed, bias_scale=bias, dtype=F64)
+  rng = np.random.default_rng(seed)
+  cfg = bits.random_sz0_configs(spec.n_sites, batch, rng)
+  return make_native(spec, oansatz.flatten(params).numpy()), params, cfg
+
+
+def _bonds(spec):
+  n = spec.n_sites
+  if spec.kind == 'conv_2d':
+    if spec.size_x == spec.size_y:
+      return lattices.j1j2_couplings(spec.size_x, 0.5)
+    return lattices.heisenberg_couplings(lattices.square_nn_bonds(spec.size_x, spec.size_y))
+  return lattices.heisenberg_couplings(lattices.chain_bonds(n), -1.0, 1.0)
+
+
+@pytest.mark.parametrize('name', NET_GOLDEN)
+def test_log_amp_golden(native, name):
+  """psi = exp(z - shift) against the reference's float32 output: rtol 5e-5
+  (two float32 evaluations of a deep network)."""
+  from gpu_util import make_native, packed_cuda
+  spec, g = load_golden(name)
+  a = make_native(spec, g['params_flat'])
+  z = a.log_amp(packed_cuda(g['configs'])).cpu().numpy().astype(np.float64)
+  np.testing.assert_allclose(np.exp(z - float(g['shift'])), g['psi'], rtol=5e-5)
+
+
+@pytest.mark.parametrize('spec', NET_SHAPES, ids=_id)
+@pytest.mark.parametrize('batch', [1, 77, 300])
+def test_log_amp_vs_oracle(native, spec, batch):
+  """|dz| <= 4e-6 * (sum of |terms| of the forward pass), float32 vs float64."""
+  from gpu_util import packed_cuda, amp_scale
+  if spec.n_sites > 200 and batch > 100:
+    batch = 100
+  a, params, cfg = _setup(spec, seed=spec.n_sites + batch, batch=batch)
+  z = a.log_amp(packed_cuda(cfg)).cpu().numpy()
+  cfg64 = torch.from_numpy(cfg).to(F64)
+  zo = oansatz.log_amp(spec, params, cfg64).numpy()
+  if spec.nonlinearity == 'relu':
+    tol = 4e-6 * amp_scale(spec, params, cfg64)
+  else:
+    tol = 2e-5 * (np.abs(zo) + spec.n_sites)
+  assert np.all(np.abs(z - zo) <= tol), (np.abs(z - zo).max(), tol.min())
+
+
+@pytest.mark.parametrize('name', NET_GOLDEN)
+def test_replay_step_golden(native, name):
+  """graph_builders.py:59-88 with the reference's uniforms: exact proposals,
+  accept mask and post-step configurations."""
+  from gpu_util import make_native, packed_cuda, unpack_np
+  spec, g = load_golden(name)
+  a = make_native(spec, g['params_flat'])
+  params = oansatz.unflatten(spec, torch.from_numpy(g['params_flat']).to(F64))
+  for s in range(g['mc_before'].shape[0]):
+    packed = packed_cuda(g['mc_before'][s])
+    down, up, log_ratio, accept = a.mc_step_replay(
+        packed, torch.from_numpy(g['mc_u_sites'][s]).cuda(),
+        torch.from_numpy(g['mc_u_acc'][s]).cuda())
+    _, o_acc, o_lr, o_down, o_up = sampler.mc_step(
+        torch.from_numpy(g['mc_before'][s]).to(F64),
+        torch.from_numpy(g['mc_u_sites'][s]).to(F64),
+        torch.from_numpy(g['mc_u_acc'][s]).to(F64),
+        lambda c: oansatz.log_amp(spec, params, c))
+    assert np.array_equal(down.cpu().numpy(), o_down.numpy())
+    assert np.array_equal(up.cpu().numpy(), o_up.numpy())
+    np.testing.assert_allclose(log_ratio.cpu().numpy(), o_lr.numpy(), atol=1e-4, rtol=1e-4)
+    near = np.abs(np.exp(o_lr.numpy()) - np.sqrt(g['mc_u_acc'][s])) < 1e-3 * np.exp(o_lr.numpy())
+    same = accept.cpu().numpy().astype(bool) == o_acc.numpy()
+    assert np.all(same | near)
+    if np.all(same):
+      assert np.array_equal(unpack_np(packed, spec.n_sites), g['mc_after'][s])
+      assert int(accept.sum()) == int(g['mc_accept_count'][s])
+
+
+@pytest.mark.parametrize('spec', [NET_SHAPES[0], NET_SHAPES[4], NET_SHAPES[7], NET_SHAPES[10]], ids=_id)
+def test_fast_sampler_matches_oracle_philox(native, spec):
+  """cgsvmc_mc_steps step by step against the numpy Philox proposal rule."""
+  from gpu_util import packed_cuda, unpack_np
+  a, params, cfg = _setup(spec, seed=9, batch=48)
+  seed, w0 = 0xC65, 500
+  fn = lambda c: oansatz.log_amp(spec, params, c)
+  cur = cfg.copy()
+  walker_ids = np.arange(cfg.shape[0], dtype=np.uint64) + np.uint64(w0)
+  mismatches = 0
+  for step in range(12):
+    packed = packed_cuda(cur)
+    count = torch.zeros(1, dtype=torch.int64, device='cuda')
+    a.mc_steps(packed, 1, seed, walker_id0=w0, step0=step, accept_count=count)
+    got = unpack_np(packed, spec.n_sites)
+    down, up, u = philox.fast_proposal(cur, seed, walker_ids, step)
+    prop = cur.copy()
+    rows = np.arange(cur.shape[0])
+    prop[rows, down] += 2
+    prop[rows, up] -= 2
+    t = torch.from_numpy
+    dl = (fn(t(prop).to(F64)) - fn(t(cur).to(F64))).numpy()
+    acc = np.exp(2 * dl) > u
+    exp = np.where(acc[:, None], prop, cur)
+    near = np.abs(np.exp(2 * dl) - u) < 1e-3 * np.exp(2 * dl)
+    row_same = np.all(got == exp, axis=1)
+    assert np.all(row_same | near)
+    other = np.where(acc[:, None], cur, prop)
+    assert np.all(row_same | np.all(got == other, axis=1))
+    mismatches += int((~row_same).sum())
+    assert int(count.item()) == int(np.all(got == prop, axis=1).sum())
+    cur = got
+  assert mismatches <= 2
+
+
+@pytest.mark.parametrize('spec', [NET_SHAPES[0], NET_SHAPES[6]], ids=_id)
+def test_multi_step_and_sharding_invariance(native, spec):
+  """One launch of n steps == n launches of one step == any sharding of the
+  walkers (Philox keyed by global walker id and step): bit-identical."""
+  from gpu_util import packed_cuda
+  batch = 96
+  a, params, cfg = _setup(spec, seed=21, batch=batch)
+  p_all = packed_cuda(cfg)
+  z_all = torch.empty(batch, dtype=torch.float32, device='cuda')
+  a.mc_steps(p_all, 10, 5, walker_id0=0, step0=0, log_amp_out=z_all)
+  p_steps = packed_cuda(cfg)
+  for s in range(0, 10, 5):
+    a.mc_steps(p_steps, 5, 5, walker_id0=0, step0=s)
+  assert torch.equal(p_all, p_steps)
+  shards = []
+  for lo in range(0, batch, 32):
+    p = packed_cuda(cfg[lo:lo + 32])
+    a.mc_steps(p, 10, 5, walker_id0=lo, step0=0)
+    shards.append(p)
+  assert torch.equal(p_all, torch.cat(shards))
+  # cached log-amplitude returned by the sampler == fresh forward pass
+  assert torch.equal(z_all, a.log_amp(p_all))
+  cfg_after = bits.unpack(p_all.cpu().numpy().view(np.uint64), spec.n_sites)
+  assert np.all(cfg_after.sum(axis=1) == 0)
+
+
+@pytest.mark.parametrize('name', NET_GOLDEN)
+def test_local_energy_golden(native, name):
+  """operators.py:227-271 against the reference's recorded diag / E_loc /
+  apply_in_place (float32 both sides): 1e-4 of the sum of |terms|."""
+  from gpu_util import make_native, packed_cuda
+  spec, g = load_golden(name)
+  a = make_native(spec, g['params_flat'])
+  ham = native.Hamiltonian(g['bonds_ij'], g['bonds_jx'], g['bonds_jz'], spec.n_sites)
+  e, z, diag, off = a.local_energy(ham, packed_cuda(g['configs']), want_parts=True)
+  scale = np.abs(g['bond_offdiag']).sum(axis=1) / g['psi'] + np.abs(g['ham_diag']) + 1
+  assert np.all(np.abs(e.cpu().numpy() - g['local_energy']) <= 1e-4 * scale)
+  np.testing.assert_allclose(diag.cpu().numpy(), g['ham_diag'], atol=1e-5)
+  psi = np.exp(z.cpu().numpy().astype(np.float64) - float(g['shift']))
+  assert np.all(np.abs(e.cpu().numpy() * psi - g['apply_in_place']) <= 2e-4 * scale * g['psi'])
+
+
+@pytest.mark.parametrize('spec', NET_SHAPES, ids=_id)
+def test_local_energy_vs_oracle(native, spec):
+  """|dE| <= 5e-5 * (|diag| + sum_k |jx_k / 2| ratio_k)."""
+  from gpu_util import packed_cuda
+  batch = 19 if spec.n_sites > 64 else 45
+  a, params, cfg = _setup(spec, seed=13, batch=batch)
+  ij, jx, jz = _bonds(spec)
+  ham = native.Hamiltonian(ij, jx, jz, spec.n_sites)
+  e, z, diag, off = a.local_energy(ham, packed_cuda(cfg), want_parts=True)
+  cfg64 = torch.from_numpy(cfg).to(F64)
+  fn = lambda c: oansatz.log_amp(spec, params, c)
+  eo = hamiltonian.local_energy(cfg64, ij, jx, jz, fn).numpy()
+  eabs = hamiltonian.local_energy(cfg64, ij, np.abs(jx), np.abs(jz), fn).numpy()
+  scale = np.abs(eabs) + 0.5 * np.abs(jz).sum() + 1.0
+  err = np.abs(e.cpu().numpy() - eo)
+  assert np.all(err <= 5e-5 * scale), (err.max(), scale.min())
+  np.testing.assert_allclose((diag + off).cpu().numpy(), e.cpu().numpy(), atol=1e-5, rtol=1e-6)
+  zo = fn(cfg64).numpy()
+  assert np.all(np.abs(z.cpu().numpy() - zo) <= 2e-4 + 2e-5 * np.abs(zo))
+
+
+def test_local_energy_ragged_batches(native):
+  """Batch sizes around the CTA walker-group size (8) and repeated bonds."""
+  from gpu_util import packed_cuda
+  spec = NET_SHAPES[0]
+  a, params, cfg = _setup(spec, seed=2, batch=23)
+  ij, jx, jz = lattices.heisenberg_couplings(lattices.chain_bonds(20) * 2, -1.0, 1.0)
+  ham = native.Hamiltonian(ij, jx, jz, 20)
+  full, _ = a.local_energy(ham, packed_cuda(cfg))
+  for b in (1, 7, 8, 9, 16, 23):
+    e, _ = a.local_energy(ham, packed_cuda(cfg[:b]))
+    assert torch.equal(e, full[:b])
+  # doubled bond list == twice the single list (list semantics, operators.py:222-223)
+  ij1, jx1, jz1 = lattices.heisenberg_couplings(lattices.chain_bonds(20), -1.0, 1.0)
+  e1, _ = a.local_energy(native.Hamiltonian(ij1, jx1, jz1, 20), packed_cuda(cfg))
+  np.testing.assert_allclose(full.cpu().numpy(), 2 * e1.cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('spec', NET_SHAPES, ids=_id)
+def test_weighted_grad_sum_vs_oracle(native, spec):
+  """S_k = sum_b w_kb O_b against float64 autograd; per entry
+  |dS| <= 3e-5 * sum_b |w_kb| |O_b|-bound (float32 forward + backward)."""
+  from gpu_util import packed_cuda
+  batch = 70 if spec.n_sites <= 100 else 21
+  a, params, cfg = _setup(spec, seed=17, batch=batch)
+  rng = np.random.default_rng(3)
+  w = rng.normal(size=(2, batch)).astype(np.float32)
+  w[0] = 1.0
+  out = a.weighted_grad_sum(packed_cuda(cfg), torch.from_numpy(w).cuda()).cpu().numpy()
+  cfg64 = torch.from_numpy(cfg).to(F64)
+  ref = estimators.weighted_grad_sum(spec, params, cfg64, torch.from_numpy(w).to(F64)).numpy()
+  for k in range(2):
+    scale = np.abs(ref[k]).max() + 1e-3
+    err = np.abs(out[k] - ref[k])
+    assert err.max() <= 1e-4 * scale + 1e-4, (k, err.max(), scale)
+    assert np.linalg.norm(out[k] - ref[k]) <= 3e-5 * np.linalg.norm(ref[k]) + 1e-4
+  # single column and accumulate-into semantics
+  one = a.weighted_grad_sum(packed_cuda(cfg), torch.from_numpy(w[1:2].copy()).cuda())
+  np.testing.assert_allclose(one[0].cpu().numpy(), out[1], rtol=1e-5, atol=1e-5)
+  twice = a.weighted_grad_sum(packed_cuda(cfg), torch.from_numpy(w[1:2].copy()).cuda(), out=one.clone())
+  np.testing.assert_allclose(twice[0].cpu().numpy(), 2 * out[1], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('name', [n for n in NET_GOLDEN if n != 'conv2d_10x10'])
+def test_energy_gradient_and_swo_golden(native, name):
+  """training.py:539-564 (one batch) and 166-175 through K3 + K4 + K5 against
+  the gradients the reference's own graph code produced."""
+  from gpu_util import make_native, packed_cuda
+  spec, g = load_golden(name)
+  a = make_native(spec, g['params_flat'])
+  if 'eg_gradient' in g:
+    ham = native.Hamiltonian(g['bonds_ij'], g['bonds_jx'], g['bonds_jz'], spec.n_sites)
+    packed = packed_cuda(g['eg_configs'])
+    e, _ = a.local_energy(ham, packed)
+    s = a.weighted_grad_sum(packed, torch.stack([torch.ones_like(e), e]))
+    stats = native.energy_stats(e).cpu().numpy()
+    mean_e = stats[0] / stats[2]
+    assert abs(mean_e - float(g['eg_mean_energy'])) < 5e-5 * (1 + abs(mean_e))
+    grad = (s[1] - mean_e * s[0]).cpu().numpy()
+    ref = g['eg_gradient']
+    assert np.linalg.norm(grad - ref) <= 5e-4 * np.linalg.norm(ref) + 1e-4
+  target = make_native(spec, g['swo_target_params_flat'])
+  packed = packed_cuda(g['swo_configs'])
+  psi = torch.exp(a.log_amp(packed).double() - float(g['shift']))
+  t = torch.exp(target.log_amp(packed).double() - float(g['swo_target_shift'])) * (2.0 ** (spec.n_sites / 2))
+  loss = torch.mean((psi - t) ** 2 / psi ** 2)
+  assert abs(loss.item() - float(g['swo_loss'])) <= 5e-4 * abs(loss.item()) + 1e-6
+  w = (2.0 * (1.0 - t / psi) / psi.numel()).float().reshape(1, -1).contiguous()
+  grad = a.weighted_grad_sum(packed, w)[0].cpu().numpy()
+  ref = g['swo_gradient']
+  assert np.linalg.norm(grad - ref) <= 1e-3 * np.linalg.norm(ref) + 1e-6
