@@ -1,0 +1,246 @@
+"""Mirror of the reference's training.py for the hot-path optimizers:
+EnergyGradientOptimizer (training.py:506-623) and
+SupervisedWavefunctionOptimizer (training.py:135-212), with the same
+TrainOps tuples, registries and epoch schedules.  The Metropolis loops of the
+reference (one session.run per step) collapse into one persistent-kernel
+launch per sweep group; `session.run(train_ops.mc_step)` still performs a
+single step for drop-in callers.
+"""
+import collections
+import math
+
+import torch
+
+from . import distributed, engine, graph_builders
+from .session import Op
+
+TrainOpsTraditional = collections.namedtuple('TrainingOpsTraditional', [
+    'accumulate_gradients', 'apply_gradients', 'reset_gradients', 'mc_step', 'acc_rate',
+    'metrics', 'epoch_increment', 'update_wf_norm'])
+TrainOpsSWO = collections.namedtuple('TrainingOpsSWO', [
+    'train_step', 'accumulate_gradients', 'apply_gradients', 'reset_gradients', 'mc_step',
+    'acc_rate', 'metrics', 'energy', 'update_supervisor', 'update_normalization',
+    'epoch_increment', 'update_wf_norm'])
+TrainOpsSupervised = collections.namedtuple('TrainingOpsSupervised', [
+    'accumulate_gradients', 'apply_gradients', 'reset_gradients', 'mc_step', 'acc_rate',
+    'metrics', 'epoch_increment', 'update_wf_norm'])
+
+
+def piecewise_constant(x, boundaries, values):
+  """tf.train.piecewise_constant: values[0] for x <= boundaries[0], ..."""
+  for b, v in zip(boundaries, values):
+    if x <= b:
+      return v
+  return values[len(boundaries)]
+
+
+class _Optimizer:
+  """Applies a gradient to the flat parameter buffer with the learning-rate
+  schedule of create_sgd_optimizer (training.py:84-91)."""
+
+  def __init__(self, hparams):
+    self._rates = list(hparams.learning_rates)
+    self._stops = list(hparams.learning_rate_stops)
+
+  def learning_rate(self):
+    return piecewise_constant(int(graph_builders.get_or_create_num_epochs()), self._stops, self._rates)
+
+
+class AdamOptimizer(_Optimizer):
+  """tf.train.AdamOptimizer(lr, beta2=hparams.beta2): beta1 = 0.9, eps = 1e-8,
+  theta -= lr * sqrt(1 - b2^t) / (1 - b1^t) * m / (sqrt(v) + eps)."""
+
+  def __init__(self, hparams):
+    super().__init__(hparams)
+    self.beta1, self.beta2, self.eps = 0.9, float(hparams.beta2), 1e-8
+    self.m = self.v = None
+    self.t = 0
+
+  def apply_gradients(self, params, grad):
+    if self.m is None:
+      self.m = torch.zeros_like(params)
+      self.v = torch.zeros_like(params)
+    self.t += 1
+    self.m.mul_(self.beta1).add_(grad, alpha=1 - self.beta1)
+    self.v.mul_(self.beta2).addcmul_(grad, grad, value=1 - self.beta2)
+    lr_t = self.learning_rate() * math.sqrt(1 - self.beta2 ** self.t) / (1 - self.beta1 ** self.t)
+    params.addcdiv_(self.m, self.v.sqrt().add_(self.eps), value=-lr_t)
+
+
+class GradientDescentOptimizer(_Optimizer):
+  def apply_gradients(self, params, grad):
+    params.add_(grad, alpha=-self.learning_rate())
+
+
+OPTIMIZERS = {      # training.py:76-81; rms_prop / momentum never worked there
+    'adam': AdamOptimizer,   # (beta2 is passed to every class, training.py:91)
+    'gradient': GradientDescentOptimizer,
+}
+
+
+def create_sgd_optimizer(hparams):
+  if hparams.optimizer not in OPTIMIZERS:
+    raise NotImplementedError('optimizer=%r: only adam (the one that works in the reference, '
+                              'SURVEY.md appendix B-5) and gradient are built' % hparams.optimizer)
+  return OPTIMIZERS[hparams.optimizer](hparams)
+
+
+def _epoch_increment():
+  def run():
+    graph_builders.get_or_create_num_epochs().add_(1)
+  return Op(run, 'epoch_increment')
+
+
+class WavefunctionOptimizer:
+  """Parent class for ground state optimizers (training.py:94-132)."""
+
+  def build_opt_ops(self, wavefunction, hamiltonian, hparams, shared_resources):
+    raise NotImplementedError
+
+  def run_optimization_epoch(self, train_ops, session, hparams, epoch_number=0):
+    raise NotImplementedError
+
+
+class EnergyGradientOptimizer(WavefunctionOptimizer):
+  """Energy-gradient optimisation, training.py:506-623."""
+
+  def build_opt_ops(self, wavefunction, hamiltonian, hparams, shared_resources):
+    n_sites = hparams.num_sites
+    local_batch, walker_id0 = distributed.shard(hparams.batch_size)
+    configs = graph_builders.get_configs(shared_resources, local_batch, n_sites,
+                                         walker_id0=walker_id0)
+    mc_step, acc_rate = graph_builders.get_monte_carlo_sampling(
+        shared_resources, configs, wavefunction)
+    ansatz = wavefunction.native(n_sites)
+    ham = hamiltonian.native(n_sites)
+    sums = engine.EnergyGradientSums(ansatz, local_batch)
+    optimizer = create_sgd_optimizer(hparams)
+    state = {'reduced': False}
+
+    def accumulate():                      # training.py:539-558, one batch
+      sums.accumulate(ham, configs.packed)
+
+    def reduce_once():
+      if not state['reduced']:
+        distributed.allreduce_sums(sums.sums, sums.stats)
+        state['reduced'] = True
+
+    def apply_gradients():                 # training.py:562-567
+      reduce_once()
+      optimizer.apply_gradients(ansatz.params, sums.gradient())
+
+    def metrics():                         # mean_energy, training.py:555, 582
+      reduce_once()
+      return float(sums.mean_energy().item())
+
+    def reset():                           # training.py:568
+      sums.reset()
+      state['reduced'] = False
+
+    self.sums = sums
+    return TrainOpsTraditional(
+        accumulate_gradients=Op(accumulate, 'accumulate_gradients'),
+        apply_gradients=Op(apply_gradients, 'apply_gradients'),
+        reset_gradients=Op(reset, 'reset_gradients'),
+        mc_step=mc_step, acc_rate=acc_rate,
+        metrics=Op(metrics, 'mean_energy'),
+        epoch_increment=_epoch_increment(),
+        update_wf_norm=wavefunction.update_norm(lambda: wavefunction(configs)))
+
+  def run_optimization_epoch(self, train_ops, session, hparams, epoch_number=0):
+    """training.py:589-623."""
+    session.run(train_ops.mc_step,
+                n_steps=hparams.num_equilibration_sweeps * hparams.num_sites)
+    if train_ops.update_wf_norm is not None:
+      session.run(train_ops.update_wf_norm)
+    session.run(train_ops.reset_gradients)
+    for _ in range(hparams.num_batches_per_epoch):
+      session.run(train_ops.accumulate_gradients)
+      session.run(train_ops.mc_step,
+                  n_steps=hparams.num_monte_carlo_sweeps * hparams.num_sites)
+    session.run(train_ops.apply_gradients)
+    energy = session.run(train_ops.metrics)
+    session.run(train_ops.reset_gradients)
+    session.run(train_ops.epoch_increment)
+    return energy
+
+
+class SupervisedWavefunctionOptimizer:
+  """SWO with |psi|^2 sampling and the adjusted L2 loss, training.py:135-212."""
+
+  def build_opt_ops(self, wavefunction, target_wavefunction, hparams, shared_resources):
+    n_sites = hparams.num_sites
+    local_batch, walker_id0 = distributed.shard(hparams.batch_size)
+    configs = graph_builders.get_configs(shared_resources, local_batch, n_sites,
+                                         walker_id0=walker_id0)
+    mc_step, acc_rate = graph_builders.get_monte_carlo_sampling(
+        shared_resources, configs, wavefunction)
+    ansatz = wavefunction.native(n_sites)
+    target = target_wavefunction.native(n_sites)
+    optimizer = create_sgd_optimizer(hparams)
+    grad = torch.zeros(1, ansatz.num_params, dtype=torch.float32, device=ansatz.params.device)
+    log_norm = 0.5 * n_sites * math.log(2.0)       # sqrt(2^N), training.py:170
+
+    def loss_and_weights():
+      # ratio = psi_target * sqrt(2^N) / psi, formed in the log domain
+      z = ansatz.log_amp(configs.packed) - wavefunction._exp_norm_shift
+      zt = target.log_amp(configs.packed) - target_wavefunction._exp_norm_shift
+      ratio = torch.exp(zt + log_norm - z)
+      total = float(hparams.batch_size)
+      loss = ((1.0 - ratio) ** 2).sum() / total        # mean (psi - t)^2 / sg(psi)^2
+      weights = (2.0 * (1.0 - ratio) / total).reshape(1, -1).contiguous()
+      return loss, weights
+
+    def train_step():                      # optimizer.minimize(loss), training.py:175
+      loss, weights = loss_and_weights()
+      grad.zero_()
+      ansatz.weighted_grad_sum(configs.packed, weights, out=grad)
+      distributed.allreduce_(grad)
+      optimizer.apply_gradients(ansatz.params, grad[0])
+      return loss
+
+    def metrics():
+      loss, _ = loss_and_weights()
+      return float(distributed.allreduce_(loss.clone()).item())
+
+    return TrainOpsSupervised(
+        accumulate_gradients=None, apply_gradients=Op(train_step, 'train_step'),
+        reset_gradients=None, mc_step=mc_step, acc_rate=acc_rate,
+        metrics=Op(metrics, 'loss'), update_wf_norm=None,
+        epoch_increment=_epoch_increment())
+
+  def run_optimization_epoch(self, train_ops, session, hparams, epoch_number):
+    """training.py:192-212."""
+    del epoch_number
+    for _ in range(hparams.num_batches_per_epoch):
+      session.run(train_ops.mc_step,
+                  n_steps=hparams.num_monte_carlo_sweeps * hparams.num_sites)
+      session.run(train_ops.apply_gradients)
+    session.run(train_ops.epoch_increment)
+
+
+def _not_built(name, why):
+  class _NotBuilt:
+    def __init__(self, *args, **kwargs):
+      raise NotImplementedError('%s: %s' % (name, why))
+  _NotBuilt.__name__ = name
+  return _NotBuilt
+
+
+GROUND_STATE_OPTIMIZERS = {     # training.py:913-917
+    'EnergyGradient': EnergyGradientOptimizer,
+    'LogOverlapITSWO': _not_built('LogOverlapImaginaryTimeSWO',
+                                  'next row after the hot path (SURVEY.md 8(f) rank 2)'),
+    'ITSWO': _not_built('ImaginaryTimeSWO',
+                        'raises AttributeError at graph build in the reference '
+                        '(hparams.time_evolution_befta, training.py:812)'),
+}
+
+SUPERVISED_OPTIMIZERS = {       # training.py:920-925
+    'SWO': SupervisedWavefunctionOptimizer,
+    'LogOverlapSWO': _not_built('LogOverlapSWO', 'next row (SURVEY.md 8(f) rank 2)'),
+    'DualSamplingSWO': _not_built('DualSamplingSWO', 'next row (SURVEY.md 8(f) rank 2)'),
+    'BasisIterSWO': _not_built('BasisIterationSWO',
+                               'calls the non-existent scipy.special.binomi in the reference '
+                               '(training.py:246)'),
+}

@@ -1,0 +1,213 @@
+"""-m gpu tests of the reference-shaped Python API (wavefunctions, operators,
+graph_builders, training, evaluation) and of the three drivers."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ansatz as oansatz
+from oracle import bits, ed, estimators, hamiltonian, lattices
+
+pytestmark = pytest.mark.gpu
+F64 = torch.float64
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(autouse=True)
+def _fresh_epoch_counter():
+  from cgs_vmc_b200 import graph_builders
+  graph_builders.reset_num_epochs()
+  yield
+
+
+def _oracle_view(wf, kind, hp):
+  """(spec, float64 params) of a built API wavefunction."""
+  if kind in ('fully_connected', 'rbm'):
+    spec = oansatz.AnsatzSpec(kind, hp.num_sites, num_layers=hp.num_fc_layers,
+                              layer_size=hp.fc_layer_size, nonlinearity=hp.nonlinearity)
+  else:
+    spec = oansatz.AnsatzSpec(kind, hp.num_sites, num_layers=hp.num_conv_layers,
+                              num_filters=hp.num_conv_filters, kernel_size=hp.kernel_size,
+                              size_x=hp.size_x, size_y=hp.size_y, nonlinearity=hp.nonlinearity)
+  params = [v.detach().cpu().to(F64) for v in wf.get_trainable_variables()]
+  assert [tuple(p.shape) for p in params] == [tuple(s) for _, s in oansatz.param_shapes(spec)]
+  return spec, params
+
+
+@pytest.mark.parametrize('kind,overrides', [
+    ('fully_connected', dict(num_sites=20)),
+    ('rbm', dict(num_sites=36, num_fc_layers=0, fc_layer_size=144)),
+    ('conv_1d', dict(num_sites=12, num_conv_layers=2, num_conv_filters=4, kernel_size=3)),
+    ('conv_2d', dict(num_sites=36, size_x=6, size_y=6, num_conv_layers=3, num_conv_filters=8, kernel_size=3)),
+])
+def test_wavefunction_and_operator_api(kind, overrides):
+  from cgs_vmc_b200 import operators, utils, wavefunctions
+  hp = utils.create_hparams(wavefunction_type=kind, **overrides)
+  wf = wavefunctions.build_wavefunction(hp).seed(3)
+  n = hp.num_sites
+  cfg = bits.random_sz0_configs(n, 40, np.random.default_rng(1))
+  inputs = torch.from_numpy(cfg).cuda()
+  psi = wf(inputs)                                           # Wavefunction.__call__
+  spec, params = _oracle_view(wf, kind, hp)
+  ref = oansatz.psi(spec, params, torch.from_numpy(cfg).to(F64), shift=-10.0)
+  np.testing.assert_allclose(psi.cpu().numpy(), ref.numpy(), rtol=1e-4)
+  with pytest.raises(ValueError):                            # wrong number of sites
+    wf(torch.ones(3, n + 1).cuda())
+  bonds = lattices.chain_bonds(n)
+  ham = operators.HeisenbergHamiltonian(bonds, -1.0, 1.0)
+  e = ham.local_value(wf, inputs)
+  eo = hamiltonian.local_energy(torch.from_numpy(cfg).to(F64), bonds, [-1.0] * n, [1.0] * n,
+                                lambda c: oansatz.log_amp(spec, params, c))
+  np.testing.assert_allclose(e.cpu().numpy(), eo.numpy(), rtol=2e-4, atol=2e-4)
+  diag, off = ham.build(wf, inputs)
+  aip = ham.apply_in_place(wf, inputs)
+  torch.testing.assert_close(diag * psi + off, aip, rtol=1e-4, atol=1e-30)
+  torch.testing.assert_close(diag + off / psi, e, rtol=1e-4, atol=1e-4)
+  # a Hamiltonian is the sum of its bonds (operators.py:241-247)
+  total = sum(operators.HeisenbergBond(b, -1.0, 1.0).local_value(wf, inputs) for b in bonds)
+  torch.testing.assert_close(total, e, rtol=1e-4, atol=1e-4)
+  with pytest.raises(NotImplementedError):
+    ham.apply(wf)
+
+
+def test_graph_builders_api():
+  from cgs_vmc_b200 import graph_builders, utils, wavefunctions
+  from cgs_vmc_b200.session import Session
+  shared = {}
+  configs = graph_builders.get_configs(shared, 64, 12)
+  assert graph_builders.get_configs(shared, 64, 12) is configs
+  with pytest.raises(ValueError, match='does not match'):    # graph_builders.py:117-118
+    graph_builders.get_configs(shared, 32, 12)
+  assert configs.value().shape == (64, 12)
+  assert torch.all(configs.value().sum(dim=1) == 0)
+  wf = wavefunctions.build_wavefunction(utils.create_hparams(
+      wavefunction_type='rbm', num_sites=12, num_fc_layers=0, fc_layer_size=8)).seed(1)
+  mc_step, acc = graph_builders.get_monte_carlo_sampling(shared, configs, wf)
+  assert graph_builders.get_monte_carlo_sampling(shared, configs, wf)[0] is mc_step
+  s = Session()
+  before = configs.value().clone()
+  s.run(mc_step)                                             # one step, like the reference
+  changed = (configs.value() != before).any(dim=1).sum().item()
+  assert changed == s.run(acc)                               # accepted moves of that step
+  assert 0 < changed <= 64
+  s.run(mc_step, n_steps=24)
+  assert torch.all(configs.value().sum(dim=1) == 0)
+  r = utils.random_configurations(12, 5, seed=3)
+  assert r.shape == (5, 12) and torch.all(r.sum(dim=1) == 0)
+
+
+def test_energy_gradient_accumulators_match_oracle():
+  """Two accumulate batches of EnergyGradientOptimizer against the oracle's
+  restatement of training.py:550-564 on the same configurations."""
+  from cgs_vmc_b200 import operators, training, utils, wavefunctions
+  from cgs_vmc_b200.session import Session
+  hp = utils.create_hparams(wavefunction_type='rbm', num_sites=16, size_x=4, size_y=4,
+                            num_fc_layers=0, fc_layer_size=24, batch_size=96)
+  wf = wavefunctions.build_wavefunction(hp).seed(11)
+  ij, jx, jz = lattices.j1j2_couplings(4, 0.5)
+  ham = operators.HeisenbergHamiltonian(ij.tolist(), jx, jz)       # per-bond couplings
+  opt = training.EnergyGradientOptimizer()
+  shared = {}
+  ops = opt.build_opt_ops(wavefunction=wf, hamiltonian=ham, hparams=hp, shared_resources=shared)
+  s = Session()
+  spec, params = _oracle_view(wf, 'rbm', hp)
+  acc = estimators.EnergyGradientAccumulator(oansatz.num_params(spec))
+  fn = lambda c: oansatz.log_amp(spec, params, c)
+  s.run(ops.reset_gradients)
+  from cgs_vmc_b200 import graph_builders
+  configs = shared[graph_builders.ResourceName.CONFIGS]
+  for _ in range(2):
+    cfg64 = configs.value().cpu().to(F64)
+    acc.accumulate(spec, params, cfg64, hamiltonian.local_energy(cfg64, ij, jx, jz, fn))
+    s.run(ops.accumulate_gradients)
+    s.run(ops.mc_step, n_steps=16)
+  assert abs(s.run(ops.metrics) - acc.mean_energy) < 1e-4
+  grad = opt.sums.gradient().cpu().numpy()
+  ref = acc.gradient().numpy()
+  assert np.linalg.norm(grad - ref) <= 5e-4 * np.linalg.norm(ref) + 1e-4
+
+
+def test_energy_gradient_training_reaches_ed_energy():
+  """run_optimization_epoch end to end on the 8-site chain: the variational
+  energy converges to within 2% of exact diagonalisation (-3.6511)."""
+  from cgs_vmc_b200 import operators, training, utils, wavefunctions
+  from cgs_vmc_b200.session import Session
+  hp = utils.create_hparams(wavefunction_type='rbm', num_sites=8, num_fc_layers=0, fc_layer_size=16,
+                            batch_size=1024, num_batches_per_epoch=4, num_equilibration_sweeps=5,
+                            learning_rates=[0.02, 0.005, 0.002, 0.001], learning_rate_stops=[60, 100, 140])
+  wf = wavefunctions.build_wavefunction(hp).seed(2)
+  ham = operators.HeisenbergHamiltonian(lattices.chain_bonds(8), -1.0, 1.0)
+  opt = training.GROUND_STATE_OPTIMIZERS['EnergyGradient']()
+  ops = opt.build_opt_ops(wavefunction=wf, hamiltonian=ham, hparams=hp, shared_resources={})
+  s = Session()
+  energies = [opt.run_optimization_epoch(ops, s, hp) for _ in range(120)]
+  e0, _, _ = ed.ground_state(8, *lattices.heisenberg_couplings(lattices.chain_bonds(8)))
+  assert energies[0] > np.mean(energies[-10:])
+  assert abs(np.mean(energies[-10:]) - e0) < 0.02 * abs(e0), (energies[0], energies[-10:], e0)
+  assert np.mean(energies[-10:]) > e0 - 0.05          # variational within MC noise
+
+
+def test_supervised_training_reduces_loss():
+  from cgs_vmc_b200 import training, utils, wavefunctions
+  from cgs_vmc_b200.session import Session
+  hp = utils.create_hparams(wavefunction_type='rbm', num_sites=16, num_fc_layers=0, fc_layer_size=12,
+                            batch_size=2048, num_batches_per_epoch=10, learning_rates=[0.01, 0.01, 0.01, 0.01])
+  target = wavefunctions.build_wavefunction(hp).seed(7)
+  trainee = wavefunctions.build_wavefunction(hp).seed(8)
+  target.native(16)
+  # scale so that psi_target * sqrt(2^N) is comparable to psi (SWO is not scale free)
+  target._exp_norm_shift += 0.5 * 16 * np.log(2.0)
+  opt = training.SUPERVISED_OPTIMIZERS['SWO']()
+  ops = opt.build_opt_ops(wavefunction=trainee, target_wavefunction=target, hparams=hp,
+                          shared_resources={})
+  s = Session()
+  first = s.run(ops.metrics)
+  for epoch in range(30):
+    opt.run_optimization_epoch(ops, s, hp, epoch)
+  last = s.run(ops.metrics)
+  assert last < 0.2 * first, (first, last)
+
+
+def test_monte_carlo_operator_evaluator():
+  from cgs_vmc_b200 import evaluation, operators, utils, wavefunctions
+  from cgs_vmc_b200.session import Session
+  hp = utils.create_hparams(wavefunction_type='fully_connected', num_sites=8, num_fc_layers=1,
+                            fc_layer_size=8, batch_size=256, num_equilibration_sweeps=3,
+                            num_evaluation_samples=5)
+  wf = wavefunctions.build_wavefunction(hp).seed(4)
+  ham = operators.HeisenbergHamiltonian(lattices.chain_bonds(8), -1.0, 1.0)
+  ev = evaluation.MonteCarloOperatorEvaluator()
+  ops = ev.build_eval_ops(wavefunction=wf, operator=ham, hparams=hp, shared_resources={})
+  values = ev.run_evaluation(ops, Session(), hp, epoch_num=0)
+  assert len(values) == 5 and all(-4.0 < v < 2.1 for v in values)
+
+
+def test_drivers_end_to_end(tmp_path):
+  """run_training -> run_energy_evaluation -> run_supervised_training."""
+  ckpt = str(tmp_path / 'gs')
+  env = dict(os.environ, PYTHONPATH=REPO)
+  common = 'batch_size=256,num_batches_per_epoch=3,num_equilibration_sweeps=2,fc_layer_size=8,num_fc_layers=0'
+  subprocess.run([sys.executable, os.path.join(REPO, 'run_training.py'), '--checkpoint_dir', ckpt,
+                  '--num_sites', '8', '--num_epochs', '3', '--wavefunction_type', 'rbm',
+                  '--heisenberg_jx', '-1.0', '--optimizer', 'EnergyGradient', '--hparams', common],
+                 check=True, env=env, timeout=300)
+  metrics = open(os.path.join(ckpt, 'metrics.txt')).read().split()
+  assert len(metrics) == 3 and all(np.isfinite(float(m)) for m in metrics)
+  assert os.path.exists(os.path.join(ckpt, 'model_prior_2_epochs.pt'))
+  assert os.path.exists(os.path.join(ckpt, 'hparams.pbtxt'))
+  out = subprocess.run([sys.executable, os.path.join(REPO, 'run_energy_evaluation.py'),
+                        '--checkpoint_dir', ckpt, '--heisenberg_jx', '-1.0',
+                        '--hparams', 'num_evaluation_samples=4'],
+                       check=True, env=env, timeout=300, capture_output=True, text=True)
+  assert 'Energy:' in out.stdout
+  swo = str(tmp_path / 'swo')
+  subprocess.run([sys.executable, os.path.join(REPO, 'run_supervised_training.py'),
+                  '--checkpoint_dir', swo, '--supervisor_dir', ckpt, '--num_epochs', '2',
+                  '--wavefunction_type', 'fully_connected',
+                  '--hparams', 'batch_size=128,num_batches_per_epoch=2,num_fc_layers=1,fc_layer_size=8'],
+                 check=True, env=env, timeout=300)
+  assert os.path.exists(os.path.join(swo, 'model_after_1_epochs.pt'))
+  assert len(open(os.path.join(swo, 'metrics.txt')).read().split()) == 2

@@ -1,0 +1,149 @@
+"""CPU tests of the host-side mirror: hyper-parameters, session shim,
+registries / error behaviour, sharding arithmetic and the packed all-reduce
+(world_size 2, gloo)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cgs_vmc_b200 import distributed, drivers, graph_builders, session, training, utils, wavefunctions
+
+
+def test_hparams_defaults_match_reference():
+  hp = utils.create_hparams()
+  # utils.py:87-148
+  assert (hp.num_sites, hp.num_fc_layers, hp.fc_layer_size) == (40, 3, 80)
+  assert (hp.num_conv_layers, hp.kernel_size, hp.num_conv_filters) == (5, 5, 16)
+  assert (hp.num_equilibration_sweeps, hp.num_monte_carlo_sweeps) == (100, 1)
+  assert (hp.batch_size, hp.num_batches_per_epoch, hp.num_epochs) == (200, 50, 500)
+  assert hp.learning_rates == [1e-3, 1e-4, 2e-5, 1e-5] and hp.learning_rate_stops == [300, 600, 1000]
+  assert (hp.optimizer, hp.beta2, hp.nonlinearity, hp.output_activation) == ('adam', 0.99, 'relu', 'exp')
+
+
+def test_hparams_parse_override_roundtrip(tmp_path):
+  hp = utils.create_hparams(num_sites=36, wavefunction_type='rbm')
+  hp.parse('batch_size=8192,fc_layer_size=144,num_fc_layers=0,learning_rates=[0.01,0.001],nonlinearity=tanh')
+  assert hp.batch_size == 8192 and hp.fc_layer_size == 144 and hp.num_fc_layers == 0
+  assert hp.learning_rates == [0.01, 0.001] and hp.nonlinearity == 'tanh'
+  with pytest.raises(KeyError):
+    hp.set_hparam('no_such_param', 1)
+  with pytest.raises(KeyError):
+    utils.create_hparams(bogus=3)
+  path = tmp_path / 'hparams.pbtxt'
+  utils.save_hparams(hp, str(path))
+  back = utils.load_hparams(str(path))
+  assert back.values() == hp.values()
+
+
+def test_piecewise_constant_boundaries():
+  # tf.train.piecewise_constant: boundaries are inclusive on the left value
+  f = lambda x: training.piecewise_constant(x, [300, 600, 1000], [1e-3, 1e-4, 2e-5, 1e-5])
+  assert (f(0), f(300), f(301), f(600), f(601), f(1000), f(1001)) == \
+      (1e-3, 1e-3, 1e-4, 1e-4, 2e-5, 2e-5, 1e-5)
+
+
+def test_session_runs_ops_and_lists():
+  s = session.Session()
+  calls = []
+  op = session.Op(lambda n_steps=1: calls.append(n_steps) or n_steps * 2, 'op')
+  assert s.run(op) == 2 and s.run(op, n_steps=5) == 10
+  assert s.run([op, None, torch.tensor(3.5)]) == [2, None, 3.5]
+  assert calls == [1, 5, 1]
+
+
+def test_registries_and_error_types():
+  assert set(wavefunctions.WAVEFUNCTION_TYPES) == {'fully_connected', 'rbm', 'conv_1d', 'conv_2d'}
+  assert set(training.GROUND_STATE_OPTIMIZERS) == {'EnergyGradient', 'LogOverlapITSWO', 'ITSWO'}
+  assert set(training.SUPERVISED_OPTIMIZERS) == {'SWO', 'LogOverlapSWO', 'DualSamplingSWO', 'BasisIterSWO'}
+  with pytest.raises(ValueError, match='not registered'):          # wavefunctions.py:1196
+    wavefunctions.build_wavefunction(utils.create_hparams(wavefunction_type='nope'))
+  with pytest.raises(NotImplementedError):
+    wavefunctions.build_wavefunction(utils.create_hparams(wavefunction_type='mps'))
+  with pytest.raises(NotImplementedError):
+    training.GROUND_STATE_OPTIMIZERS['ITSWO']()
+  with pytest.raises(NotImplementedError):
+    wavefunctions.FullyConnectedNetwork(2, 8, output_activation='cos')
+  wf = wavefunctions.build_wavefunction(utils.create_hparams(
+      wavefunction_type='conv_2d', num_sites=36, size_x=6, size_y=6))
+  assert wf._n_sites == 36 and wf._param_shapes(36)[0] == (5, 5, 1, 16)
+  assert graph_builders.ResourceName.CONFIGS.value == 'CONFIGS'
+
+
+def test_param_shapes_match_oracle_layout():
+  from oracle import ansatz as oansatz
+  cases = [
+      (dict(wavefunction_type='fully_connected', num_sites=20), oansatz.AnsatzSpec('fully_connected', 20)),
+      (dict(wavefunction_type='rbm', num_sites=36, num_fc_layers=0, fc_layer_size=144),
+       oansatz.AnsatzSpec('rbm', 36, num_layers=0, layer_size=144)),
+      (dict(wavefunction_type='rbm', num_sites=12, num_fc_layers=2, fc_layer_size=10),
+       oansatz.AnsatzSpec('rbm', 12, num_layers=2, layer_size=10)),
+      (dict(wavefunction_type='conv_1d', num_sites=12, num_conv_layers=3, kernel_size=4, num_conv_filters=3),
+       oansatz.AnsatzSpec('conv_1d', 12, num_layers=3, num_filters=3, kernel_size=4)),
+      (dict(wavefunction_type='conv_2d', num_sites=100, size_x=10, size_y=10),
+       oansatz.AnsatzSpec('conv_2d', 100, num_layers=5, num_filters=16, kernel_size=5, size_x=10, size_y=10)),
+  ]
+  for overrides, spec in cases:
+    wf = wavefunctions.build_wavefunction(utils.create_hparams(**overrides))
+    assert [tuple(s) for s in wf._param_shapes(spec.n_sites)] == \
+        [tuple(s) for _, s in oansatz.param_shapes(spec)]
+
+
+def test_load_bonds(tmp_path):
+  bonds, jx, jz = drivers.load_bonds(str(tmp_path), 6, -1.0)
+  assert bonds == [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 0)] and (jx, jz) == (-1.0, 1.0)
+  (tmp_path / 'J.txt').write_text('0 1\n1 2\n2 0\n')
+  bonds, jx, jz = drivers.load_bonds(str(tmp_path), 3, 1.0)
+  assert bonds == [(0, 1), (1, 2), (2, 0)] and (jx, jz) == (1.0, 1.0)
+  (tmp_path / 'J.txt').write_text('0 1 -1.0 1.0\n0 2 0.5 0.5\n')
+  bonds, jx, jz = drivers.load_bonds(str(tmp_path), 3, 1.0)
+  assert bonds == [(0, 1), (0, 2)]
+  np.testing.assert_allclose(jx, [-1.0, 0.5]); np.testing.assert_allclose(jz, [1.0, 0.5])
+
+
+def test_pack_unpack_sums():
+  sums = torch.arange(10, dtype=torch.float32).reshape(2, 5)
+  stats = torch.tensor([1.5, 2.5, 7.0, 0.0], dtype=torch.float64)
+  payload = distributed.pack_sums(sums, stats)
+  assert payload.dtype == torch.float32 and payload.numel() == 14
+  s2, t2 = torch.zeros_like(sums), torch.zeros_like(stats)
+  distributed.unpack_sums(payload, s2, t2)
+  assert torch.equal(s2, sums) and torch.equal(t2, stats)
+  assert distributed.world_size() == 1 and distributed.shard(64) == (64, 0)
+
+
+def _worker(rank, world, port, out_dir):
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  try:
+    local, w0 = distributed.shard(64)
+    assert (local, w0) == (32, rank * 32)
+    with pytest.raises(ValueError):
+      distributed.shard(63)
+    # each rank holds the partial sums of its walkers
+    g = torch.Generator().manual_seed(5)
+    per_walker = torch.randn(64, 2, 7, generator=g)          # same on both ranks
+    e = torch.randn(64, generator=g).double()
+    mine = slice(w0, w0 + local)
+    sums = per_walker[mine].sum(0)
+    stats = torch.tensor([e[mine].sum(), (e[mine] ** 2).sum(), float(local), 0.0], dtype=torch.float64)
+    distributed.allreduce_sums(sums, stats)
+    torch.testing.assert_close(sums, per_walker.sum(0), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(stats[:3], torch.tensor([e.sum(), (e ** 2).sum(), 64.0], dtype=torch.float64),
+                               rtol=1e-6, atol=1e-6)
+    m = distributed.allreduce_(torch.tensor([float(rank)]), op='max')
+    assert m.item() == world - 1
+    open(os.path.join(out_dir, 'ok%d' % rank), 'w').close()
+  finally:
+    dist.destroy_process_group()
+
+
+def test_sharded_allreduce_gloo_world2(tmp_path):
+  """The N > 1 host path on CPU: sharding + packed all-reduce give the
+  single-rank sums."""
+  port = 29500 + os.getpid() % 2000
+  mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  assert sorted(os.listdir(tmp_path)) == ['ok0', 'ok1']
