@@ -196,18 +196,11 @@ def run_ours(args, rank, world, local_rank):
   def step(events=None):
     """accumulate_gradients + one sweep (+ the packed all-reduce when sharded)."""
     if events: events[0].record()
-    lib = _native.load()
-    e_row = sums.weights[1]
-    _native.check(lib.cgsvmc_local_energy(
-        ansatz._handle, ham._handle, _native._ptr(state.packed), B, _native._ptr(e_row),
-        _native._ptr(sums.log_amp), None, None, _native._stream()))
-    if events: events[1].record()
-    ansatz.weighted_grad_sum(state.packed, sums.weights, out=sums.sums)
-    _native.energy_stats(e_row, sums.stats)
+    sums.accumulate(ham, state.packed)     # E_loc + both gradient sums + energy statistics
     if events: events[2].record()
     state.mc_steps(ansatz, SWEEP_STEPS)
     if events: events[3].record()
-    launches[0] += 5   # local_energy, grad, reduce_partials, energy_stats, mc
+    launches[0] += 5   # prep, walker kernel, reduce; prep, mc kernel
     if world > 1:
       payload[:2 * P].copy_(sums.sums.reshape(-1))
       payload[2 * P:].copy_(sums.stats.float())
@@ -237,8 +230,7 @@ def run_ours(args, rank, world, local_rank):
   clocks = clock.stop() if clock else None
   n_launch = launches[0]
   t_step = np.array([m[0].elapsed_time(m[4]) for m in marks]) * 1e-3
-  t_eloc = np.array([m[0].elapsed_time(m[1]) for m in marks]) * 1e-3
-  t_grad = np.array([m[1].elapsed_time(m[2]) for m in marks]) * 1e-3
+  t_acc = np.array([m[0].elapsed_time(m[2]) for m in marks]) * 1e-3
   t_mc = np.array([m[2].elapsed_time(m[3]) for m in marks]) * 1e-3
   total = torch.tensor([t_step.sum()], dtype=torch.float64, device=dev)
   if world > 1:
@@ -289,34 +281,43 @@ def run_ours(args, rank, world, local_rank):
   value = walkers_total * SWEEP_STEPS * args.steps / total_s
   eloc_rate = walkers_total * args.steps / total_s
   # dominant kernel = the one with the largest share of the step
-  shares = {'rbm_local_energy_kernel': float(t_eloc.mean()),
-            'rbm_mc_kernel': float(t_mc.mean()), 'rbm_grad_kernel+reduce+stats': float(t_grad.mean())}
-  dominant = max(('rbm_local_energy_kernel', 'rbm_mc_kernel'), key=lambda k: shares[k])
-  H = HIDDEN
-  f_inc_flop, f_inc_mufu = 4 * H + 4, 2 * H
-  f_fwd = 2 * N_SITES * H + 2 * N_SITES + 6 * H               # 10,440 + lncosh arithmetic
-  if dominant == 'rbm_mc_kernel':
-    units = B * SWEEP_STEPS
-    flop = units * f_inc_flop + B * f_fwd
-    mufu = units * f_inc_mufu + B * 2 * H
-    bytes_alg = B * (2 * 8 + 8)
+  shares = {'rbm2::walker_kernel (accumulate: E_loc + grad sums + stats) + prep + reduce': float(t_acc.mean()),
+            'rbm2::mc_kernel (36 Metropolis steps) + prep': float(t_mc.mean())}
+  dominant = 'mc' if t_mc.mean() >= t_acc.mean() else 'accumulate'
+  H, N = HIDDEN, N_SITES
+  f_inc = 4 * H + 4                                            # flop per ratio
+  f_fwd = 2 * N * H + 2 * N + 6 * H                            # 10,440 + lncosh arithmetic
+  f_grad = 2 * 2 * (N + 1) * (H + 1)                           # two weight columns, FMA = 2 flop
+  tab_bytes = 2 * H * 4                                        # two table rows per ratio
+  if dominant == 'mc':
+    kernel = 'rbm2::mc_kernel'
+    ratios = B * SWEEP_STEPS
+    flop = ratios * f_inc + B * f_fwd
+    mufu = ratios * (H // 4 + 1) + ratios * 0.4 * H            # lg2 per 4 units, rcp on accept
+    bytes_alg = B * (2 * 8)
     t_k = float(t_mc.mean())
   else:
-    flop = B * (f_fwd + n_act * f_inc_flop)
-    mufu = B * (2 * H + n_act * f_inc_mufu)
-    bytes_alg = B * (8 + 8)
-    t_k = float(t_eloc.mean())
+    kernel = 'rbm2::walker_kernel'
+    ratios = B * n_act
+    flop = B * (f_fwd + f_grad) + ratios * f_inc
+    mufu = ratios * (H // 4 + 1) + B * 2 * H
+    bytes_alg = B * (8 + 8) + 148 * 2 * P * 4 * 2
+    t_k = float(t_acc.mean())
   f_hz = pk['sm_max_mhz'] * 1e6
   fp32_peak = 148 * 128 * 2 * f_hz / 1e12                      # TFLOP/s, derived
   mufu_peak = 148 * 16 * f_hz / 1e12                           # T transcendental/s, derived
+  smem_peak = 148 * 128 * f_hz / 1e12                          # TB/s, derived (128 B/clk/SM)
   roofline = {
-      'kernel': dominant, 'bound': 'mufu',
-      'achieved': mufu / t_k / 1e12, 'peak': mufu_peak, 'unit': 'Ttranscendental/s',
-      'frac': mufu / t_k / 1e12 / mufu_peak, 'traffic': None,
-      'peak_source': 'derived: 148 SM x 16 MUFU/clk x sm_max_mhz (%s); state is SM-resident '
-                     'so neither HBM nor the tensor pipe bounds this kernel (SURVEY.md 8(d))' % pk['source'],
-      'fp32': {'achieved': flop / t_k / 1e12, 'peak': fp32_peak, 'unit': 'TFLOP/s',
-               'frac': flop / t_k / 1e12 / fp32_peak},
+      'kernel': kernel, 'bound': 'fp32 issue / shared-memory bandwidth (SM-resident state; SURVEY.md 8(d))',
+      'achieved': flop / t_k / 1e12, 'peak': fp32_peak, 'unit': 'TFLOP/s',
+      'frac': flop / t_k / 1e12 / fp32_peak, 'traffic': None,
+      'peak_source': 'derived: 148 SM x 128 FP32 lanes x 2 x sm_max_mhz (%s); neither HBM nor the '
+                     'tensor pipe bounds this kernel' % pk['source'],
+      'smem': {'achieved': ratios * tab_bytes / t_k / 1e12, 'peak': smem_peak, 'unit': 'TB/s',
+               'frac': ratios * tab_bytes / t_k / 1e12 / smem_peak,
+               'what': 'ratio-table rows read from shared memory (2 x H x 4 B per ratio)'},
+      'mufu': {'achieved': mufu / t_k / 1e12, 'peak': mufu_peak, 'unit': 'Ttranscendental/s',
+               'frac': mufu / t_k / 1e12 / mufu_peak},
       'hbm': {'achieved': bytes_alg / t_k / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
               'frac': bytes_alg / t_k / 1e9 / pk['hbm_gbs'], 'peak_source': pk['source']},
       'kernel_ms': t_k * 1e3, 'n_active_bonds_mean': n_act,
@@ -334,7 +335,7 @@ def run_ours(args, rank, world, local_rank):
                      ', all-reduce of [2P+4] floats per step' if world > 1 else '')},
       'kernel_ms': {k: v * 1e3 for k, v in shares.items()},
       'kernel_rates': {'sampler_walker_steps_per_sec': B * SWEEP_STEPS / float(t_mc.mean()),
-                       'eloc_evals_per_sec': B / float(t_eloc.mean())},
+                       'accumulate_eloc_evals_per_sec': B / float(t_acc.mean())},
       'roofline': roofline,
       'e2e': {'value': walkers_total * SWEEP_STEPS * args.steps / e2e_s, 'unit': 'walker-steps/s',
               'eloc_evals_per_sec': walkers_total * args.steps / e2e_s,

@@ -24,7 +24,7 @@ EXPORTS = [
     'cgsvmc_pack_configs', 'cgsvmc_unpack_configs', 'cgsvmc_random_configs',
     'cgsvmc_log_amp', 'cgsvmc_mc_steps', 'cgsvmc_mc_step_replay',
     'cgsvmc_flip_enum', 'cgsvmc_local_energy', 'cgsvmc_weighted_grad_sum',
-    'cgsvmc_energy_stats',
+    'cgsvmc_energy_stats', 'cgsvmc_accumulate',
 ]
 
 
@@ -71,6 +71,7 @@ def load():
   lib.cgsvmc_local_energy.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp]
   lib.cgsvmc_weighted_grad_sum.argtypes = [vp, vp, vp, i64, i32, vp, vp]
   lib.cgsvmc_energy_stats.argtypes = [vp, i64, vp, vp]
+  lib.cgsvmc_accumulate.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp]
   for name in EXPORTS:
     fn = getattr(lib, name)
     if name not in ('cgsvmc_last_error', 'cgsvmc_ansatz_num_params'):
@@ -222,6 +223,22 @@ class Ansatz:
     check(load().cgsvmc_weighted_grad_sum(self._handle, _ptr(packed), _ptr(weights),
                                           b, k, _ptr(out), _stream()))
     return out
+
+
+  def accumulate(self, ham, packed, sums, stats, e_loc_out=None, log_amp_out=None):
+    """One session.run(accumulate_gradients) (training.py:539-558): sums [2, P]
+    += (sum_b O_b, sum_b E_b O_b), stats float64[4] += (sum E, sum E^2, B, 0)."""
+    b = packed.shape[0]
+    _want(packed, torch.int64, (b, n_words(self.n_sites)), 'packed')
+    _want(sums, torch.float32, (2, self.num_params), 'sums')
+    _want(stats, torch.float64, (4,), 'stats')
+    if e_loc_out is not None:
+      _want(e_loc_out, torch.float32, (b,), 'e_loc_out')
+    if log_amp_out is not None:
+      _want(log_amp_out, torch.float32, (b,), 'log_amp_out')
+    check(load().cgsvmc_accumulate(self._handle, ham._handle, _ptr(packed), b,
+                                   _ptr(e_loc_out), _ptr(log_amp_out), _ptr(sums),
+                                   _ptr(stats), _stream()))
 
 
 class Hamiltonian:

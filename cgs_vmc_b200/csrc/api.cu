@@ -143,6 +143,8 @@ int cgsvmc_ansatz_create(const cgsvmc_ansatz_desc* desc, cgsvmc_ansatz** out) {
 int cgsvmc_ansatz_destroy(cgsvmc_ansatz* a) {
   if (a == nullptr) return CGSVMC_OK;
   if (a->scratch != nullptr) cudaFree(a->scratch);
+  if (a->tables != nullptr) cudaFree(a->tables);
+  if (a->acc_weights != nullptr) cudaFree(a->acc_weights);
   delete a;
   return CGSVMC_OK;
 }
@@ -232,6 +234,9 @@ int cgsvmc_mc_steps(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int32_t
   if (B < 0 || n_steps < 0) return invalid("mc_steps: negative size");
   if (B == 0) return CGSVMC_OK;
   if (packed == nullptr) return invalid("mc_steps: NULL configs");
+  if (rbm2_supported(a, nullptr))
+    return rbm2_mc_steps(const_cast<cgsvmc_ansatz*>(a), packed, B, n_steps, seed, walker_id0, step0,
+                         accept_count, log_amp_out, (cudaStream_t)stream);
   if (rbm_fast_supported(a))
     return rbm_mc_steps(a, packed, B, n_steps, seed, walker_id0, step0, accept_count, log_amp_out,
                         (cudaStream_t)stream);
@@ -271,6 +276,9 @@ int cgsvmc_local_energy(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint6
   if (B < 0) return invalid("local_energy: n_walkers < 0");
   if (B == 0) return CGSVMC_OK;
   if (packed == nullptr || e_loc == nullptr) return invalid("local_energy: NULL buffer");
+  if (rbm2_supported(a, h))
+    return rbm2_walker(const_cast<cgsvmc_ansatz*>(a), h, packed, B, e_loc, log_amp_out, diag_out,
+                       offdiag_ratio_out, false, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
   if (rbm_fast_supported(a))
     return rbm_local_energy(a, h, packed, B, e_loc, log_amp_out, diag_out, offdiag_ratio_out,
                             (cudaStream_t)stream);
@@ -287,8 +295,53 @@ int cgsvmc_weighted_grad_sum(const cgsvmc_ansatz* a, const uint64_t* packed, con
   if (packed == nullptr || weights == nullptr || out == nullptr)
     return invalid("weighted_grad_sum: NULL buffer");
   cgsvmc_ansatz* am = const_cast<cgsvmc_ansatz*>(a);   // scratch growth only
+  if (rbm2_supported(a, nullptr)) {
+    for (int k0 = 0; k0 < K; k0 += 2) {   // two weight columns per pass
+      const int kk = K - k0 < 2 ? K - k0 : 2;
+      if (int rc = rbm2_walker(am, nullptr, packed, B, nullptr, nullptr, nullptr, nullptr, true,
+                               weights + (int64_t)k0 * B, kk, out + (int64_t)k0 * a->n_params,
+                               nullptr, (cudaStream_t)stream))
+        return rc;
+    }
+    return CGSVMC_OK;
+  }
   if (rbm_fast_supported(a)) return rbm_grad(am, packed, weights, B, K, out, (cudaStream_t)stream);
   return net_grad(am, packed, weights, B, K, out, (cudaStream_t)stream);
+}
+
+int cgsvmc_accumulate(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, int64_t B,
+                      float* e_loc_out, float* log_amp_out, float* sums, double* stats, void* stream) {
+  if (int rc = check_ready(a)) return rc;
+  if (h == nullptr) return invalid("accumulate: NULL hamiltonian");
+  if (h->n_sites != a->desc.n_sites) return invalid("accumulate: hamiltonian and ansatz n_sites differ");
+  if (B < 0) return invalid("accumulate: n_walkers < 0");
+  if (B == 0) return CGSVMC_OK;
+  if (packed == nullptr || sums == nullptr || stats == nullptr) return invalid("accumulate: NULL buffer");
+  cgsvmc_ansatz* am = const_cast<cgsvmc_ansatz*>(a);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rbm2_supported(a, h))
+    return rbm2_walker(am, h, packed, B, e_loc_out, log_amp_out, nullptr, nullptr, true, nullptr, 2, sums,
+                       stats, st);
+  // generic path: E_loc into the second weight row, then the two gradient sums
+  const size_t need = (size_t)2 * B * sizeof(float);
+  if (am->acc_weights_bytes < need) {
+    if (am->acc_weights != nullptr) {
+      if (int rc = cuda_fail(cudaDeviceSynchronize(), "accumulate sync")) return rc;
+      cudaFree(am->acc_weights);
+      am->acc_weights = nullptr;
+      am->acc_weights_bytes = 0;
+    }
+    if (int rc = cuda_fail(cudaMalloc(&am->acc_weights, need), "accumulate alloc")) return rc;
+    am->acc_weights_bytes = need;
+  }
+  float* w = am->acc_weights;
+  if (int rc = launch_fill(w, B, 1.0f, st)) return rc;
+  if (int rc = cgsvmc_local_energy(a, h, packed, B, w + B, log_amp_out, nullptr, nullptr, stream)) return rc;
+  if (e_loc_out != nullptr)
+    if (int rc = cuda_fail(cudaMemcpyAsync(e_loc_out, w + B, (size_t)B * sizeof(float),
+                                           cudaMemcpyDeviceToDevice, st), "accumulate copy")) return rc;
+  if (int rc = cgsvmc_weighted_grad_sum(a, packed, w, B, 2, sums, stream)) return rc;
+  return launch_energy_stats(w + B, B, stats, st);
 }
 
 int cgsvmc_energy_stats(const float* e_loc, int64_t B, double* stats, void* stream) {

@@ -24,6 +24,10 @@ struct cgsvmc_ansatz {
   int max_smem_optin = 0;          // bytes
   float* scratch = nullptr;        // owned device scratch (gradient partials ...)
   size_t scratch_bytes = 0;
+  float* tables = nullptr;         // owned: derived parameter image of the rbm2 kernels
+  size_t tables_bytes = 0;
+  float* acc_weights = nullptr;    // owned: [2, B] weight rows of cgsvmc_accumulate (tile networks)
+  size_t acc_weights_bytes = 0;
 };
 
 struct cgsvmc_ham {
@@ -51,6 +55,7 @@ int launch_random_configs(uint64_t* packed, int64_t B, int N, uint64_t seed, uin
                           cudaStream_t s);
 int launch_flip_enum(const cgsvmc_ham* h, const uint64_t* packed, int64_t B, uint64_t* flipped,
                      uint32_t* mask, cudaStream_t s);
+int launch_fill(float* dst, int64_t n, float value, cudaStream_t s);
 int launch_energy_stats(const float* e, int64_t B, double* stats, cudaStream_t s);
 int launch_reduce_partials(const float* partials, int n_parts, int64_t n, float* out,
                            cudaStream_t s);
@@ -70,6 +75,19 @@ int rbm_local_energy(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t
                      float* off_out, cudaStream_t s);
 int rbm_grad(cgsvmc_ansatz* a, const uint64_t* packed, const float* weights, int64_t B, int K,
              float* out, cudaStream_t s);
+
+// ---- pure RBM, second generation (rbm2.cu): ratio tables, 4 walkers per warp ----
+// h may be NULL in rbm2_supported (sampler only).
+bool rbm2_supported(const cgsvmc_ansatz* a, const cgsvmc_ham* h);
+int rbm2_mc_steps(cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int n_steps, uint64_t seed,
+                  uint64_t walker0, uint64_t step0, unsigned long long* accept_count,
+                  float* log_amp_out, cudaStream_t s);
+// One pass over the walkers: local energy when h != NULL (e_loc / log_amp /
+// diag / off nullable), weighted gradient sums when do_grad (weights NULL =>
+// rows (1, E_loc); out [K, P] +=; stats nullable double[4] +=).
+int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, int64_t B,
+                float* e_loc, float* log_amp, float* diag, float* off, bool do_grad,
+                const float* weights, int K, float* out, double* stats, cudaStream_t s);
 
 // ---- generic tile networks: fc, rbm with hidden layers, conv (net.cu) ----
 int net_log_amp(const cgsvmc_ansatz* a, const uint64_t* packed, int64_t B, float* out,

@@ -473,7 +473,8 @@ int set_smem(F kernel, size_t bytes) {
 
 bool rbm_fast_supported(const cgsvmc_ansatz* a) {
   return a->desc.kind == CGSVMC_ANSATZ_RBM && a->desc.num_layers == 0 &&
-         a->desc.layer_size <= 256 && a->desc.n_sites <= CGSVMC_MAX_SITES;
+         a->desc.layer_size <= 256 && a->desc.n_sites <= CGSVMC_MAX_SITES &&
+         n_words(a->desc.n_sites) != 3;   // kernels are instantiated for 1, 2 and 4 words
 }
 
 int rbm_log_amp(const cgsvmc_ansatz* a, const uint64_t* packed, int64_t B, float* out,

@@ -1,0 +1,222 @@
+// Pure-RBM fast path, host side: parameter-image build, launch planning,
+// deterministic cross-CTA reduction.  Kernels: rbm2_impl.cuh.
+#include <algorithm>
+
+#include "rbm2_impl.cuh"
+
+namespace cgsvmc {
+namespace rbm2 {
+namespace {
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// One block per site (rows of the tables + row sums), then one block per 128
+// hidden units (column sums).
+__global__ void __launch_bounds__(128)
+prep_kernel(Image im, const float* __restrict__ a, const float* __restrict__ a0,
+            const float* __restrict__ W, const float* __restrict__ c, float* __restrict__ img) {
+  __shared__ float red[4];
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x < im.N) {
+    const int i = blockIdx.x;
+    float rs = 0.f;
+    for (int j = tid; j < im.HP; j += 128) {
+      const float w = j < im.H ? W[(size_t)i * im.H + j] : 0.f;
+      img[im.off_w2 + (size_t)i * im.HP + j] = 2.f * w;
+      img[im.off_f + (size_t)i * im.HP + j] = expf(4.f * w);
+      img[im.off_g + (size_t)i * im.HP + j] = expf(-4.f * w);
+      rs += w;
+    }
+    rs = warp_sum(rs);
+    if ((tid & 31) == 0) red[tid >> 5] = rs;
+    __syncthreads();
+    if (tid == 0) {
+      const float total = (red[0] + red[1]) + (red[2] + red[3]);
+      img[im.off_a2 + i] = 2.885390081777927f * (a[i] - total);
+      img[im.off_a + i] = a[i];
+    }
+  } else {
+    const int j = ((int)blockIdx.x - im.N) * 128 + tid;
+    if (j < im.HP) {
+      float cs = 0.f;
+      if (j < im.H)
+        for (int i = 0; i < im.N; ++i) cs += W[(size_t)i * im.H + j];
+      img[im.off_base + j] = (j < im.H ? c[j] : 0.f) - cs;
+    }
+    if ((int)blockIdx.x == im.N) {
+      if (tid < 4) img[im.off_a0 + tid] = a0[0];
+      for (int i = im.N + tid; i < im.NP; i += 128) { img[im.off_a2 + i] = 0.f; img[im.off_a + i] = 0.f; }
+    }
+  }
+}
+
+// out[f] += sum_c partials[c][f] in a fixed order; 64 outputs x 4 CTA slices
+// per block.  Also folds the per-CTA energy sums into stats.
+__global__ void __launch_bounds__(256)
+reduce_kernel(const float* __restrict__ partials, int n_cta, int64_t stride, int64_t n_out,
+              float* __restrict__ out, const double* __restrict__ stat_partials, int64_t B,
+              double* __restrict__ stats) {
+  __shared__ float sm[4][64];
+  const int col = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int64_t f = (int64_t)blockIdx.x * 64 + col;
+  float s = 0.f;
+  if (f < n_out)
+    for (int c = slice; c < n_cta; c += 4) s += partials[(size_t)c * stride + f];
+  sm[slice][col] = s;
+  __syncthreads();
+  if (slice == 0 && f < n_out) out[f] += (sm[0][col] + sm[1][col]) + (sm[2][col] + sm[3][col]);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && stat_partials != nullptr) {
+    double e = 0.0, e2 = 0.0;
+    for (int c = 0; c < n_cta; ++c) { e += stat_partials[2 * c]; e2 += stat_partials[2 * c + 1]; }
+    stats[0] += e;
+    stats[1] += e2;
+    stats[2] += (double)B;
+  }
+}
+
+Image make_image(int N, int H, int HP) {
+  Image im;
+  im.N = N; im.H = H; im.HP = HP; im.NP = round_up(N, 4);
+  im.words = n_words(N);
+  im.off_w2 = 0;
+  im.off_f = N * HP;
+  im.off_g = 2 * N * HP;
+  im.off_a2 = 3 * N * HP;
+  im.off_base = im.off_a2 + im.NP;
+  im.off_a = im.off_base + HP;
+  im.off_a0 = im.off_a + im.NP;
+  im.total = im.off_a0 + 4;
+  return im;
+}
+
+size_t walker_smem_bytes(const Image& im, int slots, bool ws, bool do_eloc, int n_bonds, bool do_grad) {
+  const int NP4 = round_up(im.N + 1, 4);
+  size_t b = ws ? (size_t)im.total * 4 : 0;
+  b += 2048 + 16;
+  if (do_eloc) b += (size_t)n_bonds * 16 + (size_t)slots * round_up(n_bonds, 8) * 2;
+  if (do_grad) b += (size_t)slots * im.HP * 4 + (size_t)slots * 2 * NP4 * 4;
+  b += (size_t)slots * 4;
+  return b;
+}
+
+// Fills everything but the shared-memory decisions.
+bool base_plan(const cgsvmc_ansatz* a, int64_t B, Plan* pl) {
+  const cgsvmc_ansatz_desc& d = a->desc;
+  if (d.kind != CGSVMC_ANSATZ_RBM || d.num_layers != 0) return false;
+  if (d.layer_size < 1 || d.layer_size > 256 || d.n_sites > CGSVMC_MAX_SITES) return false;
+  const int H = d.layer_size;
+  int HP = round_up(H, 32);
+  if (HP <= 160) { pl->lpw = 8; pl->kj4 = HP / 32; }
+  else { HP = round_up(H, 64); pl->lpw = 16; pl->kj4 = HP / 64; }
+  pl->im = make_image(d.n_sites, H, HP);
+  pl->nw = n_words(d.n_sites) == 3 ? 4 : n_words(d.n_sites);
+  const int wpw = 32 / pl->lpw, slots = kCtaWarps * wpw;
+  const int64_t per_sm = std::max<int64_t>(1, (B + a->num_sms - 1) / a->num_sms);
+  const int64_t rounds = (per_sm + slots - 1) / slots;
+  int64_t wpc = (per_sm + rounds - 1) / rounds;
+  wpc = std::min<int64_t>(slots, (wpc + wpw - 1) / wpw * wpw);
+  pl->wpc = (int)wpc;
+  pl->n_batches = (B + wpc - 1) / wpc;
+  pl->grid = (int)std::min<int64_t>(pl->n_batches, a->num_sms);
+  return true;
+}
+
+int build_image(cgsvmc_ansatz* a, const Plan& pl, cudaStream_t st) {
+  const size_t bytes = (size_t)pl.im.total * 4;
+  if (a->tables_bytes < bytes) {
+    if (a->tables != nullptr) {
+      if (int rc = cuda_fail(cudaDeviceSynchronize(), "tables sync")) return rc;
+      cudaFree(a->tables);
+      a->tables = nullptr;
+      a->tables_bytes = 0;
+    }
+    if (int rc = cuda_fail(cudaMalloc(&a->tables, bytes), "tables alloc")) return rc;
+    a->tables_bytes = bytes;
+  }
+  const float* p = a->params;
+  const int blocks = pl.im.N + (pl.im.HP + 127) / 128;
+  prep_kernel<<<blocks, 128, 0, st>>>(pl.im, p + a->offsets[0], p + a->offsets[1], p + a->offsets[2],
+                                      p + a->offsets[3], a->tables);
+  return cuda_fail(cudaGetLastError(), "rbm2 prep launch");
+}
+
+}  // namespace
+}  // namespace rbm2
+
+using namespace rbm2;
+
+bool rbm2_supported(const cgsvmc_ansatz* a, const cgsvmc_ham* h) {
+  Plan pl;
+  if (!base_plan(a, 1, &pl)) return false;
+  const int slots = kCtaWarps * (32 / pl.lpw);
+  const int nb = h != nullptr ? h->n_bonds : 0;
+  if (nb >= 65535) return false;
+  // the largest launch (accumulate) must fit with the image left in global memory
+  return walker_smem_bytes(pl.im, slots, false, h != nullptr, nb, true) <= (size_t)a->max_smem_optin;
+}
+
+int rbm2_mc_steps(cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int n_steps, uint64_t seed,
+                  uint64_t walker0, uint64_t step0, unsigned long long* accept_count,
+                  float* log_amp_out, cudaStream_t st) {
+  Plan pl;
+  if (!base_plan(a, B, &pl)) { set_error("rbm2: unsupported ansatz"); return CGSVMC_ERR_UNSUPPORTED; }
+  const size_t img_bytes = (size_t)pl.im.total * 4;
+  pl.ws = img_bytes + 2048 + 16 <= (size_t)a->max_smem_optin;
+  pl.mc_smem = (pl.ws ? img_bytes : 0) + 2048 + 16;
+  if (int rc = build_image(a, pl, st)) return rc;
+  switch (pl.nw) {
+    case 1: return launch_mc_nw1(pl, a->tables, packed, B, n_steps, seed, walker0, step0, accept_count, log_amp_out, st);
+    case 2: return launch_mc_nw2(pl, a->tables, packed, B, n_steps, seed, walker0, step0, accept_count, log_amp_out, st);
+    default: return launch_mc_nw4(pl, a->tables, packed, B, n_steps, seed, walker0, step0, accept_count, log_amp_out, st);
+  }
+}
+
+int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, int64_t B,
+                float* e_loc, float* log_amp, float* diag, float* off, bool do_grad,
+                const float* weights, int K, float* out, double* stats, cudaStream_t st) {
+  Plan pl;
+  if (!base_plan(a, B, &pl)) { set_error("rbm2: unsupported ansatz"); return CGSVMC_ERR_UNSUPPORTED; }
+  const bool do_eloc = h != nullptr;
+  const int slots = kCtaWarps * (32 / pl.lpw);
+  const int nb = do_eloc ? h->n_bonds : 0;
+  pl.ws = walker_smem_bytes(pl.im, slots, true, do_eloc, nb, do_grad) <= (size_t)a->max_smem_optin;
+  pl.walker_smem = walker_smem_bytes(pl.im, slots, pl.ws, do_eloc, nb, do_grad);
+  if (pl.walker_smem > (size_t)a->max_smem_optin) {
+    set_error("rbm2: problem does not fit in shared memory");
+    return CGSVMC_ERR_UNSUPPORTED;
+  }
+  if (int rc = build_image(a, pl, st)) return rc;
+  const int64_t P = a->n_params;
+  WalkerArgs A;
+  memset(&A, 0, sizeof(A));
+  A.packed = packed; A.B = B; A.wpc = pl.wpc; A.n_batches = pl.n_batches;
+  A.do_eloc = do_eloc ? 1 : 0;
+  if (do_eloc) { A.bonds_ij = h->ij; A.bonds_jx = h->jx; A.bonds_jz = h->jz; A.n_bonds = h->n_bonds; }
+  A.e_loc = e_loc; A.log_amp = log_amp; A.diag = diag; A.off = off;
+  A.do_grad = do_grad ? 1 : 0;
+  A.weights = weights; A.K = K; A.P = P;
+  if (do_grad) {
+    const size_t part_bytes = (size_t)pl.grid * 2 * P * sizeof(float);
+    const size_t part_pad = (part_bytes + 15) / 16 * 16;
+    if (int rc = ensure_scratch(a, part_pad + (size_t)pl.grid * 2 * sizeof(double))) return rc;
+    A.partials = a->scratch;
+    A.stat_partials = stats != nullptr
+        ? reinterpret_cast<double*>(reinterpret_cast<char*>(a->scratch) + part_pad) : nullptr;
+  }
+  int rc;
+  switch (pl.nw) {
+    case 1: rc = launch_walker_nw1(pl, a->tables, A, st); break;
+    case 2: rc = launch_walker_nw2(pl, a->tables, A, st); break;
+    default: rc = launch_walker_nw4(pl, a->tables, A, st); break;
+  }
+  if (rc) return rc;
+  if (do_grad) {
+    const int64_t n_out = (int64_t)K * P;
+    const int blocks = (int)((n_out + 63) / 64);
+    reduce_kernel<<<blocks, 256, 0, st>>>(A.partials, pl.grid, 2 * P, n_out, out, A.stat_partials, B, stats);
+    return cuda_fail(cudaGetLastError(), "rbm2 reduce launch");
+  }
+  return CGSVMC_OK;
+}
+
+}  // namespace cgsvmc

@@ -1,0 +1,684 @@
+// Pure RBM ansatz (rbm with num_fc_layers == 0), second-generation kernels.
+//
+//   z(sigma) = a . sigma + a0 + sum_j log cosh(theta_j),  theta = W^T sigma + c
+//                                                   (wavefunctions.py:410-436)
+//
+// Amplitude RATIOS are all the sampler (graph_builders.py:74-79) and the local
+// energy (operators.py:168-169, 259) need.  For the exchange "raise site d,
+// lower site u" theta'_j = theta_j + delta_j, delta_j = 2 W[d][j] - 2 W[u][j], and
+//
+//   cosh(theta + delta) / cosh(theta) = e^{-delta} (p e^{2 delta} + m),
+//   p = (1 + tanh theta) / 2,  m = (1 - tanh theta) / 2          (p + m = 1)
+//
+// so with the per-site tables F = e^{4W}, G = e^{-4W} (e^{2 delta_j} =
+// F[d][j] G[u][j]) and the per-site scalar A2[i] = 2 log2(e) (a_i - sum_j W[i][j])
+//
+//   log2 psi'/psi = A2[d] - A2[u] + sum_j log2(p_j F[d][j] G[u][j] + m_j).
+//
+// The inner loop is 2 table loads + 4 FP32 ops per hidden unit and NO
+// transcendental (one lg2 per 4 hidden units, on a product); the walker state
+// is (p_j, m_j) in registers, updated multiplicatively on acceptance
+// (p' = p y / n, m' = m / n, n = p y + m).  All tables live in shared memory
+// (copied once per CTA with a TMA bulk copy) when they fit.
+//
+// Mapping: LPW lanes own one walker (LPW = 8: four walkers per warp, 16: two),
+// lane `sub` holds hidden units j = 4 (sub + LPW q) + c, q < KJ4, c < 4, so a
+// table row is read with LDS.128 in phases of one walker each (conflict-free).
+// One persistent CTA of 512 threads per SM.
+#pragma once
+#include "common.cuh"
+#include "internal.h"
+#include "rbm2.h"
+
+namespace cgsvmc {
+namespace rbm2 {
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ float lg2_approx(float x) {
+  float l;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+  return l;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+  return e;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+template <bool WS>
+__device__ __forceinline__ float4 ld4(const float* p) {
+  if (WS) return *reinterpret_cast<const float4*>(p);
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <bool WS>
+__device__ __forceinline__ float ld1(const float* p) {
+  if (WS) return *p;
+  return __ldg(p);
+}
+
+template <int LPW>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPW / 2; o > 0; o >>= 1) v += __shfl_xor_sync(CGSVMC_FULL_MASK, v, o);
+  return v;
+}
+
+// TMA bulk copy global -> shared of the parameter image; every thread returns
+// after the bytes have landed.  `bar` is an 8-byte shared mbarrier.
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  const uint32_t bar_a = smem_u32(bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes)
+                 : "memory");
+    uint32_t done = 0;
+    while (done < bytes) {
+      const uint32_t chunk = min(bytes - done, 32768u);
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              smem_u32(reinterpret_cast<char*>(dst) + done)),
+          "l"(reinterpret_cast<const char*>(src) + done), "r"(chunk), "r"(bar_a)
+          : "memory");
+      done += chunk;
+    }
+  }
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(bar_a), "r"(0u)
+        : "memory");
+  }
+}
+
+// select-in-byte table: lut[v * 8 + r] = index of the r-th set bit of v
+__device__ __forceinline__ void build_lut(uint8_t* lut) {
+  for (int e = threadIdx.x; e < 2048; e += blockDim.x) {
+    const int v = e >> 3, r = e & 7;
+    int pos = 0, seen = 0;
+    for (int b = 0; b < 8; ++b)
+      if ((v >> b) & 1) { if (seen == r) pos = b; ++seen; }
+    lut[e] = (uint8_t)(r < seen ? pos : 0);
+  }
+}
+
+struct Tables {
+  const float* w2;    // [N][HP]  2 W
+  const float* f;     // [N][HP]  exp(4 W)
+  const float* g;     // [N][HP]  exp(-4 W)
+  const float* a2;    // [NP]     2 log2(e) (a_i - sum_j W_ij)
+  const float* base;  // [HP]     c_j - sum_i W_ij
+  const float* a;     // [NP]
+  const float* a0;    // [4]
+};
+
+__device__ __forceinline__ Tables tables_at(const float* img, const Image& im) {
+  Tables t;
+  t.w2 = img + im.off_w2; t.f = img + im.off_f; t.g = img + im.off_g;
+  t.a2 = img + im.off_a2; t.base = img + im.off_base; t.a = img + im.off_a; t.a0 = img + im.off_a0;
+  return t;
+}
+
+template <int NW>
+__device__ __forceinline__ int spin_bit(const uint64_t (&s)[NW], int site) {
+  uint64_t w = s[0];
+#pragma unroll
+  for (int i = 1; i < NW; ++i) if ((site >> 6) == i) w = s[i];
+  return (int)((w >> (site & 63)) & 1ull);
+}
+
+// ---------------------------------------------------------------------------
+// walker state
+// ---------------------------------------------------------------------------
+// theta_j = base_j + sum_{i up} 2 W[i][j];  p = 1 / (1 + e^{-2 theta}),
+// m = 1 / (1 + e^{2 theta}).  Optionally returns this lane's share of
+// sum_j log cosh theta_j + a . sigma (group_sum + a0 gives z).
+template <int NW, int LPW, int KJ4, bool WS>
+__device__ __forceinline__ float init_state(const Tables& t, const Image& im, const uint64_t (&s)[NW],
+                                            int sub, float (&p)[4 * KJ4], float (&m)[4 * KJ4],
+                                            bool want_z) {
+  float th[4 * KJ4];
+#pragma unroll
+  for (int q = 0; q < KJ4; ++q) {
+    const float4 b = ld4<WS>(t.base + 4 * (sub + LPW * q));
+    th[4 * q] = b.x; th[4 * q + 1] = b.y; th[4 * q + 2] = b.z; th[4 * q + 3] = b.w;
+  }
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    uint64_t bits = s[w];
+    while (bits) {
+      const int i = 64 * w + __ffsll((long long)bits) - 1;
+      bits &= bits - 1;
+      const float* row = t.w2 + (size_t)i * im.HP + 4 * sub;
+#pragma unroll
+      for (int q = 0; q < KJ4; ++q) {
+        const float4 v = ld4<WS>(row + 4 * LPW * q);
+        th[4 * q] += v.x; th[4 * q + 1] += v.y; th[4 * q + 2] += v.z; th[4 * q + 3] += v.w;
+      }
+    }
+  }
+  float zpart = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4 * KJ4; ++k) {
+    const float ax = fabsf(th[k]);
+    const float e = expf(-2.f * ax);
+    const float r = 1.f / (1.f + e);
+    const float big = r, small = e * r;
+    p[k] = th[k] >= 0.f ? big : small;
+    m[k] = th[k] >= 0.f ? small : big;
+    if (want_z) zpart += ax + log1pf(e) - 0.6931471805599453f;
+  }
+  if (want_z) {
+    for (int i = sub; i < im.N; i += LPW) {
+      const float ai = ld1<WS>(t.a + i);
+      zpart += spin_bit<NW>(s, i) ? ai : -ai;
+    }
+  }
+  return zpart;
+}
+
+// log2(psi'/psi) for "raise site d, lower site u" (uniform within the lane
+// group).  KEEP: also return y[k] = p[k] F G for the acceptance update.
+template <int LPW, int KJ4, bool WS, bool KEEP>
+__device__ __forceinline__ float exchange_log2_ratio(const Tables& t, const Image& im, int d, int u,
+                                                     int sub, const float (&p)[4 * KJ4],
+                                                     const float (&m)[4 * KJ4],
+                                                     float (&y)[4 * KJ4]) {
+  const float* fr = t.f + (size_t)d * im.HP + 4 * sub;
+  const float* gr = t.g + (size_t)u * im.HP + 4 * sub;
+  float lsum = 0.f;
+#pragma unroll
+  for (int q = 0; q < KJ4; ++q) {
+    const float4 f = ld4<WS>(fr + 4 * LPW * q);
+    const float4 g = ld4<WS>(gr + 4 * LPW * q);
+    const float y0 = p[4 * q] * (f.x * g.x), y1 = p[4 * q + 1] * (f.y * g.y);
+    const float y2 = p[4 * q + 2] * (f.z * g.z), y3 = p[4 * q + 3] * (f.w * g.w);
+    if (KEEP) { y[4 * q] = y0; y[4 * q + 1] = y1; y[4 * q + 2] = y2; y[4 * q + 3] = y3; }
+    const float n01 = (y0 + m[4 * q]) * (y1 + m[4 * q + 1]);
+    const float n23 = (y2 + m[4 * q + 2]) * (y3 + m[4 * q + 3]);
+    lsum += lg2_approx(n01 * n23);
+  }
+  lsum = group_sum<LPW>(lsum);
+  return lsum + (ld1<WS>(t.a2 + d) - ld1<WS>(t.a2 + u));
+}
+
+// ---------------------------------------------------------------------------
+// uniformly random up site and down site: the k_up-th set bit and the k_dn-th
+// clear (valid) bit in site order, resolved by the LPW lanes of the group
+// (each owns CB = 64 NW / LPW bits) with a packed prefix scan and the
+// select-in-byte table.
+// ---------------------------------------------------------------------------
+template <int CB>
+__device__ __forceinline__ int select_in_chunk(uint32_t c, int r, const uint8_t* lut) {
+  int base = 0;
+  if (CB > 16) {
+    const int pc = __popc(c & 0xffffu);
+    if (r >= pc) { r -= pc; c >>= 16; base += 16; }
+    c &= 0xffffu;
+  }
+  if (CB > 8) {
+    const int pc = __popc(c & 0xffu);
+    if (r >= pc) { r -= pc; c >>= 8; base += 8; }
+    c &= 0xffu;
+  }
+  return base + lut[c * 8 + r];
+}
+
+template <int NW, int LPW>
+struct SitePicker {
+  static constexpr int CB = 64 * NW / LPW;
+  int word, shift, sub;
+  uint32_t vchunk;
+  __device__ __forceinline__ void setup(int n_sites, int sub_) {
+    sub = sub_;
+    word = (CB * sub) >> 6;
+    shift = (CB * sub) & 63;
+    const uint64_t vm = valid_mask_word(n_sites, word);
+    vchunk = (uint32_t)(vm >> shift) & (CB == 32 ? 0xffffffffu : ((1u << CB) - 1u));
+  }
+  __device__ __forceinline__ void pick(const uint64_t (&s)[NW], int k_up, int k_dn,
+                                       const uint8_t* lut, int& up, int& dn) const {
+    uint64_t wv = s[0];
+#pragma unroll
+    for (int i = 1; i < NW; ++i) if (word == i) wv = s[i];
+    const uint32_t chunk = (uint32_t)(wv >> shift);
+    const uint32_t cu = chunk & vchunk, cd = ~chunk & vchunk;
+    const int nu = __popc(cu), nd = __popc(cd);
+    const uint32_t cnt = (uint32_t)nu | ((uint32_t)nd << 16);
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < LPW; o <<= 1) {
+      const uint32_t tv = __shfl_up_sync(CGSVMC_FULL_MASK, inc, o, LPW);
+      if (sub >= o) inc += tv;
+    }
+    const uint32_t exc = inc - cnt;
+    const int ru = k_up - (int)(exc & 0xffffu), rd = k_dn - (int)(exc >> 16);
+    const bool own_u = ru >= 0 && ru < nu, own_d = rd >= 0 && rd < nd;
+    uint32_t res = 0;
+    if (own_u) res = (uint32_t)(CB * sub + select_in_chunk<CB>(cu, ru, lut));
+    if (own_d) res |= (uint32_t)(CB * sub + select_in_chunk<CB>(cd, rd, lut)) << 16;
+#pragma unroll
+    for (int o = LPW / 2; o > 0; o >>= 1) res |= __shfl_xor_sync(CGSVMC_FULL_MASK, res, o);
+    up = (int)(res & 0xffffu);
+    dn = (int)(res >> 16);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// K2: Metropolis sampler, graph_builders.py:54-89 x n_steps
+// ---------------------------------------------------------------------------
+template <int NW, int LPW, int KJ4, bool WS>
+__global__ void __launch_bounds__(kCtaThreads, 1)
+mc_kernel(Image im, const float* __restrict__ img_g, uint64_t* __restrict__ packed, int64_t B,
+          int wpc, int64_t n_batches, int n_steps, uint64_t seed, uint64_t walker0, uint64_t step0,
+          unsigned long long* accept_count, float* __restrict__ log_amp_out) {
+  constexpr int WPW = 32 / LPW, KJ = 4 * KJ4;
+  extern __shared__ __align__(16) float smem[];
+  float* img_s = smem;
+  uint8_t* lut = reinterpret_cast<uint8_t*>(smem + (WS ? im.total : 0));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(lut + 2048);
+  if (WS) bulk_load(img_s, img_g, (uint32_t)im.total * 4u, bar);
+  build_lut(lut);
+  __syncthreads();
+  const Tables t = tables_at(WS ? img_s : img_g, im);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & (LPW - 1), grp = lane / LPW;
+  SitePicker<NW, LPW> picker;
+  picker.setup(im.N, sub);
+  unsigned int n_acc = 0;
+  for (int64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+    const int slot = warp * WPW + grp;
+    const int64_t b = batch * wpc + slot;
+    if ((int64_t)(warp * WPW) >= (int64_t)wpc || batch * wpc + warp * WPW >= B) continue;   // warp-uniform
+    const bool valid = slot < wpc && b < B;
+    const int64_t bb = valid ? b : B - 1;
+    uint64_t s[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s[w] = w < im.words ? packed[bb * im.words + w] : 0ull;
+    float p[KJ], m[KJ], y[KJ];
+    init_state<NW, LPW, KJ4, WS>(t, im, s, sub, p, m, false);
+    int n_up = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) n_up += __popcll(s[w]);
+    const int n_dn = im.N - n_up;
+    const bool can_move = valid && n_up > 0 && n_dn > 0;
+    Philox4 rnd = {0, 0, 0, 0};
+    for (int step = 0; step < n_steps; ++step) {
+      if ((step & (LPW - 1)) == 0)   // lane `sub` draws the block of step + sub
+        rnd = walker_step_random(seed, walker0 + (uint64_t)bb, step0 + (uint64_t)(step + sub));
+      const int src = step & (LPW - 1);
+      const uint32_t r0 = __shfl_sync(CGSVMC_FULL_MASK, rnd.x, src, LPW);
+      const uint32_t r1 = __shfl_sync(CGSVMC_FULL_MASK, rnd.y, src, LPW);
+      const uint32_t r2 = __shfl_sync(CGSVMC_FULL_MASK, rnd.z, src, LPW);
+      // uniformly random up site and uniformly random down site
+      // (argmax / argmin of sigma * u, graph_builders.py:59-65)
+      const int k_up = (int)__umulhi(r0, (uint32_t)n_up);
+      const int k_dn = (int)__umulhi(r1, (uint32_t)n_dn);
+      int up, dn;
+      picker.pick(s, k_up, k_dn, lut, up, dn);
+      if (!can_move) { up = 0; dn = 0; }
+      const float l2 = exchange_log2_ratio<LPW, KJ4, WS, true>(t, im, dn, up, sub, p, m, y);
+      // accept iff |psi'/psi| > sqrt(u)  <=>  (psi'/psi)^2 > u   (strict; NaN rejects)
+      const float prob = ex2_approx(2.f * l2);
+      if (can_move && prob > u32_to_unit(r2)) {
+#pragma unroll
+        for (int k = 0; k < KJ; ++k) {
+          const float r = rcp_approx(y[k] + m[k]);
+          p[k] = y[k] * r;
+          m[k] = m[k] * r;
+        }
+        flip_bit<NW>(s, up);
+        flip_bit<NW>(s, dn);
+        ++n_acc;
+      }
+    }
+    if (valid && sub == 0) {
+#pragma unroll
+      for (int w = 0; w < NW; ++w) if (w < im.words) packed[b * im.words + w] = s[w];
+    }
+    if (log_amp_out != nullptr) {
+      float z = init_state<NW, LPW, KJ4, WS>(t, im, s, sub, p, m, true);
+      z = group_sum<LPW>(z) + ld1<WS>(t.a0);
+      if (valid && sub == 0) log_amp_out[b] = z;
+    }
+  }
+  if (accept_count != nullptr) {
+    unsigned int mine = sub == 0 ? n_acc : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(CGSVMC_FULL_MASK, mine, o);
+    if (lane == 0 && mine) atomicAdd(accept_count, (unsigned long long)mine);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1 + K3 + K4 + K5 in one pass over the walkers ("walker kernel"):
+//   amplitudes z, local energies (operators.py:227-259), weighted sums of
+//   O_b = dz_b/dparams (training.py:545-558, 169-175) and energy statistics.
+// do_eloc / do_grad select the phases; with both, the gradient weights are
+// (1, E_loc) -- one session.run(accumulate_gradients).
+// ---------------------------------------------------------------------------
+struct WalkerArgs {
+  const uint64_t* packed;
+  int64_t B;
+  int wpc;
+  int64_t n_batches;
+  // local energy
+  int do_eloc;
+  const int2* bonds_ij; const float* bonds_jx; const float* bonds_jz; int n_bonds;
+  float* e_loc; float* log_amp; float* diag; float* off;
+  // gradient
+  int do_grad;
+  const float* weights;   // [K][B] or NULL (then weights = (1, E_loc))
+  int K;
+  float* partials;        // [grid][2][P]
+  double* stat_partials;  // [grid][2] or NULL
+  int64_t P;
+};
+
+template <int NW, int LPW, int KJ4, bool WS>
+__global__ void __launch_bounds__(kCtaThreads, 1)
+walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
+  constexpr int WPW = 32 / LPW, KJ = 4 * KJ4, SLOTS = kCtaWarps * WPW;
+  extern __shared__ __align__(16) float smem[];
+  // ---- shared-memory carve-up (mirrors walker_smem_bytes) ----
+  float* img_s = smem;
+  char* cur = reinterpret_cast<char*>(smem + (WS ? im.total : 0));
+  uint8_t* lut = reinterpret_cast<uint8_t*>(cur); cur += 2048;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(cur); cur += 16;
+  int4* bond_s = reinterpret_cast<int4*>(cur); cur += (size_t)(A.do_eloc ? A.n_bonds : 0) * 16;
+  const int list_ld = (A.n_bonds + 7) / 8 * 8;
+  uint16_t* list_s = reinterpret_cast<uint16_t*>(cur); cur += (size_t)(A.do_eloc ? SLOTS * list_ld : 0) * 2;
+  const int NP4 = (im.N + 1 + 3) / 4 * 4;
+  float* T_s = reinterpret_cast<float*>(cur); cur += (size_t)(A.do_grad ? SLOTS * im.HP : 0) * 4;
+  float* ws_s = reinterpret_cast<float*>(cur); cur += (size_t)(A.do_grad ? SLOTS * 2 * NP4 : 0) * 4;
+  float* e_s = reinterpret_cast<float*>(cur);
+
+  if (WS) bulk_load(img_s, img_g, (uint32_t)im.total * 4u, bar);
+  if (A.do_eloc) {
+    for (int k = threadIdx.x; k < A.n_bonds; k += kCtaThreads) {
+      const int2 ij = A.bonds_ij[k];
+      bond_s[k] = make_int4(ij.x, ij.y, __float_as_int(A.bonds_jx[k]), __float_as_int(A.bonds_jz[k]));
+    }
+  }
+  __syncthreads();
+  const Tables t = tables_at(WS ? img_s : img_g, im);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & (LPW - 1), grp = lane / LPW;
+  const int slot = warp * WPW + grp;
+
+  // gradient tiles: 4 rows (sites, row N = the "ones" row of c) x 4 hidden units
+  const int CT = im.HP / 4, RT = NP4 / 4;
+  const int n_tiles = RT * CT;
+  const int n_pass = (n_tiles + kCtaThreads - 1) / kCtaThreads;
+  const bool persist = n_pass == 1;
+  float acc[2][4][4];
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[k][r][c] = 0.f;
+  float acc_a[2] = {0.f, 0.f};   // entries threadIdx.x and threadIdx.x + 512 of the [2][NP4] a-gradient
+  double sum_e = 0.0, sum_e2 = 0.0;   // thread 0 only
+  float* part = A.partials + (size_t)blockIdx.x * 2 * A.P;
+  int batch_no = 0;
+
+  for (int64_t batch = blockIdx.x; batch < A.n_batches; batch += gridDim.x, ++batch_no) {
+    const int64_t b0 = batch * A.wpc;
+    const int n_valid = (int)min((int64_t)A.wpc, A.B - b0);
+    const bool warp_on = warp * WPW < n_valid;
+    if (warp_on) {
+      const bool valid = slot < n_valid;
+      const int64_t b = b0 + slot;
+      const int64_t bb = valid ? b : b0 + n_valid - 1;
+      uint64_t s[NW];
+#pragma unroll
+      for (int w = 0; w < NW; ++w) s[w] = w < im.words ? A.packed[bb * im.words + w] : 0ull;
+      float p[KJ], m[KJ], ydummy[KJ];
+      const bool want_z = A.log_amp != nullptr;
+      float z = init_state<NW, LPW, KJ4, WS>(t, im, s, sub, p, m, want_z);
+      if (want_z) {
+        z = group_sum<LPW>(z) + ld1<WS>(t.a0);
+        if (valid && sub == 0) A.log_amp[b] = z;
+      }
+      float e_val = 0.f;
+      if (A.do_eloc) {
+        // ---- enumerate antiparallel bonds (operators.py:154-167) ----
+        uint16_t* list = list_s + slot * list_ld;
+        float diag = 0.f;
+        int cnt = 0;
+        for (int k0 = 0; k0 < A.n_bonds; k0 += LPW) {
+          const int k = k0 + sub;
+          bool anti = false;
+          if (k < A.n_bonds) {
+            const int4 bd = bond_s[k];
+            anti = spin_bit<NW>(s, bd.x) != spin_bit<NW>(s, bd.y);
+            diag += (anti ? -0.25f : 0.25f) * __int_as_float(bd.w);   // operators.py:165,169
+          }
+          const uint32_t vote = __ballot_sync(CGSVMC_FULL_MASK, anti);
+          const uint32_t gbits = (vote >> (grp * LPW)) & ((1u << LPW) - 1u);
+          if (anti) list[cnt + __popc(gbits & ((1u << sub) - 1u))] = (uint16_t)k;
+          cnt += __popc(gbits);
+        }
+        diag = group_sum<LPW>(diag);
+        __syncwarp();
+        int n_max = cnt;
+#pragma unroll
+        for (int o = LPW; o < 32; o <<= 1) n_max = max(n_max, __shfl_xor_sync(CGSVMC_FULL_MASK, n_max, o));
+        // ---- off-diagonal terms: jx/2 psi(flip)/psi on active bonds only ----
+        float off = 0.f;
+        for (int it = 0; it < n_max; ++it) {
+          const bool act = it < cnt;
+          const int k = act ? (int)list[it] : 0;
+          const int4 bd = bond_s[k];
+          const int bi = spin_bit<NW>(s, bd.x);
+          const int up = bi ? bd.x : bd.y, dn = bi ? bd.y : bd.x;
+          const float l2 = exchange_log2_ratio<LPW, KJ4, WS, false>(t, im, dn, up, sub, p, m, ydummy);
+          if (act) off = fmaf(0.5f * __int_as_float(bd.z), ex2_approx(l2), off);   // operators.py:168-169
+        }
+        e_val = diag + off;
+        if (valid && sub == 0) {
+          if (A.e_loc) A.e_loc[b] = e_val;
+          if (A.diag) A.diag[b] = diag;
+          if (A.off) A.off[b] = off;
+        }
+      }
+      if (A.do_grad && valid) {
+        // stage tanh(theta) = p - m, the signed weights w_k sigma_i and E_loc
+        float w0, w1;
+        if (A.weights != nullptr) {
+          w0 = A.weights[b];
+          w1 = A.K > 1 ? A.weights[A.B + b] : 0.f;
+        } else {
+          w0 = 1.f; w1 = e_val;
+        }
+        float* Trow = T_s + (size_t)slot * im.HP + 4 * sub;
+#pragma unroll
+        for (int q = 0; q < KJ4; ++q)
+          *reinterpret_cast<float4*>(Trow + 4 * LPW * q) =
+              make_float4(p[4 * q] - m[4 * q], p[4 * q + 1] - m[4 * q + 1],
+                          p[4 * q + 2] - m[4 * q + 2], p[4 * q + 3] - m[4 * q + 3]);
+        float* wrow = ws_s + (size_t)slot * 2 * NP4;
+        for (int i = sub; i < NP4; i += LPW) {
+          float sg = 0.f;
+          if (i < im.N) sg = spin_bit<NW>(s, i) ? 1.f : -1.f;
+          else if (i == im.N) sg = 1.f;
+          wrow[i] = w0 * sg;
+          wrow[NP4 + i] = w1 * sg;
+        }
+        if (sub == 0) e_s[slot] = e_val;
+      }
+    }
+    if (A.do_grad) {
+      __syncthreads();
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int tile = threadIdx.x + pass * kCtaThreads;
+        if (tile < n_tiles) {
+          const int rt = tile / CT, ct = tile - rt * CT;
+          if (!persist) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+              for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[k][r][c] = 0.f;
+          }
+          for (int sb = 0; sb < n_valid; ++sb) {
+            const float4 T = *reinterpret_cast<const float4*>(T_s + (size_t)sb * im.HP + 4 * ct);
+            const float4 s0 = *reinterpret_cast<const float4*>(ws_s + (size_t)sb * 2 * NP4 + 4 * rt);
+            const float4 s1 = *reinterpret_cast<const float4*>(ws_s + (size_t)sb * 2 * NP4 + NP4 + 4 * rt);
+            const float tv[4] = {T.x, T.y, T.z, T.w};
+            const float a0v[4] = {s0.x, s0.y, s0.z, s0.w};
+            const float a1v[4] = {s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                acc[0][r][c] = fmaf(a0v[r], tv[c], acc[0][r][c]);
+                acc[1][r][c] = fmaf(a1v[r], tv[c], acc[1][r][c]);
+              }
+          }
+          if (!persist) {
+            // row i < N: W[i][j]; row N: c[j]
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const int i = 4 * rt + r;
+                if (i > im.N) continue;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const int j = 4 * ct + c;
+                  if (j >= im.H) continue;
+                  float* dst = part + (size_t)k * A.P + im.N + 1 + (size_t)i * im.H + j;
+                  *dst = batch_no == 0 ? acc[k][r][c] : *dst + acc[k][r][c];
+                }
+              }
+          }
+        }
+      }
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int e = threadIdx.x + h2 * kCtaThreads;
+        if (e < 2 * NP4)
+          for (int sb = 0; sb < n_valid; ++sb) acc_a[h2] += ws_s[(size_t)sb * 2 * NP4 + e];
+      }
+      if (threadIdx.x == 0 && A.stat_partials != nullptr) {
+        for (int sb = 0; sb < n_valid; ++sb) {
+          const double e = (double)e_s[sb];
+          sum_e += e;
+          sum_e2 += e * e;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (A.do_grad) {
+    if (persist && threadIdx.x < n_tiles) {
+      const int rt = threadIdx.x / CT, ct = threadIdx.x - rt * CT;
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int i = 4 * rt + r;
+          if (i > im.N) continue;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int j = 4 * ct + c;
+            if (j < im.H) part[(size_t)k * A.P + im.N + 1 + (size_t)i * im.H + j] = acc[k][r][c];
+          }
+        }
+    }
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int e = threadIdx.x + h2 * kCtaThreads;
+      if (e < 2 * NP4) {
+        const int k = e / NP4, i = e - k * NP4;
+        if (i <= im.N) part[(size_t)k * A.P + i] = acc_a[h2];   // a_i (i < N) and a0 (i == N)
+      }
+    }
+    if (threadIdx.x == 0 && A.stat_partials != nullptr) {
+      A.stat_partials[2 * blockIdx.x] = sum_e;
+      A.stat_partials[2 * blockIdx.x + 1] = sum_e2;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers of one (NW, LPW, KJ4) variant
+// ---------------------------------------------------------------------------
+template <typename F>
+inline int opt_in_smem(F kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(smem)");
+  }
+  return CGSVMC_OK;
+}
+
+template <int NW, int LPW, int KJ4>
+int launch_mc_variant(const Plan& pl, const float* img, uint64_t* packed, int64_t B, int n_steps,
+                      uint64_t seed, uint64_t walker0, uint64_t step0,
+                      unsigned long long* accept_count, float* log_amp_out, cudaStream_t st) {
+  if (pl.ws) {
+    auto kern = mc_kernel<NW, LPW, KJ4, true>;
+    if (int rc = opt_in_smem(kern, pl.mc_smem)) return rc;
+    kern<<<pl.grid, kCtaThreads, pl.mc_smem, st>>>(pl.im, img, packed, B, pl.wpc, pl.n_batches, n_steps,
+                                                  seed, walker0, step0, accept_count, log_amp_out);
+  } else {
+    auto kern = mc_kernel<NW, LPW, KJ4, false>;
+    if (int rc = opt_in_smem(kern, pl.mc_smem)) return rc;
+    kern<<<pl.grid, kCtaThreads, pl.mc_smem, st>>>(pl.im, img, packed, B, pl.wpc, pl.n_batches, n_steps,
+                                                  seed, walker0, step0, accept_count, log_amp_out);
+  }
+  return cuda_fail(cudaGetLastError(), "rbm2 mc launch");
+}
+
+template <int NW, int LPW, int KJ4>
+int launch_walker_variant(const Plan& pl, const float* img, const WalkerArgs& A, cudaStream_t st) {
+  if (pl.ws) {
+    auto kern = walker_kernel<NW, LPW, KJ4, true>;
+    if (int rc = opt_in_smem(kern, pl.walker_smem)) return rc;
+    kern<<<pl.grid, kCtaThreads, pl.walker_smem, st>>>(pl.im, img, A);
+  } else {
+    auto kern = walker_kernel<NW, LPW, KJ4, false>;
+    if (int rc = opt_in_smem(kern, pl.walker_smem)) return rc;
+    kern<<<pl.grid, kCtaThreads, pl.walker_smem, st>>>(pl.im, img, A);
+  }
+  return cuda_fail(cudaGetLastError(), "rbm2 walker launch");
+}
+
+#define RBM2_VARIANT_SWITCH(NWV, CALL)                       \
+  switch (pl.lpw * 16 + pl.kj4) {                            \
+    case 8 * 16 + 1: return CALL(NWV, 8, 1);                 \
+    case 8 * 16 + 2: return CALL(NWV, 8, 2);                 \
+    case 8 * 16 + 3: return CALL(NWV, 8, 3);                 \
+    case 8 * 16 + 4: return CALL(NWV, 8, 4);                 \
+    case 8 * 16 + 5: return CALL(NWV, 8, 5);                 \
+    case 16 * 16 + 3: return CALL(NWV, 16, 3);               \
+    case 16 * 16 + 4: return CALL(NWV, 16, 4);               \
+    default: break;                                          \
+  }                                                          \
+  set_error("rbm2: unsupported variant");                    \
+  return CGSVMC_ERR_UNSUPPORTED;
+
+}  // namespace rbm2
+}  // namespace cgsvmc

@@ -187,6 +187,18 @@ int launch_flip_enum(const cgsvmc_ham* h, const uint64_t* packed, int64_t B, uin
   return cuda_fail(cudaGetLastError(), "flip_enum launch");
 }
 
+__global__ void fill_kernel(float* __restrict__ dst, int64_t n, float value) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+       e += (int64_t)gridDim.x * blockDim.x) dst[e] = value;
+}
+
+int launch_fill(float* dst, int64_t n, float value, cudaStream_t s) {
+  if (n <= 0) return CGSVMC_OK;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 1024);
+  fill_kernel<<<blocks, 256, 0, s>>>(dst, n, value);
+  return cuda_fail(cudaGetLastError(), "fill launch");
+}
+
 int launch_energy_stats(const float* e, int64_t B, double* stats, cudaStream_t s) {
   if (B == 0) return CGSVMC_OK;
   energy_stats_kernel<<<blocks_for(B, kThreads * 8), kThreads, 0, s>>>(e, B, stats);

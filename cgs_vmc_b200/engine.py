@@ -65,17 +65,11 @@ class EnergyGradientSums:
     self.n_batches = 0
 
   def accumulate(self, ham, packed):
-    """session.run(accumulate_gradients), training.py:539-558 for one batch:
-    E_loc (written straight into the weight row), then S = [sum O, sum E O]
-    and the energy statistics."""
-    lib = _native.load()
-    b = packed.shape[0]
+    """session.run(accumulate_gradients), training.py:539-558 for one batch in
+    one library call: E_loc, S = [sum O, sum E O] and the energy statistics."""
     e_row = self.weights[1]
-    _native.check(lib.cgsvmc_local_energy(
-        self.ansatz._handle, ham._handle, _native._ptr(packed), b, _native._ptr(e_row),
-        _native._ptr(self.log_amp), None, None, _native._stream()))
-    self.ansatz.weighted_grad_sum(packed, self.weights, out=self.sums)
-    _native.energy_stats(e_row, self.stats)
+    self.ansatz.accumulate(ham, packed, self.sums, self.stats, e_loc_out=e_row,
+                           log_amp_out=self.log_amp)
     self.n_batches += 1
     return e_row
 

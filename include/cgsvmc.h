@@ -195,6 +195,19 @@ int cgsvmc_weighted_grad_sum(const cgsvmc_ansatz* ansatz,
                              int64_t n_walkers, int32_t n_weights, float* out,
                              void* stream);
 
+/* Replaces one session.run(accumulate_gradients) of
+ * EnergyGradientOptimizer (training.py:539-558, 615) in a single pass over the
+ * walkers: psi and local energy of every walker (operators.py:249-259), then
+ *   sums[0, :] += sum_b O_b,  sums[1, :] += sum_b E_b O_b   (O_b = d z_b / d params)
+ *   stats     += { sum E, sum E^2, B, 0 }                   (double [4])
+ * e_loc_out / log_amp_out (float32 [B]) are optional.  Equivalent to
+ * cgsvmc_local_energy + cgsvmc_weighted_grad_sum with weights (1, E_loc) +
+ * cgsvmc_energy_stats; the walker state (theta) is built once instead of
+ * three times. */
+int cgsvmc_accumulate(const cgsvmc_ansatz* ansatz, const cgsvmc_ham* ham,
+                      const uint64_t* packed, int64_t n_walkers, float* e_loc_out,
+                      float* log_amp_out, float* sums, double* stats, void* stream);
+
 /* Replaces tf.metrics.mean(local_energy) bookkeeping (training.py:555):
  * stats (double [4], device) += { sum e, sum e^2, B, 0 }. */
 int cgsvmc_energy_stats(const float* e_loc, int64_t n_walkers, double* stats,

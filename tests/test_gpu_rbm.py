@@ -41,6 +41,9 @@ RBM_SHAPES = [
     oansatz.AnsatzSpec('rbm', 256, num_layers=0, layer_size=256),   # C5, W in global
     oansatz.AnsatzSpec('rbm', 16, num_layers=0, layer_size=7),      # ragged H
     oansatz.AnsatzSpec('rbm', 70, num_layers=0, layer_size=150),
+    oansatz.AnsatzSpec('rbm', 150, num_layers=0, layer_size=64),    # 3 words per walker
+    oansatz.AnsatzSpec('rbm', 40, num_layers=0, layer_size=180),    # 16 lanes per walker
+    oansatz.AnsatzSpec('rbm', 12, num_layers=0, layer_size=32),
 ]
 
 
@@ -426,6 +429,57 @@ def test_swo_gradient_golden(native):
   grad = a.weighted_grad_sum(packed, w)[0].cpu().numpy()
   ref = g['swo_gradient']
   assert np.linalg.norm(grad - ref) <= 5e-4 * np.linalg.norm(ref) + 1e-6
+
+
+@pytest.mark.parametrize('spec', [RBM_SHAPES[0], RBM_SHAPES[2], RBM_SHAPES[3], RBM_SHAPES[6]],
+                         ids=lambda s: 'N%d_H%d' % (s.n_sites, s.layer_size))
+def test_accumulate_equals_separate_calls(native, spec):
+  """cgsvmc_accumulate == local_energy + weighted_grad_sum(1, E) + energy_stats
+  (training.py:539-558), including the += semantics and ragged batch sizes."""
+  from gpu_util import packed_cuda
+  n = spec.n_sites
+  ij, jx, jz = lattices.heisenberg_couplings(lattices.chain_bonds(n), -1.0, 1.0)
+  for batch in (1, 5, 333, 2500):
+    a, params, cfg = _setup(spec, seed=31 + batch, batch=batch, scale=0.7)
+    ham = native.Hamiltonian(ij, jx, jz, n)
+    packed = packed_cuda(cfg)
+    e, z = a.local_energy(ham, packed)
+    w = torch.stack([torch.ones_like(e), e]).contiguous()
+    ref = a.weighted_grad_sum(packed, w)
+    st_ref = native.energy_stats(e)
+    sums = torch.zeros(2, a.num_params, device='cuda')
+    stats = torch.zeros(4, dtype=torch.float64, device='cuda')
+    e_out = torch.empty(batch, device='cuda')
+    z_out = torch.empty(batch, device='cuda')
+    a.accumulate(ham, packed, sums, stats, e_loc_out=e_out, log_amp_out=z_out)
+    assert torch.equal(e_out, e) and torch.equal(z_out, z)
+    scale = ref.abs().max().item() + 1.0
+    assert float((sums - ref).abs().max()) <= 2e-6 * scale * max(1.0, batch ** 0.5)
+    np.testing.assert_allclose(stats.cpu().numpy(), st_ref.cpu().numpy(), rtol=1e-12)
+    a.accumulate(ham, packed, sums, stats)
+    assert float((sums - 2 * ref).abs().max()) <= 4e-6 * scale * max(1.0, batch ** 0.5)
+    assert stats[2].item() == 2 * batch
+
+
+def test_accumulate_full_size_sharding_invariance(native):
+  """Size-independent property at the C2 bench size: accumulating 8192 walkers
+  in one call equals accumulating four shards of 2048 (the all-reduce sum of
+  the multi-GPU run) up to float32 reassociation."""
+  spec = _c2_spec()
+  a, params, _ = _setup(spec, seed=3, batch=1)
+  ij, jx, jz = lattices.heisenberg_couplings(lattices.square_nn_bonds(6))
+  ham = native.Hamiltonian(ij, jx, jz, 36)
+  packed = native.random_configs(8192, 36, seed=6)
+  sums = torch.zeros(2, a.num_params, device='cuda')
+  stats = torch.zeros(4, dtype=torch.float64, device='cuda')
+  a.accumulate(ham, packed, sums, stats)
+  sums4 = torch.zeros_like(sums)
+  stats4 = torch.zeros_like(stats)
+  for lo in range(0, 8192, 2048):
+    a.accumulate(ham, packed[lo:lo + 2048].contiguous(), sums4, stats4)
+  scale = sums.abs().max().item()
+  assert float((sums - sums4).abs().max()) <= 2e-5 * scale
+  np.testing.assert_allclose(stats.cpu().numpy(), stats4.cpu().numpy(), rtol=1e-10)
 
 
 def test_energy_stats(native):
