@@ -28,6 +28,7 @@ WORKLOAD = 'C2: 6x6 square-lattice Heisenberg (72 NN bonds, jx=-1, jz=1), rbm H=
 N_SITES, SIZE, HIDDEN, WALKERS = 36, 6, 144, 8192
 SWEEP_STEPS = N_SITES            # num_monte_carlo_sweeps (1) * num_sites
 SEED = 0xC65
+EPOCH_BATCHES = 50               # num_batches_per_epoch default (utils.py:132-138)
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -191,6 +192,7 @@ def run_ours(args, rank, world, local_rank):
   state.mc_steps(ansatz, 20 * N_SITES)                                 # equilibrate
 
   launches = [0]
+  counter = [0]
   ev = lambda: torch.cuda.Event(enable_timing=True)
 
   def step(events=None):
@@ -200,11 +202,16 @@ def run_ours(args, rank, world, local_rank):
     if events: events[2].record()
     state.mc_steps(ansatz, SWEEP_STEPS)
     if events: events[3].record()
-    launches[0] += 5   # prep, walker kernel, reduce; prep, mc kernel
-    if world > 1:
+    launches[0] += 3   # walker kernel, reduce, mc kernel (parameter tables are cached)
+    counter[0] += 1
+    if world > 1 and counter[0] % EPOCH_BATCHES == 0:
+      # epoch end (training.py:619-620): the only exchange of the sharded run --
+      # accumulation is linear, so the [2P + 4] sums are all-reduced once per
+      # epoch, not once per batch
       payload[:2 * P].copy_(sums.sums.reshape(-1))
       payload[2 * P:].copy_(sums.stats.float())
       dist.all_reduce(payload)
+      sums.reset()
 
   for _ in range(max(args.warmup, 3)):
     step()
@@ -241,26 +248,53 @@ def run_ours(args, rank, world, local_rank):
   host_cfg = torch.empty(B, N_SITES, dtype=torch.float32).pin_memory()
   host_cfg.copy_(state.configs().cpu())
   host_stats = torch.empty(4, dtype=torch.float64).pin_memory()
+  host_sums = torch.empty(2, P, dtype=torch.float32).pin_memory()
   dev_cfg = torch.empty(B, N_SITES, dtype=torch.float32, device=dev)
 
-  def e2e_step():
-    dev_cfg.copy_(host_cfg, non_blocking=True)                    # H2D inputs
-    state.packed = _native.pack_configs(dev_cfg)
-    step()
-    _native.unpack_configs(state.packed, N_SITES, out=dev_cfg)
-    host_cfg.copy_(dev_cfg, non_blocking=True)                    # D2H state
-    host_stats.copy_(sums.stats, non_blocking=True)               # D2H result
-    torch.cuda.current_stream().synchronize()
+  copy_stream = torch.cuda.Stream(device=dev)
+  dev_cfgs = [dev_cfg, torch.empty_like(dev_cfg)]
+  h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
+  consumed = [torch.cuda.Event(), torch.cuda.Event()]
+  results_ready = [torch.cuda.Event(), torch.cuda.Event()]
+  host_out = [(host_sums, host_stats), (torch.empty_like(host_sums).pin_memory(),
+                                        torch.empty_like(host_stats).pin_memory())]
+  main = torch.cuda.current_stream()
 
-  for _ in range(3):
-    e2e_step()
+  def e2e_issue(k):
+    """The step as a host-side caller sees it: the float32 [B, N] configuration
+    tensor of the reference (graph_builders.py:92-125) comes from pinned host
+    memory, the estimator sums and energy statistics go back to the host.  The
+    upload of batch k runs on a copy stream and overlaps the compute of batch
+    k - 1 (double buffering); every step's copies are inside the timed region."""
+    i = k & 1
+    with torch.cuda.stream(copy_stream):
+      copy_stream.wait_event(consumed[i])
+      dev_cfgs[i].copy_(host_cfg, non_blocking=True)              # H2D inputs
+      h2d_done[i].record(copy_stream)
+    main.wait_event(h2d_done[i])
+    state.packed = _native.pack_configs(dev_cfgs[i])
+    consumed[i].record(main)
+    step()
+    host_out[i][0].copy_(sums.sums, non_blocking=True)            # D2H result: [2, P] sums
+    host_out[i][1].copy_(sums.stats, non_blocking=True)           # D2H result: energy statistics
+    results_ready[i].record(main)
+
+  def e2e_run(n):
+    for k in range(n):
+      e2e_issue(k)
+      if k > 0:
+        results_ready[(k - 1) & 1].synchronize()                  # host consumes step k - 1
+    results_ready[(n - 1) & 1].synchronize()
+
+  for ev_ in consumed:
+    ev_.record(main)
+  e2e_run(4)
   torch.cuda.synchronize()
   if world > 1:
     dist.barrier()
   e0, e1 = ev(), ev()
   e0.record()
-  for _ in range(args.steps):
-    e2e_step()
+  e2e_run(args.steps)
   e1.record()
   torch.cuda.synchronize()
   e2e_total = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
@@ -332,7 +366,8 @@ def run_ours(args, rank, world, local_rank):
                  'n_bonds': 72, 'n_params': P,
                  'l2': 'flushed: %d MiB memset between steps, outside the per-step CUDA-event pairs' % (L2_FLUSH_BYTES >> 20),
                  'parallelism': 'walkers sharded, params replicated' + (
-                     ', all-reduce of [2P+4] floats per step' if world > 1 else '')},
+                     ', one all-reduce of [2P+4] floats per epoch of %d steps' % EPOCH_BATCHES
+                     if world > 1 else '')},
       'kernel_ms': {k: v * 1e3 for k, v in shares.items()},
       'kernel_rates': {'sampler_walker_steps_per_sec': B * SWEEP_STEPS / float(t_mc.mean()),
                        'accumulate_eloc_evals_per_sec': B / float(t_acc.mean())},
@@ -340,7 +375,7 @@ def run_ours(args, rank, world, local_rank):
       'e2e': {'value': walkers_total * SWEEP_STEPS * args.steps / e2e_s, 'unit': 'walker-steps/s',
               'eloc_evals_per_sec': walkers_total * args.steps / e2e_s,
               'ms_per_step': e2e_s / args.steps * 1e3,
-              'h2d_bytes_per_step': B * N_SITES * 4, 'd2h_bytes_per_step': B * N_SITES * 4 + 32},
+              'h2d_bytes_per_step': B * N_SITES * 4, 'd2h_bytes_per_step': 2 * P * 4 + 32},
       'gpu_launches': n_launch,
       'clocks': clocks,
       'wall_s_timed_region': wall,

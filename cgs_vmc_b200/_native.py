@@ -20,7 +20,8 @@ ACTIVATIONS = {'relu': 0, 'tanh': 1, 'sigmoid': 2, 'identity': 3, 'cos': 4,
 EXPORTS = [
     'cgsvmc_version', 'cgsvmc_last_error', 'cgsvmc_ansatz_create',
     'cgsvmc_ansatz_destroy', 'cgsvmc_ansatz_num_params',
-    'cgsvmc_ansatz_bind_params', 'cgsvmc_ham_create', 'cgsvmc_ham_destroy',
+    'cgsvmc_ansatz_bind_params', 'cgsvmc_ansatz_track_params',
+    'cgsvmc_ansatz_params_changed', 'cgsvmc_ham_create', 'cgsvmc_ham_destroy',
     'cgsvmc_pack_configs', 'cgsvmc_unpack_configs', 'cgsvmc_random_configs',
     'cgsvmc_log_amp', 'cgsvmc_mc_steps', 'cgsvmc_mc_step_replay',
     'cgsvmc_flip_enum', 'cgsvmc_local_energy', 'cgsvmc_weighted_grad_sum',
@@ -59,6 +60,8 @@ def load():
   lib.cgsvmc_ansatz_num_params.argtypes = [vp]
   lib.cgsvmc_ansatz_num_params.restype = i64
   lib.cgsvmc_ansatz_bind_params.argtypes = [vp, vp]
+  lib.cgsvmc_ansatz_track_params.argtypes = [vp, ctypes.c_int]
+  lib.cgsvmc_ansatz_params_changed.argtypes = [vp]
   lib.cgsvmc_ham_create.argtypes = [vp, vp, vp, i32, i32, ctypes.POINTER(vp)]
   lib.cgsvmc_ham_destroy.argtypes = [vp]
   lib.cgsvmc_pack_configs.argtypes = [vp, i64, i32, vp, vp]
@@ -142,6 +145,10 @@ class Ansatz:
     self.num_params = int(lib.cgsvmc_ansatz_num_params(handle))
     self.params = torch.zeros(self.num_params, dtype=torch.float32, device=self.device)
     check(lib.cgsvmc_ansatz_bind_params(handle, _ptr(self.params)))
+    # derived tables are rebuilt only when torch reports an in-place change of
+    # the parameter buffer (its version counter covers views as well)
+    check(lib.cgsvmc_ansatz_track_params(handle, 1))
+    self._seen_version = None
 
   def set_params(self, flat):
     """Copies a flat parameter vector (layout of include/cgsvmc.h) in place."""
@@ -161,6 +168,12 @@ class Ansatz:
     except Exception:   # interpreter shutdown
       pass
 
+  def _sync_params(self):
+    v = self.params._version
+    if v != self._seen_version:
+      check(load().cgsvmc_ansatz_params_changed(self._handle))
+      self._seen_version = v
+
   # ---- compute entry points -------------------------------------------
   def log_amp(self, packed, out=None):
     b = packed.shape[0]
@@ -172,6 +185,7 @@ class Ansatz:
 
   def mc_steps(self, packed, n_steps, seed, walker_id0=0, step0=0,
                accept_count=None, log_amp_out=None):
+    self._sync_params()
     b = packed.shape[0]
     _want(packed, torch.int64, (b, n_words(self.n_sites)), 'packed')
     if accept_count is not None:
@@ -198,6 +212,7 @@ class Ansatz:
     return down, up, log_ratio, accept
 
   def local_energy(self, ham, packed, want_parts=False):
+    self._sync_params()
     b = packed.shape[0]
     _want(packed, torch.int64, (b, n_words(self.n_sites)), 'packed')
     dev = packed.device
@@ -210,6 +225,7 @@ class Ansatz:
     return (e, z, diag, off) if want_parts else (e, z)
 
   def weighted_grad_sum(self, packed, weights, out=None):
+    self._sync_params()
     b = packed.shape[0]
     _want(packed, torch.int64, (b, n_words(self.n_sites)), 'packed')
     if weights.dim() == 1:
@@ -228,6 +244,7 @@ class Ansatz:
   def accumulate(self, ham, packed, sums, stats, e_loc_out=None, log_amp_out=None):
     """One session.run(accumulate_gradients) (training.py:539-558): sums [2, P]
     += (sum_b O_b, sum_b E_b O_b), stats float64[4] += (sum E, sum E^2, B, 0)."""
+    self._sync_params()
     b = packed.shape[0]
     _want(packed, torch.int64, (b, n_words(self.n_sites)), 'packed')
     _want(sums, torch.float32, (2, self.num_params), 'sums')

@@ -154,6 +154,20 @@ int64_t cgsvmc_ansatz_num_params(const cgsvmc_ansatz* a) { return a == nullptr ?
 int cgsvmc_ansatz_bind_params(cgsvmc_ansatz* a, const float* params_dev) {
   if (a == nullptr || params_dev == nullptr) return invalid("bind_params: NULL argument");
   a->params = params_dev;
+  a->tables_valid = false;
+  return CGSVMC_OK;
+}
+
+int cgsvmc_ansatz_track_params(cgsvmc_ansatz* a, int enabled) {
+  if (a == nullptr) return invalid("track_params: NULL argument");
+  a->track_params = enabled != 0;
+  a->tables_valid = false;
+  return CGSVMC_OK;
+}
+
+int cgsvmc_ansatz_params_changed(cgsvmc_ansatz* a) {
+  if (a == nullptr) return invalid("params_changed: NULL argument");
+  a->tables_valid = false;
   return CGSVMC_OK;
 }
 

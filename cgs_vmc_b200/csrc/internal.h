@@ -26,6 +26,8 @@ struct cgsvmc_ansatz {
   size_t scratch_bytes = 0;
   float* tables = nullptr;         // owned: derived parameter image of the rbm2 kernels
   size_t tables_bytes = 0;
+  bool tables_valid = false;       // tables match the bound parameters
+  bool track_params = false;       // rebuild tables only after bind_params / params_changed
   float* acc_weights = nullptr;    // owned: [2, B] weight rows of cgsvmc_accumulate (tile networks)
   size_t acc_weights_bytes = 0;
 };

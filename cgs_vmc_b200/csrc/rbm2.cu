@@ -1,6 +1,7 @@
 // Pure-RBM fast path, host side: parameter-image build, launch planning,
 // deterministic cross-CTA reduction.  Kernels: rbm2_impl.cuh.
 #include <algorithm>
+#include <cstdlib>
 
 #include "rbm2_impl.cuh"
 
@@ -50,27 +51,37 @@ prep_kernel(Image im, const float* __restrict__ a, const float* __restrict__ a0,
   }
 }
 
-// out[f] += sum_c partials[c][f] in a fixed order; 64 outputs x 4 CTA slices
-// per block.  Also folds the per-CTA energy sums into stats.
+// out[f] += sum_c partials[c][f] in a fixed order: 32 outputs x 8 CTA slices
+// per block (the partials were just written and sit in L2).  Also folds the
+// per-CTA energy sums into stats.
 __global__ void __launch_bounds__(256)
 reduce_kernel(const float* __restrict__ partials, int n_cta, int64_t stride, int64_t n_out,
               float* __restrict__ out, const double* __restrict__ stat_partials, int64_t B,
               double* __restrict__ stats) {
-  __shared__ float sm[4][64];
-  const int col = threadIdx.x & 63, slice = threadIdx.x >> 6;
-  const int64_t f = (int64_t)blockIdx.x * 64 + col;
+  __shared__ float sm[8][32];
+  const int col = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int64_t f = (int64_t)blockIdx.x * 32 + col;
   float s = 0.f;
-  if (f < n_out)
-    for (int c = slice; c < n_cta; c += 4) s += partials[(size_t)c * stride + f];
+  if (f < n_out) {
+    const float* src = partials + f;
+#pragma unroll 4
+    for (int c = slice; c < n_cta; c += 8) s += __ldcg(src + (size_t)c * stride);
+  }
   sm[slice][col] = s;
   __syncthreads();
-  if (slice == 0 && f < n_out) out[f] += (sm[0][col] + sm[1][col]) + (sm[2][col] + sm[3][col]);
-  if (blockIdx.x == 0 && threadIdx.x == 0 && stat_partials != nullptr) {
+  if (slice == 0 && f < n_out)
+    out[f] += ((sm[0][col] + sm[1][col]) + (sm[2][col] + sm[3][col])) +
+              ((sm[4][col] + sm[5][col]) + (sm[6][col] + sm[7][col]));
+  if (blockIdx.x == 0 && threadIdx.x < 32 && stat_partials != nullptr) {
     double e = 0.0, e2 = 0.0;
-    for (int c = 0; c < n_cta; ++c) { e += stat_partials[2 * c]; e2 += stat_partials[2 * c + 1]; }
-    stats[0] += e;
-    stats[1] += e2;
-    stats[2] += (double)B;
+    for (int c = threadIdx.x; c < n_cta; c += 32) { e += stat_partials[2 * c]; e2 += stat_partials[2 * c + 1]; }
+    e = warp_sum(e);
+    e2 = warp_sum(e2);
+    if (threadIdx.x == 0) {
+      stats[0] += e;
+      stats[1] += e2;
+      stats[2] += (double)B;
+    }
   }
 }
 
@@ -92,7 +103,7 @@ Image make_image(int N, int H, int HP) {
 size_t walker_smem_bytes(const Image& im, int slots, bool ws, bool do_eloc, int n_bonds, bool do_grad) {
   const int NP4 = round_up(im.N + 1, 4);
   size_t b = ws ? (size_t)im.total * 4 : 0;
-  b += 2048 + 16;
+  b += 16;
   if (do_eloc) b += (size_t)n_bonds * 16 + (size_t)slots * round_up(n_bonds, 8) * 2;
   if (do_grad) b += (size_t)slots * im.HP * 4 + (size_t)slots * 2 * NP4 * 4;
   b += (size_t)slots * 4;
@@ -105,12 +116,20 @@ bool base_plan(const cgsvmc_ansatz* a, int64_t B, Plan* pl) {
   if (d.kind != CGSVMC_ANSATZ_RBM || d.num_layers != 0) return false;
   if (d.layer_size < 1 || d.layer_size > 256 || d.n_sites > CGSVMC_MAX_SITES) return false;
   const int H = d.layer_size;
-  int HP = round_up(H, 32);
-  if (HP <= 160) { pl->lpw = 8; pl->kj4 = HP / 32; }
-  else { HP = round_up(H, 64); pl->lpw = 16; pl->kj4 = HP / 64; }
+  const int HP = round_up(H, 32);
+  pl->kjv = HP / 32;
+  // 8 lanes per walker (four walkers per warp) while the state fits 128
+  // registers, else 16; measured on B200 at C2: 8 lanes 100 us / step, 16 lanes
+  // 110 us (profiles/r01e_*).  CGSVMC_RBM2_LPW=16 forces the 16-lane layout.
+  static const int forced_lpw = [] {
+    const char* e = getenv("CGSVMC_RBM2_LPW");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  pl->lpw = (forced_lpw != 16 && pl->kjv <= 5) ? 8 : 16;
   pl->im = make_image(d.n_sites, H, HP);
   pl->nw = n_words(d.n_sites) == 3 ? 4 : n_words(d.n_sites);
-  const int wpw = 32 / pl->lpw, slots = kCtaWarps * wpw;
+  const int wpw = 32 / pl->lpw, slots = variant_slots(pl->lpw, pl->kjv);
+  pl->slots = slots;
   const int64_t per_sm = std::max<int64_t>(1, (B + a->num_sms - 1) / a->num_sms);
   const int64_t rounds = (per_sm + slots - 1) / slots;
   int64_t wpc = (per_sm + rounds - 1) / rounds;
@@ -132,11 +151,14 @@ int build_image(cgsvmc_ansatz* a, const Plan& pl, cudaStream_t st) {
     }
     if (int rc = cuda_fail(cudaMalloc(&a->tables, bytes), "tables alloc")) return rc;
     a->tables_bytes = bytes;
+    a->tables_valid = false;
   }
+  if (a->track_params && a->tables_valid) return CGSVMC_OK;
   const float* p = a->params;
   const int blocks = pl.im.N + (pl.im.HP + 127) / 128;
   prep_kernel<<<blocks, 128, 0, st>>>(pl.im, p + a->offsets[0], p + a->offsets[1], p + a->offsets[2],
                                       p + a->offsets[3], a->tables);
+  a->tables_valid = true;
   return cuda_fail(cudaGetLastError(), "rbm2 prep launch");
 }
 
@@ -148,7 +170,7 @@ using namespace rbm2;
 bool rbm2_supported(const cgsvmc_ansatz* a, const cgsvmc_ham* h) {
   Plan pl;
   if (!base_plan(a, 1, &pl)) return false;
-  const int slots = kCtaWarps * (32 / pl.lpw);
+  const int slots = pl.slots;
   const int nb = h != nullptr ? h->n_bonds : 0;
   if (nb >= 65535) return false;
   // the largest launch (accumulate) must fit with the image left in global memory
@@ -177,7 +199,7 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
   Plan pl;
   if (!base_plan(a, B, &pl)) { set_error("rbm2: unsupported ansatz"); return CGSVMC_ERR_UNSUPPORTED; }
   const bool do_eloc = h != nullptr;
-  const int slots = kCtaWarps * (32 / pl.lpw);
+  const int slots = pl.slots;
   const int nb = do_eloc ? h->n_bonds : 0;
   pl.ws = walker_smem_bytes(pl.im, slots, true, do_eloc, nb, do_grad) <= (size_t)a->max_smem_optin;
   pl.walker_smem = walker_smem_bytes(pl.im, slots, pl.ws, do_eloc, nb, do_grad);
@@ -212,7 +234,7 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
   if (rc) return rc;
   if (do_grad) {
     const int64_t n_out = (int64_t)K * P;
-    const int blocks = (int)((n_out + 63) / 64);
+    const int blocks = (int)((n_out + 31) / 32);
     reduce_kernel<<<blocks, 256, 0, st>>>(A.partials, pl.grid, 2 * P, n_out, out, A.stat_partials, B, stats);
     return cuda_fail(cudaGetLastError(), "rbm2 reduce launch");
   }

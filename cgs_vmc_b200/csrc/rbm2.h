@@ -6,9 +6,6 @@
 namespace cgsvmc {
 namespace rbm2 {
 
-constexpr int kCtaThreads = 512;
-constexpr int kCtaWarps = 16;
-
 // Parameter image (float offsets), built by prep_kernel from the flat
 // parameter buffer: [2W | e^{4W} | e^{-4W} | A2 | base | a | a0].
 struct Image {
@@ -19,7 +16,8 @@ struct Image {
 
 struct Plan {
   Image im;
-  int nw, lpw, kj4;
+  int nw, lpw, kjv;     // words per walker, lanes per walker, HP / 32
+  int slots;             // walkers per CTA batch the variant can hold
   bool ws;               // image in shared memory
   int wpc;               // walkers per CTA batch
   int64_t n_batches;

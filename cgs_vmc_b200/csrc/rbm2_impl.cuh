@@ -21,10 +21,11 @@
 // (p' = p y / n, m' = m / n, n = p y + m).  All tables live in shared memory
 // (copied once per CTA with a TMA bulk copy) when they fit.
 //
-// Mapping: LPW lanes own one walker (LPW = 8: four walkers per warp, 16: two),
-// lane `sub` holds hidden units j = 4 (sub + LPW q) + c, q < KJ4, c < 4, so a
-// table row is read with LDS.128 in phases of one walker each (conflict-free).
-// One persistent CTA of 512 threads per SM.
+// Mapping: LPW lanes own one walker (LPW = 8: four walkers per warp, 16: two);
+// with VW = 32 / LPW lane `sub` holds hidden units j = VW (sub + LPW q) + c,
+// q < KJV = HP / 32, c < VW, so a table row is read with LDS.128 / LDS.64 in
+// phases of one walker (128 contiguous bytes) each -- conflict-free.
+// One persistent CTA per SM (1024 threads when the state fits 64 registers).
 #pragma once
 #include "common.cuh"
 #include "internal.h"
@@ -56,10 +57,21 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return r;
 }
 
-template <bool WS>
-__device__ __forceinline__ float4 ld4(const float* p) {
-  if (WS) return *reinterpret_cast<const float4*>(p);
-  return __ldg(reinterpret_cast<const float4*>(p));
+// VW consecutive floats (VW = 4: LDS.128, 2: LDS.64)
+template <int VW, bool WS>
+__device__ __forceinline__ void ldv(const float* p, float (&v)[VW]) {
+  if (VW == 4) {
+    const float4 x = WS ? *reinterpret_cast<const float4*>(p) : __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = x.x; v[1] = x.y; v[2 % VW] = x.z; v[3 % VW] = x.w;
+  } else {
+    const float2 x = WS ? *reinterpret_cast<const float2*>(p) : __ldg(reinterpret_cast<const float2*>(p));
+    v[0] = x.x; v[1] = x.y;
+  }
+}
+template <int VW>
+__device__ __forceinline__ void stv(float* p, const float (&v)[VW]) {
+  if (VW == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2 % VW], v[3 % VW]);
+  else *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
 }
 template <bool WS>
 __device__ __forceinline__ float ld1(const float* p) {
@@ -149,15 +161,18 @@ __device__ __forceinline__ int spin_bit(const uint64_t (&s)[NW], int site) {
 // theta_j = base_j + sum_{i up} 2 W[i][j];  p = 1 / (1 + e^{-2 theta}),
 // m = 1 / (1 + e^{2 theta}).  Optionally returns this lane's share of
 // sum_j log cosh theta_j + a . sigma (group_sum + a0 gives z).
-template <int NW, int LPW, int KJ4, bool WS>
+template <int NW, int LPW, int KJV, bool WS>
 __device__ __forceinline__ float init_state(const Tables& t, const Image& im, const uint64_t (&s)[NW],
-                                            int sub, float (&p)[4 * KJ4], float (&m)[4 * KJ4],
-                                            bool want_z) {
-  float th[4 * KJ4];
+                                            int sub, float (&p)[32 / LPW * KJV],
+                                            float (&m)[32 / LPW * KJV], bool want_z) {
+  constexpr int VW = 32 / LPW, KJ = VW * KJV, HP = 32 * KJV;
+  float th[KJ];
 #pragma unroll
-  for (int q = 0; q < KJ4; ++q) {
-    const float4 b = ld4<WS>(t.base + 4 * (sub + LPW * q));
-    th[4 * q] = b.x; th[4 * q + 1] = b.y; th[4 * q + 2] = b.z; th[4 * q + 3] = b.w;
+  for (int q = 0; q < KJV; ++q) {
+    float v[VW];
+    ldv<VW, WS>(t.base + VW * sub + 32 * q, v);
+#pragma unroll
+    for (int c = 0; c < VW; ++c) th[VW * q + c] = v[c];
   }
 #pragma unroll
   for (int w = 0; w < NW; ++w) {
@@ -165,17 +180,19 @@ __device__ __forceinline__ float init_state(const Tables& t, const Image& im, co
     while (bits) {
       const int i = 64 * w + __ffsll((long long)bits) - 1;
       bits &= bits - 1;
-      const float* row = t.w2 + (size_t)i * im.HP + 4 * sub;
+      const float* row = t.w2 + i * HP + VW * sub;
 #pragma unroll
-      for (int q = 0; q < KJ4; ++q) {
-        const float4 v = ld4<WS>(row + 4 * LPW * q);
-        th[4 * q] += v.x; th[4 * q + 1] += v.y; th[4 * q + 2] += v.z; th[4 * q + 3] += v.w;
+      for (int q = 0; q < KJV; ++q) {
+        float v[VW];
+        ldv<VW, WS>(row + 32 * q, v);
+#pragma unroll
+        for (int c = 0; c < VW; ++c) th[VW * q + c] += v[c];
       }
     }
   }
   float zpart = 0.f;
 #pragma unroll
-  for (int k = 0; k < 4 * KJ4; ++k) {
+  for (int k = 0; k < KJ; ++k) {
     const float ax = fabsf(th[k]);
     const float e = expf(-2.f * ax);
     const float r = 1.f / (1.f + e);
@@ -194,25 +211,36 @@ __device__ __forceinline__ float init_state(const Tables& t, const Image& im, co
 }
 
 // log2(psi'/psi) for "raise site d, lower site u" (uniform within the lane
-// group).  KEEP: also return y[k] = p[k] F G for the acceptance update.
-template <int LPW, int KJ4, bool WS, bool KEEP>
-__device__ __forceinline__ float exchange_log2_ratio(const Tables& t, const Image& im, int d, int u,
-                                                     int sub, const float (&p)[4 * KJ4],
-                                                     const float (&m)[4 * KJ4],
-                                                     float (&y)[4 * KJ4]) {
-  const float* fr = t.f + (size_t)d * im.HP + 4 * sub;
-  const float* gr = t.g + (size_t)u * im.HP + 4 * sub;
+// group).  KEEP: also return tq[k] = F[d][j] G[u][j] for the acceptance update.
+template <int LPW, int KJV, bool WS, bool KEEP>
+__device__ __forceinline__ float exchange_log2_ratio(const Tables& t, int d, int u, int sub,
+                                                     const float (&p)[32 / LPW * KJV],
+                                                     const float (&m)[32 / LPW * KJV],
+                                                     float (&tq)[32 / LPW * KJV]) {
+  constexpr int VW = 32 / LPW, KJ = VW * KJV, HP = 32 * KJV;
+  const float* fr = t.f + d * HP + VW * sub;
+  const float* gr = t.g + u * HP + VW * sub;
+  float n[KJ];
+#pragma unroll
+  for (int q = 0; q < KJV; ++q) {
+    float f[VW], g[VW];
+    ldv<VW, WS>(fr + 32 * q, f);
+    ldv<VW, WS>(gr + 32 * q, g);
+#pragma unroll
+    for (int c = 0; c < VW; ++c) {
+      const float fg = f[c] * g[c];
+      if (KEEP) tq[VW * q + c] = fg;
+      n[VW * q + c] = fmaf(p[VW * q + c], fg, m[VW * q + c]);
+    }
+  }
+  // products of four terms, one lg2 each
   float lsum = 0.f;
 #pragma unroll
-  for (int q = 0; q < KJ4; ++q) {
-    const float4 f = ld4<WS>(fr + 4 * LPW * q);
-    const float4 g = ld4<WS>(gr + 4 * LPW * q);
-    const float y0 = p[4 * q] * (f.x * g.x), y1 = p[4 * q + 1] * (f.y * g.y);
-    const float y2 = p[4 * q + 2] * (f.z * g.z), y3 = p[4 * q + 3] * (f.w * g.w);
-    if (KEEP) { y[4 * q] = y0; y[4 * q + 1] = y1; y[4 * q + 2] = y2; y[4 * q + 3] = y3; }
-    const float n01 = (y0 + m[4 * q]) * (y1 + m[4 * q + 1]);
-    const float n23 = (y2 + m[4 * q + 2]) * (y3 + m[4 * q + 3]);
-    lsum += lg2_approx(n01 * n23);
+  for (int k = 0; k < KJ; k += 4) {
+    float pr = n[k];
+#pragma unroll
+    for (int c = 1; c < 4; ++c) if (k + c < KJ) pr *= n[k + c];
+    lsum += lg2_approx(pr);
   }
   lsum = group_sum<LPW>(lsum);
   return lsum + (ld1<WS>(t.a2 + d) - ld1<WS>(t.a2 + u));
@@ -283,12 +311,21 @@ struct SitePicker {
 // ---------------------------------------------------------------------------
 // K2: Metropolis sampler, graph_builders.py:54-89 x n_steps
 // ---------------------------------------------------------------------------
-template <int NW, int LPW, int KJ4, bool WS>
-__global__ void __launch_bounds__(kCtaThreads, 1)
+// CTA size: 1024 threads when the per-lane state fits a 64-register budget.
+template <int LPW, int KJV>
+struct Geometry {
+  static constexpr int VW = 32 / LPW, KJ = VW * KJV, HP = 32 * KJV, WPW = 32 / LPW;
+  static constexpr int THREADS = KJ <= 10 ? 1024 : 512;
+  static constexpr int WARPS = THREADS / 32, SLOTS = WARPS * WPW;
+};
+
+template <int NW, int LPW, int KJV, bool WS>
+__global__ void __launch_bounds__((Geometry<LPW, KJV>::THREADS), 1)
 mc_kernel(Image im, const float* __restrict__ img_g, uint64_t* __restrict__ packed, int64_t B,
           int wpc, int64_t n_batches, int n_steps, uint64_t seed, uint64_t walker0, uint64_t step0,
           unsigned long long* accept_count, float* __restrict__ log_amp_out) {
-  constexpr int WPW = 32 / LPW, KJ = 4 * KJ4;
+  using Geo = Geometry<LPW, KJV>;
+  constexpr int WPW = Geo::WPW, KJ = Geo::KJ;
   extern __shared__ __align__(16) float smem[];
   float* img_s = smem;
   uint8_t* lut = reinterpret_cast<uint8_t*>(smem + (WS ? im.total : 0));
@@ -306,14 +343,14 @@ mc_kernel(Image im, const float* __restrict__ img_g, uint64_t* __restrict__ pack
   for (int64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
     const int slot = warp * WPW + grp;
     const int64_t b = batch * wpc + slot;
-    if ((int64_t)(warp * WPW) >= (int64_t)wpc || batch * wpc + warp * WPW >= B) continue;   // warp-uniform
+    if (warp * WPW >= wpc || batch * wpc + warp * WPW >= B) continue;   // warp-uniform
     const bool valid = slot < wpc && b < B;
     const int64_t bb = valid ? b : B - 1;
     uint64_t s[NW];
 #pragma unroll
     for (int w = 0; w < NW; ++w) s[w] = w < im.words ? packed[bb * im.words + w] : 0ull;
-    float p[KJ], m[KJ], y[KJ];
-    init_state<NW, LPW, KJ4, WS>(t, im, s, sub, p, m, false);
+    float p[KJ], m[KJ], tq[KJ];
+    init_state<NW, LPW, KJV, WS>(t, im, s, sub, p, m, false);
     int n_up = 0;
 #pragma unroll
     for (int w = 0; w < NW; ++w) n_up += __popcll(s[w]);
@@ -334,14 +371,15 @@ mc_kernel(Image im, const float* __restrict__ img_g, uint64_t* __restrict__ pack
       int up, dn;
       picker.pick(s, k_up, k_dn, lut, up, dn);
       if (!can_move) { up = 0; dn = 0; }
-      const float l2 = exchange_log2_ratio<LPW, KJ4, WS, true>(t, im, dn, up, sub, p, m, y);
+      const float l2 = exchange_log2_ratio<LPW, KJV, WS, true>(t, dn, up, sub, p, m, tq);
       // accept iff |psi'/psi| > sqrt(u)  <=>  (psi'/psi)^2 > u   (strict; NaN rejects)
       const float prob = ex2_approx(2.f * l2);
       if (can_move && prob > u32_to_unit(r2)) {
 #pragma unroll
         for (int k = 0; k < KJ; ++k) {
-          const float r = rcp_approx(y[k] + m[k]);
-          p[k] = y[k] * r;
+          const float y = p[k] * tq[k];
+          const float r = rcp_approx(y + m[k]);
+          p[k] = y * r;
           m[k] = m[k] * r;
         }
         flip_bit<NW>(s, up);
@@ -354,7 +392,7 @@ mc_kernel(Image im, const float* __restrict__ img_g, uint64_t* __restrict__ pack
       for (int w = 0; w < NW; ++w) if (w < im.words) packed[b * im.words + w] = s[w];
     }
     if (log_amp_out != nullptr) {
-      float z = init_state<NW, LPW, KJ4, WS>(t, im, s, sub, p, m, true);
+      float z = init_state<NW, LPW, KJV, WS>(t, im, s, sub, p, m, true);
       z = group_sum<LPW>(z) + ld1<WS>(t.a0);
       if (valid && sub == 0) log_amp_out[b] = z;
     }
@@ -392,27 +430,28 @@ struct WalkerArgs {
   int64_t P;
 };
 
-template <int NW, int LPW, int KJ4, bool WS>
-__global__ void __launch_bounds__(kCtaThreads, 1)
+template <int NW, int LPW, int KJV, bool WS>
+__global__ void __launch_bounds__((Geometry<LPW, KJV>::THREADS), 1)
 walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
-  constexpr int WPW = 32 / LPW, KJ = 4 * KJ4, SLOTS = kCtaWarps * WPW;
+  using Geo = Geometry<LPW, KJV>;
+  constexpr int WPW = Geo::WPW, KJ = Geo::KJ, VW = Geo::VW, HP = Geo::HP;
+  constexpr int SLOTS = Geo::SLOTS, THREADS = Geo::THREADS;
   extern __shared__ __align__(16) float smem[];
   // ---- shared-memory carve-up (mirrors walker_smem_bytes) ----
   float* img_s = smem;
   char* cur = reinterpret_cast<char*>(smem + (WS ? im.total : 0));
-  uint8_t* lut = reinterpret_cast<uint8_t*>(cur); cur += 2048;
   uint64_t* bar = reinterpret_cast<uint64_t*>(cur); cur += 16;
   int4* bond_s = reinterpret_cast<int4*>(cur); cur += (size_t)(A.do_eloc ? A.n_bonds : 0) * 16;
   const int list_ld = (A.n_bonds + 7) / 8 * 8;
   uint16_t* list_s = reinterpret_cast<uint16_t*>(cur); cur += (size_t)(A.do_eloc ? SLOTS * list_ld : 0) * 2;
   const int NP4 = (im.N + 1 + 3) / 4 * 4;
-  float* T_s = reinterpret_cast<float*>(cur); cur += (size_t)(A.do_grad ? SLOTS * im.HP : 0) * 4;
+  float* T_s = reinterpret_cast<float*>(cur); cur += (size_t)(A.do_grad ? SLOTS * HP : 0) * 4;
   float* ws_s = reinterpret_cast<float*>(cur); cur += (size_t)(A.do_grad ? SLOTS * 2 * NP4 : 0) * 4;
   float* e_s = reinterpret_cast<float*>(cur);
 
   if (WS) bulk_load(img_s, img_g, (uint32_t)im.total * 4u, bar);
   if (A.do_eloc) {
-    for (int k = threadIdx.x; k < A.n_bonds; k += kCtaThreads) {
+    for (int k = threadIdx.x; k < A.n_bonds; k += THREADS) {
       const int2 ij = A.bonds_ij[k];
       bond_s[k] = make_int4(ij.x, ij.y, __float_as_int(A.bonds_jx[k]), __float_as_int(A.bonds_jz[k]));
     }
@@ -425,18 +464,11 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
   const int slot = warp * WPW + grp;
 
   // gradient tiles: 4 rows (sites, row N = the "ones" row of c) x 4 hidden units
-  const int CT = im.HP / 4, RT = NP4 / 4;
+  constexpr int CT = HP / 4;
+  const int RT = NP4 / 4;
   const int n_tiles = RT * CT;
-  const int n_pass = (n_tiles + kCtaThreads - 1) / kCtaThreads;
-  const bool persist = n_pass == 1;
-  float acc[2][4][4];
-#pragma unroll
-  for (int k = 0; k < 2; ++k)
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[k][r][c] = 0.f;
-  float acc_a[2] = {0.f, 0.f};   // entries threadIdx.x and threadIdx.x + 512 of the [2][NP4] a-gradient
+  const int n_pass = (n_tiles + THREADS - 1) / THREADS;
+  float acc_a[2] = {0.f, 0.f};   // entries threadIdx.x (+ THREADS) of the [2][NP4] a-gradient
   double sum_e = 0.0, sum_e2 = 0.0;   // thread 0 only
   float* part = A.partials + (size_t)blockIdx.x * 2 * A.P;
   int batch_no = 0;
@@ -452,9 +484,9 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
       uint64_t s[NW];
 #pragma unroll
       for (int w = 0; w < NW; ++w) s[w] = w < im.words ? A.packed[bb * im.words + w] : 0ull;
-      float p[KJ], m[KJ], ydummy[KJ];
+      float p[KJ], m[KJ], tdummy[KJ];
       const bool want_z = A.log_amp != nullptr;
-      float z = init_state<NW, LPW, KJ4, WS>(t, im, s, sub, p, m, want_z);
+      float z = init_state<NW, LPW, KJV, WS>(t, im, s, sub, p, m, want_z);
       if (want_z) {
         z = group_sum<LPW>(z) + ld1<WS>(t.a0);
         if (valid && sub == 0) A.log_amp[b] = z;
@@ -491,7 +523,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
           const int4 bd = bond_s[k];
           const int bi = spin_bit<NW>(s, bd.x);
           const int up = bi ? bd.x : bd.y, dn = bi ? bd.y : bd.x;
-          const float l2 = exchange_log2_ratio<LPW, KJ4, WS, false>(t, im, dn, up, sub, p, m, ydummy);
+          const float l2 = exchange_log2_ratio<LPW, KJV, WS, false>(t, dn, up, sub, p, m, tdummy);
           if (act) off = fmaf(0.5f * __int_as_float(bd.z), ex2_approx(l2), off);   // operators.py:168-169
         }
         e_val = diag + off;
@@ -510,12 +542,14 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
         } else {
           w0 = 1.f; w1 = e_val;
         }
-        float* Trow = T_s + (size_t)slot * im.HP + 4 * sub;
+        float* Trow = T_s + slot * HP + VW * sub;
 #pragma unroll
-        for (int q = 0; q < KJ4; ++q)
-          *reinterpret_cast<float4*>(Trow + 4 * LPW * q) =
-              make_float4(p[4 * q] - m[4 * q], p[4 * q + 1] - m[4 * q + 1],
-                          p[4 * q + 2] - m[4 * q + 2], p[4 * q + 3] - m[4 * q + 3]);
+        for (int q = 0; q < KJV; ++q) {
+          float v[VW];
+#pragma unroll
+          for (int c = 0; c < VW; ++c) v[c] = p[VW * q + c] - m[VW * q + c];
+          stv<VW>(Trow + 32 * q, v);
+        }
         float* wrow = ws_s + (size_t)slot * 2 * NP4;
         for (int i = sub; i < NP4; i += LPW) {
           float sg = 0.f;
@@ -530,19 +564,20 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
     if (A.do_grad) {
       __syncthreads();
       for (int pass = 0; pass < n_pass; ++pass) {
-        const int tile = threadIdx.x + pass * kCtaThreads;
+        const int tile = threadIdx.x + pass * THREADS;
         if (tile < n_tiles) {
           const int rt = tile / CT, ct = tile - rt * CT;
-          if (!persist) {
+          // the accumulators live only here: a CTA's partial sums are kept in
+          // its (L2-resident) slice of `partials` between batches
+          float acc[2][4][4];
 #pragma unroll
-            for (int k = 0; k < 2; ++k)
+          for (int k = 0; k < 2; ++k)
 #pragma unroll
-              for (int r = 0; r < 4; ++r)
+            for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[k][r][c] = 0.f;
-          }
+              for (int c = 0; c < 4; ++c) acc[k][r][c] = 0.f;
           for (int sb = 0; sb < n_valid; ++sb) {
-            const float4 T = *reinterpret_cast<const float4*>(T_s + (size_t)sb * im.HP + 4 * ct);
+            const float4 T = *reinterpret_cast<const float4*>(T_s + sb * HP + 4 * ct);
             const float4 s0 = *reinterpret_cast<const float4*>(ws_s + (size_t)sb * 2 * NP4 + 4 * rt);
             const float4 s1 = *reinterpret_cast<const float4*>(ws_s + (size_t)sb * 2 * NP4 + NP4 + 4 * rt);
             const float tv[4] = {T.x, T.y, T.z, T.w};
@@ -556,28 +591,26 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
                 acc[1][r][c] = fmaf(a1v[r], tv[c], acc[1][r][c]);
               }
           }
-          if (!persist) {
-            // row i < N: W[i][j]; row N: c[j]
+          // row i < N: W[i][j]; row N: c[j]
 #pragma unroll
-            for (int k = 0; k < 2; ++k)
+          for (int k = 0; k < 2; ++k)
 #pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                const int i = 4 * rt + r;
-                if (i > im.N) continue;
+            for (int r = 0; r < 4; ++r) {
+              const int i = 4 * rt + r;
+              if (i > im.N) continue;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  const int j = 4 * ct + c;
-                  if (j >= im.H) continue;
-                  float* dst = part + (size_t)k * A.P + im.N + 1 + (size_t)i * im.H + j;
-                  *dst = batch_no == 0 ? acc[k][r][c] : *dst + acc[k][r][c];
-                }
+              for (int c = 0; c < 4; ++c) {
+                const int j = 4 * ct + c;
+                if (j >= im.H) continue;
+                float* dst = part + (size_t)k * A.P + im.N + 1 + (size_t)i * im.H + j;
+                *dst = batch_no == 0 ? acc[k][r][c] : *dst + acc[k][r][c];
               }
-          }
+            }
         }
       }
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
-        const int e = threadIdx.x + h2 * kCtaThreads;
+        const int e = threadIdx.x + h2 * THREADS;
         if (e < 2 * NP4)
           for (int sb = 0; sb < n_valid; ++sb) acc_a[h2] += ws_s[(size_t)sb * 2 * NP4 + e];
       }
@@ -592,24 +625,9 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
     }
   }
   if (A.do_grad) {
-    if (persist && threadIdx.x < n_tiles) {
-      const int rt = threadIdx.x / CT, ct = threadIdx.x - rt * CT;
-#pragma unroll
-      for (int k = 0; k < 2; ++k)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int i = 4 * rt + r;
-          if (i > im.N) continue;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int j = 4 * ct + c;
-            if (j < im.H) part[(size_t)k * A.P + im.N + 1 + (size_t)i * im.H + j] = acc[k][r][c];
-          }
-        }
-    }
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2) {
-      const int e = threadIdx.x + h2 * kCtaThreads;
+      const int e = threadIdx.x + h2 * THREADS;
       if (e < 2 * NP4) {
         const int k = e / NP4, i = e - k * NP4;
         if (i <= im.N) part[(size_t)k * A.P + i] = acc_a[h2];   // a_i (i < N) and a0 (i == N)
@@ -623,7 +641,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
 }
 
 // ---------------------------------------------------------------------------
-// host-side launchers of one (NW, LPW, KJ4) variant
+// host-side launchers of one (NW, LPW, KJV) variant
 // ---------------------------------------------------------------------------
 template <typename F>
 inline int opt_in_smem(F kernel, size_t bytes) {
@@ -634,47 +652,61 @@ inline int opt_in_smem(F kernel, size_t bytes) {
   return CGSVMC_OK;
 }
 
-template <int NW, int LPW, int KJ4>
+template <int NW, int LPW, int KJV>
 int launch_mc_variant(const Plan& pl, const float* img, uint64_t* packed, int64_t B, int n_steps,
                       uint64_t seed, uint64_t walker0, uint64_t step0,
                       unsigned long long* accept_count, float* log_amp_out, cudaStream_t st) {
+  constexpr int THREADS = Geometry<LPW, KJV>::THREADS;
   if (pl.ws) {
-    auto kern = mc_kernel<NW, LPW, KJ4, true>;
+    auto kern = mc_kernel<NW, LPW, KJV, true>;
     if (int rc = opt_in_smem(kern, pl.mc_smem)) return rc;
-    kern<<<pl.grid, kCtaThreads, pl.mc_smem, st>>>(pl.im, img, packed, B, pl.wpc, pl.n_batches, n_steps,
-                                                  seed, walker0, step0, accept_count, log_amp_out);
+    kern<<<pl.grid, THREADS, pl.mc_smem, st>>>(pl.im, img, packed, B, pl.wpc, pl.n_batches, n_steps,
+                                              seed, walker0, step0, accept_count, log_amp_out);
   } else {
-    auto kern = mc_kernel<NW, LPW, KJ4, false>;
+    auto kern = mc_kernel<NW, LPW, KJV, false>;
     if (int rc = opt_in_smem(kern, pl.mc_smem)) return rc;
-    kern<<<pl.grid, kCtaThreads, pl.mc_smem, st>>>(pl.im, img, packed, B, pl.wpc, pl.n_batches, n_steps,
-                                                  seed, walker0, step0, accept_count, log_amp_out);
+    kern<<<pl.grid, THREADS, pl.mc_smem, st>>>(pl.im, img, packed, B, pl.wpc, pl.n_batches, n_steps,
+                                              seed, walker0, step0, accept_count, log_amp_out);
   }
   return cuda_fail(cudaGetLastError(), "rbm2 mc launch");
 }
 
-template <int NW, int LPW, int KJ4>
+template <int NW, int LPW, int KJV>
 int launch_walker_variant(const Plan& pl, const float* img, const WalkerArgs& A, cudaStream_t st) {
+  constexpr int THREADS = Geometry<LPW, KJV>::THREADS;
   if (pl.ws) {
-    auto kern = walker_kernel<NW, LPW, KJ4, true>;
+    auto kern = walker_kernel<NW, LPW, KJV, true>;
     if (int rc = opt_in_smem(kern, pl.walker_smem)) return rc;
-    kern<<<pl.grid, kCtaThreads, pl.walker_smem, st>>>(pl.im, img, A);
+    kern<<<pl.grid, THREADS, pl.walker_smem, st>>>(pl.im, img, A);
   } else {
-    auto kern = walker_kernel<NW, LPW, KJ4, false>;
+    auto kern = walker_kernel<NW, LPW, KJV, false>;
     if (int rc = opt_in_smem(kern, pl.walker_smem)) return rc;
-    kern<<<pl.grid, kCtaThreads, pl.walker_smem, st>>>(pl.im, img, A);
+    kern<<<pl.grid, THREADS, pl.walker_smem, st>>>(pl.im, img, A);
   }
   return cuda_fail(cudaGetLastError(), "rbm2 walker launch");
 }
 
+// walkers per CTA batch of a variant (host-side planning)
+inline int variant_slots(int lpw, int kjv) {
+  const int kj = (32 / lpw) * kjv;
+  return ((kj <= 10 ? 1024 : 512) / 32) * (32 / lpw);
+}
+
 #define RBM2_VARIANT_SWITCH(NWV, CALL)                       \
-  switch (pl.lpw * 16 + pl.kj4) {                            \
+  switch (pl.lpw * 16 + pl.kjv) {                            \
     case 8 * 16 + 1: return CALL(NWV, 8, 1);                 \
     case 8 * 16 + 2: return CALL(NWV, 8, 2);                 \
     case 8 * 16 + 3: return CALL(NWV, 8, 3);                 \
     case 8 * 16 + 4: return CALL(NWV, 8, 4);                 \
     case 8 * 16 + 5: return CALL(NWV, 8, 5);                 \
+    case 16 * 16 + 1: return CALL(NWV, 16, 1);               \
+    case 16 * 16 + 2: return CALL(NWV, 16, 2);               \
     case 16 * 16 + 3: return CALL(NWV, 16, 3);               \
     case 16 * 16 + 4: return CALL(NWV, 16, 4);               \
+    case 16 * 16 + 5: return CALL(NWV, 16, 5);               \
+    case 16 * 16 + 6: return CALL(NWV, 16, 6);               \
+    case 16 * 16 + 7: return CALL(NWV, 16, 7);               \
+    case 16 * 16 + 8: return CALL(NWV, 16, 8);               \
     default: break;                                          \
   }                                                          \
   set_error("rbm2: unsupported variant");                    \

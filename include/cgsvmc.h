@@ -100,6 +100,15 @@ int64_t cgsvmc_ansatz_num_params(const cgsvmc_ansatz* ansatz);
 /* Borrows a device buffer of P floats; it must stay valid until the next bind
  * or destroy.  The library only reads it. */
 int cgsvmc_ansatz_bind_params(cgsvmc_ansatz* ansatz, const float* params_dev);
+/* Some kernels read tables derived from the parameters (exp(+-4W) of the
+ * pure RBM).  By default they are rebuilt by a small kernel at every call, so
+ * the bound buffer may be modified in place at any time (the reference's
+ * variables are updated in place by optimizer.apply_gradients,
+ * training.py:565-567).  With tracking enabled the tables are rebuilt only
+ * after cgsvmc_ansatz_bind_params or cgsvmc_ansatz_params_changed: the caller
+ * promises to report every in-place modification. */
+int cgsvmc_ansatz_track_params(cgsvmc_ansatz* ansatz, int enabled);
+int cgsvmc_ansatz_params_changed(cgsvmc_ansatz* ansatz);
 
 /* Replaces HeisenbergHamiltonian.__init__ (operators.py:212-225), with one
  * (j_x, j_z) per bond as in HeisenbergBond.__init__ (operators.py:131-135).

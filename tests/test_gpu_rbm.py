@@ -482,6 +482,32 @@ def test_accumulate_full_size_sharding_invariance(native):
   np.testing.assert_allclose(stats.cpu().numpy(), stats4.cpu().numpy(), rtol=1e-10)
 
 
+def test_in_place_parameter_updates_are_seen(native):
+  """The reference's variables are updated in place by apply_gradients
+  (training.py:565-567); the derived exp(+-4W) tables must follow."""
+  from gpu_util import packed_cuda
+  spec = RBM_SHAPES[1]
+  a, params, cfg = _setup(spec, seed=5, batch=40)
+  ij, jx, jz = lattices.heisenberg_couplings(lattices.chain_bonds(spec.n_sites), -1.0, 1.0)
+  ham = native.Hamiltonian(ij, jx, jz, spec.n_sites)
+  packed = packed_cuda(cfg)
+  e0, _ = a.local_energy(ham, packed)
+  a.params.mul_(0.5)                                   # torch in-place update
+  e1, _ = a.local_energy(ham, packed)
+  params_half = [p * 0.5 for p in params]
+  fn = lambda c: oansatz.log_amp(spec, params_half, c)
+  eo = hamiltonian.local_energy(torch.from_numpy(cfg).to(F64), ij, jx, jz, fn).numpy()
+  np.testing.assert_allclose(e1.cpu().numpy(), eo, rtol=2e-5, atol=2e-5)
+  assert float((e1 - e0).abs().max()) > 1e-3
+  p2 = packed.clone()
+  a.params.mul_(2.0)
+  a.mc_steps(p2, 8, 3)
+  p3 = packed.clone()
+  b, _, _ = _setup(spec, seed=5, batch=40)
+  b.mc_steps(p3, 8, 3)
+  assert torch.equal(p2, p3)
+
+
 def test_energy_stats(native):
   e = torch.randn(100003, device='cuda')
   stats = native.energy_stats(e)
