@@ -151,6 +151,20 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t a_desc, uint64
       : "memory");
 }
 
+// One lane of the (converged) warp; lets the compiler move the MMA operands to
+// uniform registers without a per-lane waterfall loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(
@@ -369,7 +383,7 @@ struct Engine {
             const uint32_t b_lo = (b_units + (uint32_t)(pr * 2 * 3 * CC)) | b_lbo;
             const uint64_t a = ((uint64_t)desc_hi << 32) | a_lo;
             const uint64_t b = ((uint64_t)desc_hi << 32) | b_lo;
-            if (lane == 0) mma_f16(d_tmem, a, b, idesc3, pr > 0 ? 1u : 0u);
+            if (elect_one()) mma_f16(d_tmem, a, b, idesc3, pr > 0 ? 1u : 0u);
           }
         }
       } else {
@@ -379,8 +393,10 @@ struct Engine {
         for (int t = 0; t < d.n_tiles; ++t) {
           const uint32_t d_tmem = tmem + (uint32_t)(t * 3 * CC);
           const uint32_t a_tile = a_units + (uint32_t)(t * 128);
-          for (int tap = 0; tap < taps; ++tap) {
-            const uint32_t a_row = a_tile + (uint32_t)tap_shift[tap];
+          for (int dx = 0; dx < d.kx; ++dx)
+          for (int dy = 0; dy < d.ky; ++dy) {
+            const int tap = dx * d.ky + dy;
+            const uint32_t a_row = a_tile + (uint32_t)(dx * d.GW + dy);
             const uint32_t b_row = b_units + (uint32_t)tap * b_tap_units;
 #pragma unroll
             for (int ks = 0; ks < CC / 16; ++ks) {
@@ -390,7 +406,7 @@ struct Engine {
               const uint64_t a2 = ((uint64_t)desc_hi << 32) | (a_lo + split_units);
               const uint64_t a3 = ((uint64_t)desc_hi << 32) | (a_lo + 2 * split_units);
               const uint64_t b = ((uint64_t)desc_hi << 32) | b_lo;
-              if (lane == 0) {
+              if (elect_one()) {
                 mma_f16(d_tmem, a1, b, idesc3, (tap | ks) ? 1u : 0u);   // [P0 P1 P2] += A1 [b1 b2 b3]
                 mma_f16(d_tmem + CC, a2, b, idesc2, 1u);                 // [P1 P2]    += A2 [b1 b2]
                 mma_f16(d_tmem + 2 * CC, a3, b, idesc1, 1u);             // [P2]       += A3 [b1]
@@ -399,7 +415,7 @@ struct Engine {
           }
         }
       }
-      if (lane == 0)
+      if (elect_one())
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                          smem_u32(mma_bar))
                      : "memory");

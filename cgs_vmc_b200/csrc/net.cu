@@ -864,12 +864,11 @@ conv_grad_kernel(NetDesc d, int T, const uint64_t* __restrict__ packed,
   Conv::build_tables(d, xi, yi, false);
   Conv::build_tables(d, xib, yib, true);
 
-  float acc[K][kGradE];
-#pragma unroll
-  for (int k = 0; k < K; ++k)
-#pragma unroll
-    for (int m = 0; m < kGradE; ++m) acc[k][m] = 0.f;
-  const int64_t e0 = (int64_t)blockIdx.y * (kThreads * kGradE) + threadIdx.x;
+  // every CTA owns a slice [K][P] of `partials` (L2 resident) and adds the
+  // contribution of each of its walker tiles to it; the forward / backward pass
+  // of a tile is done once for all parameter entries
+  float* part = partials + (int64_t)blockIdx.x * K * P;
+  bool first_tile = true;
 
   const int64_t b_begin = (int64_t)blockIdx.x * walkers_per_cta;
   const int64_t b_end = min(B, b_begin + walkers_per_cta);
@@ -903,9 +902,10 @@ conv_grad_kernel(NetDesc d, int T, const uint64_t* __restrict__ packed,
     }
     // accumulate
 #pragma unroll 1
-    for (int m = 0; m < kGradE; ++m) {
-      const int64_t e = e0 + (int64_t)m * kThreads;
-      if (e >= P) break;
+    for (int64_t e = threadIdx.x; e < P; e += kThreads) {
+      float acc[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] = 0.f;
       int l = 0;
       while (l + 1 < L && e >= d.w_off[l + 1]) ++l;
       const int cl = l == 0 ? 1 : C;
@@ -918,7 +918,7 @@ conv_grad_kernel(NetDesc d, int T, const uint64_t* __restrict__ packed,
           float g = 0.f;
           for (int pos = 0; pos < N; ++pos) g += dp[pos];
 #pragma unroll
-          for (int k = 0; k < K; ++k) acc[k][m] = fmaf(wk[k * T + t], g, acc[k][m]);
+          for (int k = 0; k < K; ++k) acc[k] = fmaf(wk[k * T + t], g, acc[k]);
         }
       } else {
         const int q = (int)(e - d.w_off[l]);
@@ -934,19 +934,17 @@ conv_grad_kernel(NetDesc d, int T, const uint64_t* __restrict__ packed,
             for (int y = 0; y < d.Y; ++y) g = fmaf(hp[sx + yi[y * d.ky + dy]], dp[x * d.Y + y], g);
           }
 #pragma unroll
-          for (int k = 0; k < K; ++k) acc[k][m] = fmaf(wk[k * T + t], g, acc[k][m]);
+          for (int k = 0; k < K; ++k) acc[k] = fmaf(wk[k * T + t], g, acc[k]);
         }
       }
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        float* dst = part + (int64_t)k * P + e;
+        *dst = first_tile ? acc[k] : *dst + acc[k];
+      }
     }
+    first_tile = false;
     __syncthreads();
-  }
-#pragma unroll
-  for (int m = 0; m < kGradE; ++m) {
-    const int64_t e = e0 + (int64_t)m * kThreads;
-    if (e < P) {
-#pragma unroll
-      for (int k = 0; k < K; ++k) partials[((int64_t)blockIdx.x * K + k) * P + e] = acc[k][m];
-    }
   }
 }
 
@@ -1141,7 +1139,8 @@ int net_grad(cgsvmc_ansatz* a, const uint64_t* packed, const float* weights, int
     smem = need(tw4 ? 36 : 12, T);
     if ((int64_t)smem > a->max_smem_optin) { set_error("weighted_grad_sum: network does not fit in shared memory"); return CGSVMC_ERR_UNSUPPORTED; }
   }
-  int64_t groups = std::max<int64_t>(1, (2 * (int64_t)a->num_sms) / chunks);
+  // conv: one CTA per SM handles all parameter entries of its walkers
+  int64_t groups = conv ? (int64_t)a->num_sms : std::max<int64_t>(1, (2 * (int64_t)a->num_sms) / chunks);
   groups = std::min<int64_t>(groups, (B + T - 1) / T);
   int64_t per_cta = (B + groups - 1) / groups;
   per_cta = (per_cta + T - 1) / T * T;
@@ -1169,7 +1168,7 @@ int net_grad(cgsvmc_ansatz* a, const uint64_t* packed, const float* weights, int
     }
     if (int rc = cuda_fail(cudaGetLastError(), "transpose launch")) return rc;
   }
-  dim3 grid((unsigned)groups, (unsigned)chunks);
+  dim3 grid((unsigned)groups, conv ? 1u : (unsigned)chunks);
   for (int k0 = 0; k0 < K; k0 += 2) {
     const int kk = std::min(2, K - k0);
     const float* w = weights + (int64_t)k0 * B;
