@@ -40,6 +40,8 @@ def parse_args():
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--walkers', type=int, default=WALKERS, help='walkers per GPU')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-cuda-graph', dest='cuda_graph', action='store_false',
+                  help='launch the kernels of a step one by one instead of replaying a captured graph')
   return ap.parse_args()
 
 
@@ -195,14 +197,23 @@ def run_ours(args, rank, world, local_rank):
   counter = [0]
   ev = lambda: torch.cuda.Event(enable_timing=True)
 
+  graphed = engine.GraphedBatchStep(state, ansatz, ham, sums, SWEEP_STEPS) if args.cuda_graph else None
+
   def step(events=None):
-    """accumulate_gradients + one sweep (+ the packed all-reduce when sharded)."""
-    if events: events[0].record()
-    sums.accumulate(ham, state.packed)     # E_loc + both gradient sums + energy statistics
-    if events: events[2].record()
-    state.mc_steps(ansatz, SWEEP_STEPS)
-    if events: events[3].record()
-    launches[0] += 3   # walker kernel, reduce, mc kernel (parameter tables are cached)
+    """accumulate_gradients + one sweep (+ the packed all-reduce when sharded).
+    Timed as one captured CUDA graph (default) or, with --no-cuda-graph /
+    when per-phase events are wanted, as separate launches."""
+    if graphed is not None and events is None:
+      graphed.replay()
+      launches[0] += 5   # prep, walker kernel, reduce, mc kernel, step-counter advance
+    else:
+      if events: events[0].record()
+      sums.accumulate(ham, state.packed)     # E_loc + both gradient sums + energy statistics
+      if events: events[2].record()
+      state.mc_steps(ansatz, SWEEP_STEPS)
+      state.step_dev.fill_(state.step)
+      if events: events[3].record()
+      launches[0] += 3   # walker kernel, reduce, mc kernel (parameter tables are cached)
     counter[0] += 1
     if world > 1 and counter[0] % EPOCH_BATCHES == 0:
       # epoch end (training.py:619-620): the only exchange of the sharded run --
@@ -223,12 +234,13 @@ def run_ours(args, rank, world, local_rank):
   # ---- timed region: K steps, device-resident inputs -----------------------
   clock = ClockSampler(local_rank) if rank == 0 else None
   launches[0] = 0
-  marks = [[ev() for _ in range(5)] for _ in range(args.steps)]
+  marks = [[ev(), ev()] for _ in range(args.steps)]
   torch.cuda.synchronize()
   wall0 = time.perf_counter()
   for k in range(args.steps):
-    step(marks[k])
-    marks[k][4].record()
+    marks[k][0].record()
+    step()
+    marks[k][1].record()
     flush.zero_()                      # L2 flush, outside the per-step event pair
   torch.cuda.synchronize()
   wall = time.perf_counter() - wall0
@@ -236,9 +248,17 @@ def run_ours(args, rank, world, local_rank):
     dist.barrier()
   clocks = clock.stop() if clock else None
   n_launch = launches[0]
-  t_step = np.array([m[0].elapsed_time(m[4]) for m in marks]) * 1e-3
-  t_acc = np.array([m[0].elapsed_time(m[2]) for m in marks]) * 1e-3
-  t_mc = np.array([m[2].elapsed_time(m[3]) for m in marks]) * 1e-3
+  t_step = np.array([m[0].elapsed_time(m[1]) for m in marks]) * 1e-3
+  # per-phase device times (kernel shares, roofline kernel time): the same step
+  # launched kernel by kernel with events between the phases, outside the timed region
+  phase = [[ev() for _ in range(5)] for _ in range(20)]
+  for k in range(20):
+    step(phase[k])
+    phase[k][4].record()
+    flush.zero_()
+  torch.cuda.synchronize()
+  t_acc = np.array([m[0].elapsed_time(m[2]) for m in phase]) * 1e-3
+  t_mc = np.array([m[2].elapsed_time(m[3]) for m in phase]) * 1e-3
   total = torch.tensor([t_step.sum()], dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(total, op=dist.ReduceOp.MAX)
@@ -272,7 +292,7 @@ def run_ours(args, rank, world, local_rank):
       dev_cfgs[i].copy_(host_cfg, non_blocking=True)              # H2D inputs
       h2d_done[i].record(copy_stream)
     main.wait_event(h2d_done[i])
-    state.packed = _native.pack_configs(dev_cfgs[i])
+    _native.pack_configs(dev_cfgs[i], out=state.packed)
     consumed[i].record(main)
     step()
     host_out[i][0].copy_(sums.sums, non_blocking=True)            # D2H result: [2, P] sums
@@ -365,6 +385,8 @@ def run_ours(args, rank, world, local_rank):
       'config': {'workload': WORKLOAD, 'walkers_per_gpu': B, 'mc_steps_per_step': SWEEP_STEPS,
                  'n_bonds': 72, 'n_params': P,
                  'l2': 'flushed: %d MiB memset between steps, outside the per-step CUDA-event pairs' % (L2_FLUSH_BYTES >> 20),
+                 'launch': ('one captured CUDA graph per step (table build, walker kernel, reduce, '
+                            'mc kernel, step-counter advance)' if args.cuda_graph else 'kernel by kernel'),
                  'parallelism': 'walkers sharded, params replicated' + (
                      ', one all-reduce of [2P+4] floats per epoch of %d steps' % EPOCH_BATCHES
                      if world > 1 else '')},

@@ -23,7 +23,7 @@ EXPORTS = [
     'cgsvmc_ansatz_bind_params', 'cgsvmc_ansatz_track_params',
     'cgsvmc_ansatz_params_changed', 'cgsvmc_ham_create', 'cgsvmc_ham_destroy',
     'cgsvmc_pack_configs', 'cgsvmc_unpack_configs', 'cgsvmc_random_configs',
-    'cgsvmc_log_amp', 'cgsvmc_mc_steps', 'cgsvmc_mc_step_replay',
+    'cgsvmc_log_amp', 'cgsvmc_mc_steps', 'cgsvmc_mc_steps_graph', 'cgsvmc_mc_step_replay',
     'cgsvmc_flip_enum', 'cgsvmc_local_energy', 'cgsvmc_weighted_grad_sum',
     'cgsvmc_energy_stats', 'cgsvmc_accumulate',
 ]
@@ -69,6 +69,7 @@ def load():
   lib.cgsvmc_random_configs.argtypes = [vp, i64, i32, u64, u64, vp]
   lib.cgsvmc_log_amp.argtypes = [vp, vp, i64, vp, vp]
   lib.cgsvmc_mc_steps.argtypes = [vp, vp, i64, i32, u64, u64, u64, vp, vp, vp]
+  lib.cgsvmc_mc_steps_graph.argtypes = [vp, vp, i64, i32, u64, u64, vp, vp, vp, vp]
   lib.cgsvmc_mc_step_replay.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
   lib.cgsvmc_flip_enum.argtypes = [vp, vp, i64, vp, vp, vp]
   lib.cgsvmc_local_energy.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp]
@@ -196,6 +197,20 @@ class Ansatz:
                                  int(seed), int(walker_id0), int(step0),
                                  _ptr(accept_count), _ptr(log_amp_out), _stream()))
 
+  def mc_steps_graph(self, packed, n_steps, seed, walker_id0, step_counter,
+                     accept_count=None, log_amp_out=None):
+    """mc_steps with the Philox step offset in device memory (int64 [1] tensor,
+    advanced by n_steps on the stream): safe to capture in a CUDA graph."""
+    self._sync_params()
+    b = packed.shape[0]
+    _want(packed, torch.int64, (b, n_words(self.n_sites)), 'packed')
+    _want(step_counter, torch.int64, (1,), 'step_counter')
+    if accept_count is not None:
+      _want(accept_count, torch.int64, (1,), 'accept_count')
+    check(load().cgsvmc_mc_steps_graph(self._handle, _ptr(packed), b, int(n_steps), int(seed),
+                                       int(walker_id0), _ptr(step_counter), _ptr(accept_count),
+                                       _ptr(log_amp_out), _stream()))
+
   def mc_step_replay(self, packed, u_sites, u_acc):
     b = packed.shape[0]
     _want(packed, torch.int64, (b, n_words(self.n_sites)), 'packed')
@@ -301,12 +316,16 @@ class Hamiltonian:
     return mask, flipped
 
 
-def pack_configs(configs):
+def pack_configs(configs, out=None):
   """float32 [B, N] of +-1 (CUDA) -> int64-viewed uint64 [B, W]."""
   require_cuda()
   b, n = configs.shape
   _want(configs, torch.float32, (b, n), 'configs')
-  packed = torch.empty(b, n_words(n), dtype=torch.int64, device=configs.device)
+  if out is None:
+    packed = torch.empty(b, n_words(n), dtype=torch.int64, device=configs.device)
+  else:
+    _want(out, torch.int64, (b, n_words(n)), 'out')
+    packed = out
   check(load().cgsvmc_pack_configs(_ptr(configs), b, n, _ptr(packed), _stream()))
   return packed
 

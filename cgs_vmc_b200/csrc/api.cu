@@ -263,6 +263,23 @@ int cgsvmc_mc_steps(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int32_t
                       (cudaStream_t)stream);
 }
 
+int cgsvmc_mc_steps_graph(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int32_t n_steps,
+                          uint64_t seed, uint64_t walker_id0, uint64_t* step_counter,
+                          unsigned long long* accept_count, float* log_amp_out, void* stream) {
+  if (a == nullptr) return invalid("ansatz handle is NULL");
+  if (step_counter == nullptr) return invalid("mc_steps_graph: NULL step counter");
+  if (rbm_fast_supported(a) && !rbm2_supported(a, nullptr)) {
+    set_error("mc_steps_graph: not available on the first-generation RBM kernels");
+    return CGSVMC_ERR_UNSUPPORTED;
+  }
+  cgsvmc_ansatz* am = const_cast<cgsvmc_ansatz*>(a);
+  am->step_counter_dev = step_counter;
+  const int rc = cgsvmc_mc_steps(a, packed, B, n_steps, seed, walker_id0, 0, accept_count, log_amp_out, stream);
+  am->step_counter_dev = nullptr;
+  if (rc != CGSVMC_OK || B == 0) return rc;
+  return launch_advance_counter(step_counter, (uint64_t)n_steps, (cudaStream_t)stream);
+}
+
 int cgsvmc_mc_step_replay(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, const float* u_sites,
                           const float* u_acc, int32_t* down_site, int32_t* up_site,
                           float* log_ratio, uint8_t* accept_mask, void* stream) {

@@ -552,8 +552,9 @@ __device__ __forceinline__ int kth_set_bit(const uint64_t* words, int nw, int k)
 template <int CC>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_mc_kernel(TcDesc d, uint64_t* __restrict__ packed, int64_t B, int n_steps, uint64_t seed,
-             uint64_t walker0, uint64_t step0, unsigned long long* accept_count,
-             float* __restrict__ log_amp_out) {
+             uint64_t walker0, uint64_t step0, const uint64_t* __restrict__ step0_dev,
+             unsigned long long* accept_count, float* __restrict__ log_amp_out) {
+  if (step0_dev != nullptr) step0 += *step0_dev;
   extern __shared__ __align__(1024) char smem[];
   Engine eng(d);
   eng.setup(smem);
@@ -911,12 +912,12 @@ int conv_tc_mc_steps(cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int n_steps,
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((B + d.G - 1) / d.G, a->num_sms));
   if (d.C == 16) {
     if (int rc = opt_in(tc_mc_kernel<16>, smem)) return rc;
-    tc_mc_kernel<16><<<grid, kThreads, smem, st>>>(d, packed, B, n_steps, seed, walker0, step0, accept_count,
-                                                  log_amp_out);
+    tc_mc_kernel<16><<<grid, kThreads, smem, st>>>(d, packed, B, n_steps, seed, walker0, step0,
+                                                  a->step_counter_dev, accept_count, log_amp_out);
   } else {
     if (int rc = opt_in(tc_mc_kernel<32>, smem)) return rc;
-    tc_mc_kernel<32><<<grid, kThreads, smem, st>>>(d, packed, B, n_steps, seed, walker0, step0, accept_count,
-                                                  log_amp_out);
+    tc_mc_kernel<32><<<grid, kThreads, smem, st>>>(d, packed, B, n_steps, seed, walker0, step0,
+                                                  a->step_counter_dev, accept_count, log_amp_out);
   }
   return cuda_fail(cudaGetLastError(), "conv_tc mc launch");
 }

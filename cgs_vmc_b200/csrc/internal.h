@@ -28,6 +28,7 @@ struct cgsvmc_ansatz {
   size_t tables_bytes = 0;
   bool tables_valid = false;       // tables match the bound parameters
   bool track_params = false;       // rebuild tables only after bind_params / params_changed
+  const uint64_t* step_counter_dev = nullptr;   // set during cgsvmc_mc_steps_graph: device-side step offset
   float* acc_weights = nullptr;    // owned: [2, B] weight rows of cgsvmc_accumulate (tile networks)
   size_t acc_weights_bytes = 0;
 };
@@ -57,6 +58,7 @@ int launch_random_configs(uint64_t* packed, int64_t B, int N, uint64_t seed, uin
                           cudaStream_t s);
 int launch_flip_enum(const cgsvmc_ham* h, const uint64_t* packed, int64_t B, uint64_t* flipped,
                      uint32_t* mask, cudaStream_t s);
+int launch_advance_counter(uint64_t* counter, uint64_t by, cudaStream_t s);
 int launch_fill(float* dst, int64_t n, float value, cudaStream_t s);
 int launch_energy_stats(const float* e, int64_t B, double* stats, cudaStream_t s);
 int launch_reduce_partials(const float* partials, int n_parts, int64_t n, float* out,

@@ -430,7 +430,9 @@ template <class NET>
 __global__ void __launch_bounds__(kThreads)
 net_mc_kernel(NetDesc d, int T, size_t fwd_bytes, uint64_t* __restrict__ packed, int64_t B,
               int n_steps, uint64_t seed, uint64_t walker0, uint64_t step0,
-              unsigned long long* accept_count, float* __restrict__ log_amp_out) {
+              const uint64_t* __restrict__ step0_dev, unsigned long long* accept_count,
+              float* __restrict__ log_amp_out) {
+  if (step0_dev != nullptr) step0 += *step0_dev;
   extern __shared__ __align__(16) float smem[];
   Carver carve(smem, fwd_bytes);
   uint64_t* prop = carve.take<uint64_t>((size_t)T * d.NW);   // proposed configs [T][NW]
@@ -1073,7 +1075,7 @@ int net_mc_steps(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int n_step
   const size_t smem = plan.fwd_bytes + 2 * carve_bytes((size_t)plan.T * d.NW, 8) + 3 * carve_bytes(plan.T, 4);
   const int grid = grid_for(a, (B + plan.T - 1) / plan.T);
   NET_LAUNCH(net_mc_kernel, smem, grid, d, plan.T, plan.fwd_bytes, packed, B, n_steps, seed,
-             walker0, step0, accept_count, log_amp_out);
+             walker0, step0, a->step_counter_dev, accept_count, log_amp_out);
   return cuda_fail(cudaGetLastError(), "net_mc_steps launch");
 }
 

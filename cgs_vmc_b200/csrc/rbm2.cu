@@ -185,6 +185,7 @@ int rbm2_mc_steps(cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int n_steps, ui
   const size_t img_bytes = (size_t)pl.im.total * 4;
   pl.ws = img_bytes + 2048 + 16 <= (size_t)a->max_smem_optin;
   pl.mc_smem = (pl.ws ? img_bytes : 0) + 2048 + 16;
+  pl.step0_dev = a->step_counter_dev;
   if (int rc = build_image(a, pl, st)) return rc;
   switch (pl.nw) {
     case 1: return launch_mc_nw1(pl, a->tables, packed, B, n_steps, seed, walker0, step0, accept_count, log_amp_out, st);

@@ -23,6 +23,7 @@ struct Plan {
   int64_t n_batches;
   int grid;
   size_t mc_smem, walker_smem;
+  const uint64_t* step0_dev;   // optional device-side Philox step offset (CUDA graphs)
 };
 
 struct WalkerArgs;

@@ -323,8 +323,10 @@ template <int NW, int LPW, int KJV, bool WS>
 __global__ void __launch_bounds__((Geometry<LPW, KJV>::THREADS), 1)
 mc_kernel(Image im, const float* __restrict__ img_g, uint64_t* __restrict__ packed, int64_t B,
           int wpc, int64_t n_batches, int n_steps, uint64_t seed, uint64_t walker0, uint64_t step0,
-          unsigned long long* accept_count, float* __restrict__ log_amp_out) {
+          const uint64_t* __restrict__ step0_dev, unsigned long long* accept_count,
+          float* __restrict__ log_amp_out) {
   using Geo = Geometry<LPW, KJV>;
+  if (step0_dev != nullptr) step0 += *step0_dev;
   constexpr int WPW = Geo::WPW, KJ = Geo::KJ;
   extern __shared__ __align__(16) float smem[];
   float* img_s = smem;
@@ -661,12 +663,12 @@ int launch_mc_variant(const Plan& pl, const float* img, uint64_t* packed, int64_
     auto kern = mc_kernel<NW, LPW, KJV, true>;
     if (int rc = opt_in_smem(kern, pl.mc_smem)) return rc;
     kern<<<pl.grid, THREADS, pl.mc_smem, st>>>(pl.im, img, packed, B, pl.wpc, pl.n_batches, n_steps,
-                                              seed, walker0, step0, accept_count, log_amp_out);
+                                              seed, walker0, step0, pl.step0_dev, accept_count, log_amp_out);
   } else {
     auto kern = mc_kernel<NW, LPW, KJV, false>;
     if (int rc = opt_in_smem(kern, pl.mc_smem)) return rc;
     kern<<<pl.grid, THREADS, pl.mc_smem, st>>>(pl.im, img, packed, B, pl.wpc, pl.n_batches, n_steps,
-                                              seed, walker0, step0, accept_count, log_amp_out);
+                                              seed, walker0, step0, pl.step0_dev, accept_count, log_amp_out);
   }
   return cuda_fail(cudaGetLastError(), "rbm2 mc launch");
 }

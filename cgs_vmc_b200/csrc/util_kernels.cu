@@ -192,6 +192,13 @@ __global__ void fill_kernel(float* __restrict__ dst, int64_t n, float value) {
        e += (int64_t)gridDim.x * blockDim.x) dst[e] = value;
 }
 
+__global__ void advance_counter_kernel(uint64_t* counter, uint64_t by) { *counter += by; }
+
+int launch_advance_counter(uint64_t* counter, uint64_t by, cudaStream_t s) {
+  advance_counter_kernel<<<1, 1, 0, s>>>(counter, by);
+  return cuda_fail(cudaGetLastError(), "advance_counter launch");
+}
+
 int launch_fill(float* dst, int64_t n, float value, cudaStream_t s) {
   if (n <= 0) return CGSVMC_OK;
   const int blocks = (int)std::min<int64_t>((n + 255) / 256, 1024);

@@ -26,6 +26,8 @@ class WalkerState:
     self.packed = packed
     self.accept_count = torch.zeros(1, dtype=torch.int64, device=packed.device)
     self.proposed = 0
+    # device-side copy of the Philox step offset for CUDA-graph replays
+    self.step_dev = torch.zeros(1, dtype=torch.int64, device=packed.device)
 
   def configs(self):
     """float32 [B, N] of +-1: the reference's view of the state."""
@@ -34,7 +36,8 @@ class WalkerState:
   def set_configs(self, configs):
     if tuple(configs.shape) != (self.batch_size, self.n_sites):
       raise ValueError('Size of existing variable does not match.')   # graph_builders.py:118
-    self.packed = _native.pack_configs(configs.to(self.packed.device, torch.float32).contiguous())
+    # in place: captured CUDA graphs keep pointing at the same buffer
+    _native.pack_configs(configs.to(self.packed.device, torch.float32).contiguous(), out=self.packed)
 
   def mc_steps(self, ansatz, n_steps, log_amp_out=None):
     """n_steps x session.run(mc_step) (graph_builders.py:38-89) in one launch."""
@@ -42,6 +45,12 @@ class WalkerState:
                     self.accept_count, log_amp_out)
     self.step += int(n_steps)
     self.proposed += int(n_steps) * self.batch_size
+
+  def mc_steps_graph(self, ansatz, n_steps):
+    """The same with the step offset read from `step_dev` on the device
+    (capturable); the caller keeps `step_dev` and `step` in sync."""
+    ansatz.mc_steps_graph(self.packed, n_steps, self.seed, self.walker_id0, self.step_dev,
+                          self.accept_count)
 
 
 class EnergyGradientSums:
@@ -82,3 +91,46 @@ class EnergyGradientSums:
     (B times the covariance: tf.gradients sums over the batch)."""
     nb = float(self.n_batches if n_batches is None else n_batches)
     return self.sums[1] / nb - self.mean_energy().float() * self.sums[0] / nb
+
+
+class GraphedBatchStep:
+  """One batch iteration of EnergyGradientOptimizer.run_optimization_epoch
+  (training.py:614-617) -- accumulate_gradients followed by
+  num_monte_carlo_sweeps * num_sites Metropolis steps -- captured once as a
+  CUDA graph and replayed: one graph launch instead of a Python dispatch per
+  kernel (the reference pays one session.run per Metropolis step).
+
+  The parameter tables are rebuilt inside the graph, so in-place optimizer
+  updates between replays are picked up; the Philox step offset lives in
+  device memory and is advanced by the graph itself."""
+
+  def __init__(self, state, ansatz, ham, sums, n_steps):
+    self.state, self.ansatz, self.ham, self.sums, self.n_steps = state, ansatz, ham, sums, int(n_steps)
+    state.step_dev.fill_(state.step)
+    saved = (sums.sums.clone(), sums.stats.clone(), state.packed.clone(), state.accept_count.clone())
+    side = torch.cuda.Stream(device=state.packed.device)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):           # warm-up: sizes every scratch buffer
+      self._body()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    # undo the warm-up so that capture + replays see the caller's state
+    sums.sums.copy_(saved[0]); sums.stats.copy_(saved[1])
+    state.packed.copy_(saved[2]); state.accept_count.copy_(saved[3])
+    state.step_dev.fill_(state.step)
+    self.graph = torch.cuda.CUDAGraph()
+    _native.check(_native.load().cgsvmc_ansatz_params_changed(ansatz._handle))   # capture the table build
+    with torch.cuda.graph(self.graph):
+      self._body()
+    # capture does not execute: nothing to undo
+
+  def _body(self):
+    self.sums.ansatz.accumulate(self.ham, self.state.packed, self.sums.sums, self.sums.stats,
+                                e_loc_out=self.sums.weights[1], log_amp_out=self.sums.log_amp)
+    self.state.mc_steps_graph(self.ansatz, self.n_steps)
+
+  def replay(self):
+    self.graph.replay()
+    self.sums.n_batches += 1
+    self.state.step += self.n_steps
+    self.state.proposed += self.n_steps * self.state.batch_size

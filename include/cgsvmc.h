@@ -158,6 +158,17 @@ int cgsvmc_mc_steps(const cgsvmc_ansatz* ansatz, uint64_t* packed_inout,
                     unsigned long long* accept_count, float* log_amp_out,
                     void* stream);
 
+/* CUDA-graph friendly form of cgsvmc_mc_steps: the Philox step offset is read
+ * from device memory (*step_counter, uint64) when the kernel runs and advanced
+ * by n_steps afterwards on the same stream, so a captured graph of
+ * "accumulate + sweep" (training.py:614-617) can be replayed every batch
+ * without re-using random numbers. */
+int cgsvmc_mc_steps_graph(const cgsvmc_ansatz* ansatz, uint64_t* packed_inout,
+                          int64_t n_walkers, int32_t n_steps, uint64_t seed,
+                          uint64_t walker_id0, uint64_t* step_counter,
+                          unsigned long long* accept_count, float* log_amp_out,
+                          void* stream);
+
 /* One step in REPLAY mode (tests): consumes caller-supplied uniforms exactly
  * like graph_builders.py:59-79 -- u_sites float32 [B, N] (argmin / argmax of
  * sigma * u with first-occurrence ties), u_acc float32 [B] (accept iff

@@ -508,6 +508,36 @@ def test_in_place_parameter_updates_are_seen(native):
   assert torch.equal(p2, p3)
 
 
+def test_graphed_batch_step_equals_separate_launches(native):
+  """engine.GraphedBatchStep (accumulate + sweep captured as one CUDA graph,
+  training.py:614-617) replays bit-identically to the separate launches,
+  including after an in-place parameter update between replays."""
+  from cgs_vmc_b200 import engine
+  spec = _c2_spec()
+  a, params, _ = _setup(spec, seed=3, batch=1)
+  ij, jx, jz = lattices.heisenberg_couplings(lattices.square_nn_bonds(6))
+  ham = native.Hamiltonian(ij, jx, jz, 36)
+  s1 = engine.WalkerState(1000, 36, seed=5, walker_id0=7)
+  s2 = engine.WalkerState(1000, 36, seed=5, walker_id0=7)
+  s1.mc_steps(a, 11)
+  s2.mc_steps(a, 11)
+  sums1 = engine.EnergyGradientSums(a, 1000)
+  sums2 = engine.EnergyGradientSums(a, 1000)
+  g = engine.GraphedBatchStep(s1, a, ham, sums1, 36)
+  assert torch.equal(s1.packed, s2.packed)            # construction leaves the state untouched
+  for rep in range(4):
+    if rep == 2:
+      a.params.mul_(0.9)                              # optimizer-style in-place update
+    g.replay()
+    sums2.accumulate(ham, s2.packed)
+    s2.mc_steps(a, 36)
+    assert torch.equal(s1.packed, s2.packed)
+  assert torch.equal(sums1.sums, sums2.sums)
+  assert torch.equal(sums1.stats, sums2.stats)
+  assert torch.equal(s1.accept_count, s2.accept_count)
+  assert s1.step == s2.step and int(s1.step_dev.item()) == s1.step
+
+
 def test_energy_stats(native):
   e = torch.randn(100003, device='cuda')
   stats = native.energy_stats(e)
