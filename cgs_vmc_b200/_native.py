@@ -177,6 +177,7 @@ class Ansatz:
 
   # ---- compute entry points -------------------------------------------
   def log_amp(self, packed, out=None):
+    self._sync_params()
     b = packed.shape[0]
     _want(packed, torch.int64, (b, n_words(self.n_sites)), 'packed')
     if out is None:
@@ -212,6 +213,7 @@ class Ansatz:
                                        _ptr(log_amp_out), _stream()))
 
   def mc_step_replay(self, packed, u_sites, u_acc):
+    self._sync_params()
     b = packed.shape[0]
     _want(packed, torch.int64, (b, n_words(self.n_sites)), 'packed')
     _want(u_sites, torch.float32, (b, self.n_sites), 'u_sites')

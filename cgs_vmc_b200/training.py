@@ -1,17 +1,21 @@
-"""Mirror of the reference's training.py for the hot-path optimizers:
-EnergyGradientOptimizer (training.py:506-623) and
-SupervisedWavefunctionOptimizer (training.py:135-212), with the same
-TrainOps tuples, registries and epoch schedules.  The Metropolis loops of the
+"""Mirror of the reference's training.py for its working optimizers:
+EnergyGradientOptimizer (training.py:506-623),
+SupervisedWavefunctionOptimizer (135-212), LogOverlapSWO (298-404),
+DualSamplingSWO (407-503) and LogOverlapImaginaryTimeSWO (626-778), with the
+same TrainOps tuples, registries and epoch schedules.  Every estimator is the
+one device primitive S_k = sum_b w_kb O_b (cgsvmc_weighted_grad_sum) with
+different weight columns.  The Metropolis loops of the
 reference (one session.run per step) collapse into one persistent-kernel
 launch per sweep group; `session.run(train_ops.mc_step)` still performs a
 single step for drop-in callers.
 """
 import collections
+import copy
 import math
 
 import torch
 
-from . import distributed, engine, graph_builders
+from . import distributed, engine, graph_builders, wavefunctions
 from .session import Op
 
 TrainOpsTraditional = collections.namedtuple('TrainingOpsTraditional', [
@@ -219,6 +223,237 @@ class SupervisedWavefunctionOptimizer:
     session.run(train_ops.epoch_increment)
 
 
+class _OverlapSums:
+  """Accumulators of the log-overlap gradient shared by LogOverlapSWO and
+  LogOverlapImaginaryTimeSWO (training.py:336-360, 672-699): with O_b =
+  d log psi_b and a per-walker ratio r_b,
+    g = mean_batches(sum_b O_b) - mean_batches(sum_b r_b O_b) / mean_samples(r)
+  (tf.gradients sums over the batch, tf.metrics.mean_tensor averages over
+  accumulate calls, tf.metrics.mean over samples).  One packed float32 buffer
+  [2P + 4] = [S_1 | S_r | sum r, sum e, n, 0] is the all-reduce payload."""
+
+  def __init__(self, ansatz, local_batch):
+    dev = ansatz.params.device
+    self.ansatz, self.P = ansatz, ansatz.num_params
+    self.buf = torch.zeros(2 * self.P + 4, dtype=torch.float32, device=dev)
+    self.sums = self.buf[:2 * self.P].view(2, self.P)
+    self.tail = self.buf[2 * self.P:]
+    self.scratch = torch.zeros(2, self.P, dtype=torch.float32, device=dev)
+    self.weights = torch.ones(2, local_batch, dtype=torch.float32, device=dev)
+    self.n_batches = 0
+    self.reduced = False
+
+  def reset(self):
+    self.buf.zero_()
+    self.n_batches = 0
+    self.reduced = False
+
+  def accumulate(self, packed, ratio, energy=None):
+    self.weights[1].copy_(ratio)
+    self.scratch.zero_()
+    self.ansatz.weighted_grad_sum(packed, self.weights, out=self.scratch)
+    self.sums.add_(self.scratch)
+    self.tail[0] += ratio.sum()
+    if energy is not None:
+      self.tail[1] += energy.sum()
+    self.tail[2] += float(ratio.numel())
+    self.n_batches += 1
+    self.reduced = False
+
+  def _reduce(self):
+    if not self.reduced:
+      distributed.allreduce_(self.buf)
+      self.reduced = True
+
+  def gradient(self):
+    self._reduce()
+    nb = float(self.n_batches)
+    mean_ratio = self.tail[0] / self.tail[2]
+    return self.sums[0] / nb - (self.sums[1] / nb) / mean_ratio
+
+  def mean_energy(self):
+    self._reduce()
+    return float((self.tail[1] / self.tail[2]).item())
+
+
+class LogOverlapSWO:
+  """SWO with |psi|^2 sampling and log |<psi|phi>|^2 as the objective,
+  training.py:298-404."""
+
+  def build_opt_ops(self, wavefunction, target_wavefunction, hparams, shared_resources):
+    n_sites = hparams.num_sites
+    local_batch, walker_id0 = distributed.shard(hparams.batch_size)
+    configs = graph_builders.get_configs(shared_resources, local_batch, n_sites,
+                                         walker_id0=walker_id0)
+    mc_step, acc_rate = graph_builders.get_monte_carlo_sampling(
+        shared_resources, configs, wavefunction)
+    ansatz = wavefunction.native(n_sites)
+    target = target_wavefunction.native(n_sites)
+    optimizer = create_sgd_optimizer(hparams)
+    sums = _OverlapSums(ansatz, local_batch)
+
+    def accumulate():                      # ratio = psi_target / psi, training.py:339
+      z = ansatz.log_amp(configs.packed) - wavefunction._exp_norm_shift
+      zt = target.log_amp(configs.packed) - target_wavefunction._exp_norm_shift
+      sums.accumulate(configs.packed, torch.exp(zt - z))
+
+    def apply_gradients():                 # training.py:358-362
+      optimizer.apply_gradients(ansatz.params, sums.gradient())
+
+    self.sums = sums
+    return TrainOpsSupervised(
+        accumulate_gradients=Op(accumulate, 'accumulate_gradients'),
+        apply_gradients=Op(apply_gradients, 'apply_gradients'),
+        reset_gradients=Op(sums.reset, 'reset_gradients'),
+        mc_step=mc_step, acc_rate=acc_rate, metrics=None,
+        update_wf_norm=wavefunction.update_norm(lambda: wavefunction(configs)),
+        epoch_increment=_epoch_increment())
+
+  def run_optimization_epoch(self, train_ops, session, hparams, epoch_number):
+    """training.py:382-404."""
+    del epoch_number
+    for _ in range(hparams.num_batches_per_epoch):
+      session.run(train_ops.mc_step,
+                  n_steps=hparams.num_monte_carlo_sweeps * hparams.num_sites)
+      session.run(train_ops.reset_gradients)
+      session.run(train_ops.accumulate_gradients)
+      session.run(train_ops.apply_gradients)
+    session.run(train_ops.epoch_increment)
+
+
+class DualSamplingSWO:
+  """SWO sampling |psi|^2 of both the trainee and the target with the plain
+  L2 loss mean (psi - t)^2, training.py:407-503."""
+
+  TARGET_SEED_XOR = 0x7A46E7      # the target walkers get their own Philox key
+
+  def build_opt_ops(self, wavefunction, target_wavefunction, hparams, shared_resources):
+    n_sites = hparams.num_sites
+    local_half, walker_id0 = distributed.shard(hparams.batch_size // 2)
+    psi_configs = graph_builders.get_configs(shared_resources, local_half, n_sites,
+                                             walker_id0=walker_id0)
+    target_configs = graph_builders.get_configs(
+        shared_resources, local_half, n_sites,
+        configs_id=graph_builders.ResourceName.TARGET_CONFIGS,
+        seed=0xC65 ^ self.TARGET_SEED_XOR, walker_id0=walker_id0)
+    # explicit, separate samplers for the two wavefunctions (training.py:441-447)
+    target_mc_step, target_acc = graph_builders.build_monte_carlo_sampling(
+        target_configs, target_wavefunction)
+    psi_mc_step, psi_acc = graph_builders.build_monte_carlo_sampling(psi_configs, wavefunction)
+    ansatz = wavefunction.native(n_sites)
+    target = target_wavefunction.native(n_sites)
+    optimizer = create_sgd_optimizer(hparams)
+    dev = ansatz.params.device
+    grad = torch.zeros(1, ansatz.num_params, dtype=torch.float32, device=dev)
+    log_norm = 0.5 * n_sites * math.log(2.0)       # sqrt(2^N), training.py:451
+    total = float(2 * local_half * distributed.world_size())
+
+    def mc_step(n_steps=1):
+      psi_mc_step(n_steps=n_steps)
+      target_mc_step(n_steps=n_steps)
+
+    def acc_rate():
+      return [psi_acc(), target_acc()]
+
+    def loss_and_weights():
+      packed = torch.cat([psi_configs.packed, target_configs.packed], dim=0)
+      psi = torch.exp(ansatz.log_amp(packed) - wavefunction._exp_norm_shift)
+      t = torch.exp(target.log_amp(packed) - target_wavefunction._exp_norm_shift + log_norm)
+      diff = psi - t
+      loss = (diff * diff).sum() / total                 # training.py:461-463
+      weights = (2.0 * diff * psi / total).reshape(1, -1).contiguous()
+      return packed, loss, weights
+
+    def train_step():                      # optimizer.minimize(loss), training.py:466
+      packed, loss, weights = loss_and_weights()
+      grad.zero_()
+      ansatz.weighted_grad_sum(packed, weights, out=grad)
+      distributed.allreduce_(grad)
+      optimizer.apply_gradients(ansatz.params, grad[0])
+      return loss
+
+    def metrics():
+      _, loss, _ = loss_and_weights()
+      return float(distributed.allreduce_(loss.clone()).item())
+
+    self.loss_and_weights = loss_and_weights
+    return TrainOpsSupervised(
+        accumulate_gradients=None, apply_gradients=Op(train_step, 'train_step'),
+        reset_gradients=None, mc_step=Op(mc_step, 'mc_step'), acc_rate=Op(acc_rate, 'acc_rate'),
+        metrics=Op(metrics, 'loss'), update_wf_norm=None,
+        epoch_increment=_epoch_increment())
+
+  def run_optimization_epoch(self, train_ops, session, hparams, epoch_number):
+    """training.py:483-503."""
+    del epoch_number
+    for _ in range(hparams.num_batches_per_epoch):
+      session.run(train_ops.mc_step,
+                  n_steps=hparams.num_monte_carlo_sweeps * hparams.num_sites)
+      session.run(train_ops.apply_gradients)
+    session.run(train_ops.epoch_increment)
+
+
+class LogOverlapImaginaryTimeSWO(WavefunctionOptimizer):
+  """Imaginary-time SWO through the log-overlap gradient, training.py:626-778:
+  the supervisor psi_O is a deep copy of the trainee refreshed once per epoch
+  and the target is (1 - beta H) psi_O."""
+
+  def build_opt_ops(self, wavefunction, hamiltonian, hparams, shared_resources):
+    n_sites = hparams.num_sites
+    local_batch, walker_id0 = distributed.shard(hparams.batch_size)
+    configs = graph_builders.get_configs(shared_resources, local_batch, n_sites,
+                                         walker_id0=walker_id0)
+    mc_step, acc_rate = graph_builders.get_monte_carlo_sampling(
+        shared_resources, configs, wavefunction)
+    ansatz = wavefunction.native(n_sites)
+    wf_omega = copy.deepcopy(wavefunction)        # supervisor, training.py:661
+    omega = wf_omega.native(n_sites)
+    ham = hamiltonian.native(n_sites)
+    beta = float(hparams.time_evolution_beta)
+    optimizer = create_sgd_optimizer(hparams)
+    sums = _OverlapSums(ansatz, local_batch)
+
+    def accumulate():
+      # H psi_O = E_loc[psi_O] psi_O (apply_in_place, operators.py:261-271), so
+      # ratio = (psi_O - beta H psi_O) / psi = exp(z_O - z) (1 - beta E_O)
+      e_omega, z_omega = omega.local_energy(ham, configs.packed)
+      z = ansatz.log_amp(configs.packed) - wavefunction._exp_norm_shift
+      ratio = torch.exp(z_omega - wf_omega._exp_norm_shift - z) * (1.0 - beta * e_omega)
+      sums.accumulate(configs.packed, ratio, energy=e_omega)
+
+    def apply_gradients():                 # training.py:693-701
+      optimizer.apply_gradients(ansatz.params, sums.gradient())
+
+    self.sums, self.supervisor = sums, wf_omega
+    return TrainOpsSWO(
+        train_step=None,
+        accumulate_gradients=Op(accumulate, 'accumulate_gradients'),
+        apply_gradients=Op(apply_gradients, 'apply_gradients'),
+        reset_gradients=Op(sums.reset, 'reset_gradients'),
+        mc_step=mc_step, acc_rate=acc_rate, metrics=None,
+        energy=Op(sums.mean_energy, 'mean_energy'),
+        update_supervisor=wavefunctions.module_transfer_ops(wavefunction, wf_omega),
+        update_normalization=None,
+        epoch_increment=_epoch_increment(),
+        update_wf_norm=wavefunction.update_norm(lambda: wavefunction(configs)))
+
+  def run_optimization_epoch(self, train_ops, session, hparams, epoch_number=0):
+    """training.py:729-778."""
+    session.run(train_ops.mc_step,
+                n_steps=hparams.num_equilibration_sweeps * hparams.num_sites)
+    if train_ops.update_wf_norm is not None:
+      session.run(train_ops.update_wf_norm)
+    session.run(train_ops.update_supervisor)
+    for _ in range(hparams.num_batches_per_epoch):
+      session.run(train_ops.mc_step,
+                  n_steps=hparams.num_monte_carlo_sweeps * hparams.num_sites)
+      session.run(train_ops.reset_gradients)
+      session.run(train_ops.accumulate_gradients)
+      session.run(train_ops.apply_gradients)
+    session.run(train_ops.epoch_increment)
+    return session.run(train_ops.energy)
+
+
 def _not_built(name, why):
   class _NotBuilt:
     def __init__(self, *args, **kwargs):
@@ -229,8 +464,7 @@ def _not_built(name, why):
 
 GROUND_STATE_OPTIMIZERS = {     # training.py:913-917
     'EnergyGradient': EnergyGradientOptimizer,
-    'LogOverlapITSWO': _not_built('LogOverlapImaginaryTimeSWO',
-                                  'next row after the hot path (SURVEY.md 8(f) rank 2)'),
+    'LogOverlapITSWO': LogOverlapImaginaryTimeSWO,
     'ITSWO': _not_built('ImaginaryTimeSWO',
                         'raises AttributeError at graph build in the reference '
                         '(hparams.time_evolution_befta, training.py:812)'),
@@ -238,8 +472,8 @@ GROUND_STATE_OPTIMIZERS = {     # training.py:913-917
 
 SUPERVISED_OPTIMIZERS = {       # training.py:920-925
     'SWO': SupervisedWavefunctionOptimizer,
-    'LogOverlapSWO': _not_built('LogOverlapSWO', 'next row (SURVEY.md 8(f) rank 2)'),
-    'DualSamplingSWO': _not_built('DualSamplingSWO', 'next row (SURVEY.md 8(f) rank 2)'),
+    'LogOverlapSWO': LogOverlapSWO,
+    'DualSamplingSWO': DualSamplingSWO,
     'BasisIterSWO': _not_built('BasisIterationSWO',
                                'calls the non-existent scipy.special.binomi in the reference '
                                '(training.py:246)'),

@@ -85,3 +85,34 @@ def energy_stats(e_loc):
   """Sum E, sum E^2, count: what K5 packs next to the gradient sums."""
   e = e_loc.to(torch.float64)
   return float(e.sum()), float((e * e).sum()), e.numel()
+
+
+def log_overlap_grad(spec, params, configs, ratio):
+  """LogOverlapSWO / LogOverlapImaginaryTimeSWO gradient for one batch
+  (training.py:336-360, 672-699): tf.gradients sums over the batch,
+  tf.metrics.mean(ratio) is a per-sample mean, so
+    g = sum_b O_b - (sum_b r_b O_b) / mean_b(r_b)."""
+  ones = torch.ones_like(ratio)
+  s = weighted_grad_sum(spec, params, configs, torch.stack([ones, ratio]))
+  return s[0] - s[1] / ratio.mean()
+
+
+def dual_sampling_loss_and_grad(spec, params, configs, psi_target, shift=-10.0):
+  """DualSamplingSWO (training.py:452-466): loss = mean_b (psi_b - t_b)^2 with
+  t = psi_target * sqrt(2^N), NOT divided by psi^2; d loss = mean_b 2 (psi_b -
+  t_b) psi_b O_b.  `configs` is concat([psi walkers, target walkers])."""
+  n_sites = configs.shape[1]
+  z = _ansatz.log_amp(spec, params, configs)
+  psi = torch.exp(z - shift)
+  t = psi_target.to(psi.dtype) * math.sqrt(2.0 ** n_sites)
+  loss = torch.mean((psi - t) ** 2)
+  w = 2.0 * (psi - t) * psi / configs.shape[0]
+  grad = weighted_grad_sum(spec, params, configs, w[None, :])[0]
+  return loss, grad
+
+
+def imaginary_time_ratio(psi, psi_omega, e_loc_omega, beta):
+  """training.py:655-670: ratio = (psi_O - beta H psi_O) / psi with
+  H psi_O = E_loc[psi_O] psi_O (apply_in_place, operators.py:261-271); the
+  supervisor energy estimate is mean(E_loc[psi_O]) (training.py:662, 681)."""
+  return psi_omega * (1.0 - beta * e_loc_omega) / psi

@@ -18,9 +18,20 @@ def pytest_configure(config):
   config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
 
 
-def golden_names():
+def _names():
   return sorted(os.path.basename(p)[:-4]
                 for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+
+
+def golden_names():
+  """Cases of make_golden.py (amplitudes, sampler, Hamiltonian, EnergyGradient, SWO)."""
+  return [n for n in _names() if not n.startswith('opt_')]
+
+
+def opt_golden_names():
+  """Cases of make_golden_optimizers.py (LogOverlapSWO, DualSamplingSWO,
+  LogOverlapImaginaryTimeSWO)."""
+  return [n for n in _names() if n.startswith('opt_')]
 
 
 def load_golden(name):
@@ -33,5 +44,11 @@ def load_golden(name):
 
 @pytest.fixture(params=golden_names())
 def golden(request):
+  spec, data = load_golden(request.param)
+  return request.param, spec, data
+
+
+@pytest.fixture(params=opt_golden_names())
+def opt_golden(request):
   spec, data = load_golden(request.param)
   return request.param, spec, data

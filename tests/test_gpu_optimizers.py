@@ -1,0 +1,181 @@
+"""LogOverlapSWO, DualSamplingSWO and LogOverlapImaginaryTimeSWO on the CUDA
+path (cgs_vmc_b200.training) against gradients recorded from the reference's
+own build_opt_ops (tests/golden/opt_*.npz, made by make_golden_optimizers.py),
+plus end-to-end convergence checks against exact diagonalisation."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, opt_golden_names
+from oracle import ansatz as oansatz
+from oracle import ed, lattices
+
+pytestmark = pytest.mark.gpu
+
+GRAD_RTOL = 3e-4     # of the largest entry (float32 estimator sums)
+
+
+def _hparams(spec, **extra):
+  from cgs_vmc_b200 import utils
+  if spec.kind in ('fully_connected', 'rbm'):
+    kw = dict(num_fc_layers=spec.num_layers, fc_layer_size=spec.layer_size)
+  else:
+    kw = dict(num_conv_layers=spec.num_layers, num_conv_filters=spec.num_filters,
+              kernel_size=spec.kernel_size, size_x=spec.size_x, size_y=spec.size_y)
+  kw.update(extra)
+  return utils.create_hparams(wavefunction_type=spec.kind, num_sites=spec.n_sites,
+                              nonlinearity=spec.nonlinearity, **kw)
+
+
+def _wavefunction(hp, flat, shift):
+  from cgs_vmc_b200 import wavefunctions
+  wf = wavefunctions.build_wavefunction(hp)
+  wf.native(hp.num_sites).set_params(torch.from_numpy(flat))
+  wf._exp_norm_shift = float(shift)
+  return wf
+
+
+def _close(got, ref, rtol=GRAD_RTOL):
+  scale = float(np.abs(ref).max())
+  np.testing.assert_allclose(got.detach().cpu().numpy(), ref, rtol=0, atol=rtol * scale)
+
+
+@pytest.mark.parametrize('name', opt_golden_names())
+def test_log_overlap_swo_gradient_golden(name):
+  from cgs_vmc_b200 import graph_builders, training
+  from cgs_vmc_b200.session import Session
+  spec, g = load_golden(name)
+  hp = _hparams(spec, batch_size=g['lo_configs'].shape[0])
+  wf = _wavefunction(hp, g['params_flat'], g['shift'])
+  target = _wavefunction(hp, g['target_params_flat'], g['target_shift'])
+  opt = training.SUPERVISED_OPTIMIZERS['LogOverlapSWO']()
+  shared = {}
+  ops = opt.build_opt_ops(wavefunction=wf, target_wavefunction=target, hparams=hp,
+                          shared_resources=shared)
+  shared[graph_builders.ResourceName.CONFIGS].assign(torch.from_numpy(g['lo_configs']))
+  s = Session()
+  s.run(ops.reset_gradients)
+  s.run(ops.accumulate_gradients)
+  _close(opt.sums.gradient(), g['lo_gradient'])
+  # tf.metrics.mean_tensor semantics: two identical accumulate calls average back
+  s.run(ops.accumulate_gradients)
+  _close(opt.sums.gradient(), g['lo_gradient'])
+
+
+@pytest.mark.parametrize('name', opt_golden_names())
+def test_dual_sampling_swo_golden(name):
+  from cgs_vmc_b200 import graph_builders, training
+  spec, g = load_golden(name)
+  half = g['ds_psi_configs'].shape[0]
+  hp = _hparams(spec, batch_size=2 * half)
+  wf = _wavefunction(hp, g['params_flat'], g['shift'])
+  # ds_target_shift already holds the -N/2 ln 2 that the optimizer's sqrt(2^N) undoes
+  target = _wavefunction(hp, g['target_params_flat'], g['ds_target_shift'])
+  opt = training.SUPERVISED_OPTIMIZERS['DualSamplingSWO']()
+  shared = {}
+  ops = opt.build_opt_ops(wavefunction=wf, target_wavefunction=target, hparams=hp,
+                          shared_resources=shared)
+  assert shared[graph_builders.ResourceName.CONFIGS].shape == (half, spec.n_sites)
+  assert shared[graph_builders.ResourceName.TARGET_CONFIGS].shape == (half, spec.n_sites)
+  shared[graph_builders.ResourceName.CONFIGS].assign(torch.from_numpy(g['ds_psi_configs']))
+  shared[graph_builders.ResourceName.TARGET_CONFIGS].assign(torch.from_numpy(g['ds_target_configs']))
+  packed, loss, weights = opt.loss_and_weights()
+  assert abs(float(loss) - float(g['ds_loss'])) <= 2e-4 * abs(float(g['ds_loss']))
+  grad = wf.native().weighted_grad_sum(packed, weights)
+  _close(grad[0], g['ds_gradient'])
+  assert ops.accumulate_gradients is None and ops.reset_gradients is None
+
+
+@pytest.mark.parametrize('name', opt_golden_names())
+def test_log_overlap_itswo_golden(name):
+  from cgs_vmc_b200 import graph_builders, operators, training
+  from cgs_vmc_b200.session import Session
+  spec, g = load_golden(name)
+  hp = _hparams(spec, batch_size=g['it_configs'].shape[0], time_evolution_beta=float(g['it_beta']))
+  wf = _wavefunction(hp, g['params_flat'], g['shift'])
+  ham = operators.HeisenbergHamiltonian([tuple(b) for b in g['bonds_ij']],
+                                        float(g['bonds_jx'][0]), float(g['bonds_jz'][0]))
+  opt = training.GROUND_STATE_OPTIMIZERS['LogOverlapITSWO']()
+  shared = {}
+  ops = opt.build_opt_ops(wavefunction=wf, hamiltonian=ham, hparams=hp, shared_resources=shared)
+  assert opt.supervisor is not wf and opt.supervisor._unique_name.startswith('dc_')
+  opt.supervisor.native().set_params(torch.from_numpy(g['it_omega_params_flat']))
+  opt.supervisor._exp_norm_shift = float(g['it_omega_shift'])
+  shared[graph_builders.ResourceName.CONFIGS].assign(torch.from_numpy(g['it_configs']))
+  s = Session()
+  s.run(ops.reset_gradients)
+  s.run(ops.accumulate_gradients)
+  _close(opt.sums.gradient(), g['it_gradient'])
+  e = s.run(ops.energy)
+  assert abs(e - float(g['it_energy'])) <= 5e-5 * (1 + abs(float(g['it_energy'])))
+  # update_supervisor copies the trainee's variables (wavefunctions.py:300-325)
+  s.run(ops.update_supervisor)
+  assert torch.equal(opt.supervisor.native().params, wf.native().params)
+  assert opt.supervisor.native().params.data_ptr() != wf.native().params.data_ptr()
+
+
+def _all_sz0(n):
+  idx = [i for i in range(2 ** n) if bin(i).count('1') == n // 2]
+  c = np.array([[1.0 if (i >> k) & 1 else -1.0 for k in range(n)] for i in idx], dtype=np.float32)
+  return torch.from_numpy(c)
+
+
+def _overlap(wf, target, cfg):
+  a = wf.log_amplitude(cfg).double()
+  b = target.log_amplitude(cfg).double()
+  pa, pb = torch.exp(a - a.max()), torch.exp(b - b.max())
+  return float((pa * pb).sum() ** 2 / ((pa * pa).sum() * (pb * pb).sum()))
+
+
+def test_log_overlap_itswo_reaches_ed_energy():
+  """run_optimization_epoch end to end on the 8-site chain: imaginary-time
+  SWO drives the supervisor energy to exact diagonalisation (-3.6511)."""
+  from cgs_vmc_b200 import graph_builders, operators, training, utils, wavefunctions
+  from cgs_vmc_b200.session import Session
+  graph_builders.reset_num_epochs()
+  hp = utils.create_hparams(wavefunction_type='rbm', num_sites=8, num_fc_layers=0, fc_layer_size=16,
+                            batch_size=2048, num_batches_per_epoch=10, num_equilibration_sweeps=3,
+                            time_evolution_beta=0.1,
+                            learning_rates=[0.01, 0.005, 0.002, 0.001], learning_rate_stops=[60, 100, 140])
+  wf = wavefunctions.build_wavefunction(hp).seed(2)
+  ham = operators.HeisenbergHamiltonian(lattices.chain_bonds(8), -1.0, 1.0)
+  opt = training.GROUND_STATE_OPTIMIZERS['LogOverlapITSWO']()
+  ops = opt.build_opt_ops(wavefunction=wf, hamiltonian=ham, hparams=hp, shared_resources={})
+  s = Session()
+  energies = [opt.run_optimization_epoch(ops, s, hp) for _ in range(120)]
+  e0, _, _ = ed.ground_state(8, *lattices.heisenberg_couplings(lattices.chain_bonds(8)))
+  assert energies[0] > np.mean(energies[-10:])
+  assert abs(np.mean(energies[-10:]) - e0) < 0.03 * abs(e0), (energies[0], energies[-10:], e0)
+
+
+@pytest.mark.parametrize('optimizer', ['LogOverlapSWO', 'DualSamplingSWO'])
+def test_supervised_optimizers_increase_overlap(optimizer):
+  """Exact overlap |<psi|phi>|^2 / (<psi|psi><phi|phi>) over all 70 Sz=0 states
+  of 8 sites grows under training."""
+  from cgs_vmc_b200 import graph_builders, training, utils, wavefunctions
+  from cgs_vmc_b200.session import Session
+  graph_builders.reset_num_epochs()
+  hp = utils.create_hparams(wavefunction_type='rbm', num_sites=8, num_fc_layers=0, fc_layer_size=8,
+                            batch_size=2048, num_batches_per_epoch=10,
+                            learning_rates=[0.01, 0.01, 0.01, 0.01])
+  target = wavefunctions.build_wavefunction(hp).seed(7)
+  trainee = wavefunctions.build_wavefunction(hp).seed(8)
+  target.native(8)
+  with torch.no_grad():
+    target.native().params.mul_(3.0)          # a target with structure
+  trainee.native(8)
+  cfg = _all_sz0(8).cuda()
+  if optimizer == 'DualSamplingSWO':          # the plain L2 loss is not scale free
+    za, zb = trainee.log_amplitude(cfg), target.log_amplitude(cfg)
+    target._exp_norm_shift += float((zb - za).mean()) + 0.5 * 8 * np.log(2.0)
+    trainee._exp_norm_shift += float(za.max())
+    target._exp_norm_shift += float(za.max())
+  before = _overlap(trainee, target, cfg)
+  opt = training.SUPERVISED_OPTIMIZERS[optimizer]()
+  ops = opt.build_opt_ops(wavefunction=trainee, target_wavefunction=target, hparams=hp,
+                          shared_resources={})
+  s = Session()
+  for epoch in range(40):
+    opt.run_optimization_epoch(ops, s, hp, epoch)
+  after = _overlap(trainee, target, cfg)
+  assert after > before and 1.0 - after < 0.5 * (1.0 - before), (before, after)
