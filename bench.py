@@ -54,15 +54,15 @@ def peaks():
 
 
 def problem():
-  """Synthetic inputs of SURVEY.md 8(d): Sonnet-default weights (seed 1234),
-  NN bonds with (jx, jz) = (-1, 1)."""
-  from oracle import ansatz as oansatz
-  from oracle import lattices
-  spec = oansatz.AnsatzSpec('rbm', N_SITES, num_layers=0, layer_size=HIDDEN,
-                            size_x=SIZE, size_y=SIZE)
-  flat = oansatz.flatten(oansatz.init_params(spec, seed=1234)).float()
+  """Synthetic inputs of SURVEY.md 8(d): Sonnet-default weights (truncated
+  normal, sigma = 1 / sqrt(fan_in), zero biases; torch.Generator seed 1234) in
+  the flat layout of include/cgsvmc.h, NN bonds with (jx, jz) = (-1, 1)."""
+  from cgs_vmc_b200 import lattices, wavefunctions
+  gen = torch.Generator().manual_seed(1234)
+  shapes = [(N_SITES, 1), (1,), (N_SITES, HIDDEN), (HIDDEN,)]     # a, a0, W, c
+  flat = torch.cat([t.reshape(-1) for t in wavefunctions._sonnet_init(shapes, gen)]).float()
   ij, jx, jz = lattices.heisenberg_couplings(lattices.square_nn_bonds(SIZE), -1.0, 1.0)
-  return spec, flat, ij, jx, jz
+  return flat, ij, jx, jz
 
 
 # ----------------------------------------------------------------------------
@@ -124,8 +124,10 @@ class ClockSampler:
 # CPU arm: the reference-equivalent op sequence on the host cores
 # ----------------------------------------------------------------------------
 def cpu_arm(walkers, steps, warmup):
+  from oracle import ansatz as oansatz
   from oracle import bits, cpu_baseline
-  spec, flat, ij, jx, jz = problem()
+  flat, ij, jx, jz = problem()
+  spec = oansatz.AnsatzSpec('rbm', N_SITES, num_layers=0, layer_size=HIDDEN, size_x=SIZE, size_y=SIZE)
   cores = os.cpu_count() or 1
   torch.set_num_threads(cores)
   cfg = bits.random_sz0_configs(N_SITES, walkers, np.random.default_rng(1234))
@@ -181,7 +183,7 @@ def run_ours(args, rank, world, local_rank):
   dev = torch.device('cuda', local_rank)
   if world > 1:
     dist.init_process_group('nccl', device_id=dev)
-  spec, flat, ij, jx, jz = problem()
+  flat, ij, jx, jz = problem()
   B = args.walkers
   ansatz = _native.Ansatz('rbm', N_SITES, num_layers=0, layer_size=HIDDEN, device=dev)
   ansatz.set_params(flat)
@@ -205,7 +207,7 @@ def run_ours(args, rank, world, local_rank):
     when per-phase events are wanted, as separate launches."""
     if graphed is not None and events is None:
       graphed.replay()
-      launches[0] += 5   # prep, walker kernel, reduce, mc kernel, step-counter advance
+      launches[0] += 2   # fused estimator + sweep kernel, reduction (+ table build after a parameter update)
     else:
       if events: events[0].record()
       sums.accumulate(ham, state.packed)     # E_loc + both gradient sums + energy statistics
@@ -265,49 +267,24 @@ def run_ours(args, rank, world, local_rank):
   total_s = float(total.item())
 
   # ---- e2e: the same step through host buffers -----------------------------
+  # engine.HostFedBatchStep: the float32 [B, N] configuration tensor of the
+  # reference (graph_builders.py:92-125) comes from pinned host memory every
+  # step (copy stream, double-buffered: the upload of batch k overlaps the
+  # compute of batch k - 1); pack + batch step + the device->host copy of the
+  # [2, P] sums and the energy statistics are one captured graph per slot.
+  # Every step's copies are inside the timed region.
   host_cfg = torch.empty(B, N_SITES, dtype=torch.float32).pin_memory()
   host_cfg.copy_(state.configs().cpu())
-  host_stats = torch.empty(4, dtype=torch.float64).pin_memory()
-  host_sums = torch.empty(2, P, dtype=torch.float32).pin_memory()
-  dev_cfg = torch.empty(B, N_SITES, dtype=torch.float32, device=dev)
-
-  copy_stream = torch.cuda.Stream(device=dev)
-  dev_cfgs = [dev_cfg, torch.empty_like(dev_cfg)]
-  h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
-  consumed = [torch.cuda.Event(), torch.cuda.Event()]
-  results_ready = [torch.cuda.Event(), torch.cuda.Event()]
-  host_out = [(host_sums, host_stats), (torch.empty_like(host_sums).pin_memory(),
-                                        torch.empty_like(host_stats).pin_memory())]
-  main = torch.cuda.current_stream()
-
-  def e2e_issue(k):
-    """The step as a host-side caller sees it: the float32 [B, N] configuration
-    tensor of the reference (graph_builders.py:92-125) comes from pinned host
-    memory, the estimator sums and energy statistics go back to the host.  The
-    upload of batch k runs on a copy stream and overlaps the compute of batch
-    k - 1 (double buffering); every step's copies are inside the timed region."""
-    i = k & 1
-    with torch.cuda.stream(copy_stream):
-      copy_stream.wait_event(consumed[i])
-      dev_cfgs[i].copy_(host_cfg, non_blocking=True)              # H2D inputs
-      h2d_done[i].record(copy_stream)
-    main.wait_event(h2d_done[i])
-    _native.pack_configs(dev_cfgs[i], out=state.packed)
-    consumed[i].record(main)
-    step()
-    host_out[i][0].copy_(sums.sums, non_blocking=True)            # D2H result: [2, P] sums
-    host_out[i][1].copy_(sums.stats, non_blocking=True)           # D2H result: energy statistics
-    results_ready[i].record(main)
+  fed = engine.HostFedBatchStep(state, ansatz, ham, sums, SWEEP_STEPS)
 
   def e2e_run(n):
     for k in range(n):
-      e2e_issue(k)
-      if k > 0:
-        results_ready[(k - 1) & 1].synchronize()                  # host consumes step k - 1
-    results_ready[(n - 1) & 1].synchronize()
+      fed.submit(host_cfg)
+      if fed.outstanding() > 1:
+        fed.result()                                              # host consumes step k - 1
+    while fed.outstanding():
+      fed.result()
 
-  for ev_ in consumed:
-    ev_.record(main)
   e2e_run(4)
   torch.cuda.synchronize()
   if world > 1:
@@ -329,34 +306,29 @@ def run_ours(args, rank, world, local_rank):
 
   # ---- bookkeeping ----------------------------------------------------------
   pk = peaks()
-  n_act = float(np.mean(__import__('oracle').hamiltonian.n_active(
-      state.configs().cpu().numpy(), ij)))
+  cfg_now = state.configs()
+  bonds_t = torch.as_tensor(np.asarray(ij), device=dev, dtype=torch.long)
+  n_act = float((cfg_now[:, bonds_t[:, 0]] * cfg_now[:, bonds_t[:, 1]] < 0).sum(dim=1).float().mean().item())
   walkers_total = B * world
   value = walkers_total * SWEEP_STEPS * args.steps / total_s
   eloc_rate = walkers_total * args.steps / total_s
-  # dominant kernel = the one with the largest share of the step
-  shares = {'rbm2::walker_kernel (accumulate: E_loc + grad sums + stats) + prep + reduce': float(t_acc.mean()),
-            'rbm2::mc_kernel (36 Metropolis steps) + prep': float(t_mc.mean())}
-  dominant = 'mc' if t_mc.mean() >= t_acc.mean() else 'accumulate'
+  # The step is one fused kernel (estimators + sweep) plus the reduction; the
+  # split launches below are timed only to show how the fused time divides.
+  shares = {'split launch: rbm2::walker_kernel (accumulate) + reduce': float(t_acc.mean()),
+            'split launch: rbm2::mc_kernel (36 Metropolis steps)': float(t_mc.mean())}
   H, N = HIDDEN, N_SITES
   f_inc = 4 * H + 4                                            # flop per ratio
   f_fwd = 2 * N * H + 2 * N + 6 * H                            # 10,440 + lncosh arithmetic
   f_grad = 2 * 2 * (N + 1) * (H + 1)                           # two weight columns, FMA = 2 flop
   tab_bytes = 2 * H * 4                                        # two table rows per ratio
-  if dominant == 'mc':
-    kernel = 'rbm2::mc_kernel'
-    ratios = B * SWEEP_STEPS
-    flop = ratios * f_inc + B * f_fwd
-    mufu = ratios * (H // 4 + 1) + ratios * 0.4 * H            # lg2 per 4 units, rcp on accept
-    bytes_alg = B * (2 * 8)
-    t_k = float(t_mc.mean())
-  else:
-    kernel = 'rbm2::walker_kernel'
-    ratios = B * n_act
-    flop = B * (f_fwd + f_grad) + ratios * f_inc
-    mufu = ratios * (H // 4 + 1) + B * 2 * H
-    bytes_alg = B * (8 + 8) + 148 * 2 * P * 4 * 2
-    t_k = float(t_acc.mean())
+  kernel = 'rbm2::walker_kernel<MC> (cgsvmc_batch_step: E_loc + gradient sums + 36 Metropolis steps)'
+  ratios = B * (n_act + SWEEP_STEPS)                           # E_loc bond flips + sampler proposals
+  flop = B * (f_fwd + f_grad) + ratios * f_inc
+  mufu = ratios * (H // 4 + 1) + B * 3 * H                     # lg2 per 4 units; ex2, rcp, lg2 per unit of the state build
+  bytes_alg = B * (8 + 8 + 4 + 4) + 148 * 2 * P * 4            # configs in/out, E_loc, z; per-CTA partial sums
+  # device time of the captured step (fused kernel + reduction + launch gap):
+  # an upper bound of the fused kernel's own duration, so `frac` is conservative
+  t_k = total_s / args.steps if graphed is not None else float(t_acc.mean() + t_mc.mean())
   f_hz = pk['sm_max_mhz'] * 1e6
   fp32_peak = 148 * 128 * 2 * f_hz / 1e12                      # TFLOP/s, derived
   mufu_peak = 148 * 16 * f_hz / 1e12                           # T transcendental/s, derived
@@ -375,7 +347,14 @@ def run_ours(args, rank, world, local_rank):
       'hbm': {'achieved': bytes_alg / t_k / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
               'frac': bytes_alg / t_k / 1e9 / pk['hbm_gbs'], 'peak_source': pk['source']},
       'kernel_ms': t_k * 1e3, 'n_active_bonds_mean': n_act,
+      'kernel_ms_is': 'CUDA-event time of the whole captured step on the launching stream (fused kernel + '
+                      'reduction); ncu share of the fused kernel: profiles/ launch list',
   }
+  traffic_path = os.path.join(REPO, 'profiles', 'dram_traffic.json')
+  if os.path.exists(traffic_path):          # dram__bytes_read + write of one ncu --set full capture
+    tr = json.load(open(traffic_path))
+    roofline['traffic'] = tr.get('bytes_per_launch')
+    roofline['traffic_source'] = tr.get('source')
   line = {
       'metric': 'walker_steps_per_sec', 'value': value, 'unit': 'walker-steps/s',
       'eloc_evals_per_sec': eloc_rate,
@@ -385,8 +364,9 @@ def run_ours(args, rank, world, local_rank):
       'config': {'workload': WORKLOAD, 'walkers_per_gpu': B, 'mc_steps_per_step': SWEEP_STEPS,
                  'n_bonds': 72, 'n_params': P,
                  'l2': 'flushed: %d MiB memset between steps, outside the per-step CUDA-event pairs' % (L2_FLUSH_BYTES >> 20),
-                 'launch': ('one captured CUDA graph per step (table build, walker kernel, reduce, '
-                            'mc kernel, step-counter advance)' if args.cuda_graph else 'kernel by kernel'),
+                 'launch': ('one captured CUDA graph per step: cgsvmc_batch_step = fused estimator + sweep '
+                            'kernel and the deterministic reduction (the table build is replayed only '
+                            'after a parameter update)' if args.cuda_graph else 'kernel by kernel'),
                  'parallelism': 'walkers sharded, params replicated' + (
                      ', one all-reduce of [2P+4] floats per epoch of %d steps' % EPOCH_BATCHES
                      if world > 1 else '')},
@@ -397,7 +377,7 @@ def run_ours(args, rank, world, local_rank):
       'e2e': {'value': walkers_total * SWEEP_STEPS * args.steps / e2e_s, 'unit': 'walker-steps/s',
               'eloc_evals_per_sec': walkers_total * args.steps / e2e_s,
               'ms_per_step': e2e_s / args.steps * 1e3,
-              'h2d_bytes_per_step': B * N_SITES * 4, 'd2h_bytes_per_step': 2 * P * 4 + 32},
+              'h2d_bytes_per_step': fed.h2d_bytes, 'd2h_bytes_per_step': fed.d2h_bytes},
       'gpu_launches': n_launch,
       'clocks': clocks,
       'wall_s_timed_region': wall,

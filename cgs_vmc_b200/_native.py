@@ -10,7 +10,9 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libcgsvmc.so')
+# CGSVMC_LIBRARY selects another build of the same library (the phase-timing
+# development build of profiles/run_rbm2_phases.py); never a different backend.
+LIB_PATH = os.environ.get('CGSVMC_LIBRARY') or os.path.join(_HERE, 'libcgsvmc.so')
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
 ANSATZ_KINDS = {'fully_connected': 1, 'rbm': 2, 'conv_1d': 3, 'conv_2d': 4}
@@ -25,7 +27,7 @@ EXPORTS = [
     'cgsvmc_pack_configs', 'cgsvmc_unpack_configs', 'cgsvmc_random_configs',
     'cgsvmc_log_amp', 'cgsvmc_mc_steps', 'cgsvmc_mc_steps_graph', 'cgsvmc_mc_step_replay',
     'cgsvmc_flip_enum', 'cgsvmc_local_energy', 'cgsvmc_weighted_grad_sum',
-    'cgsvmc_energy_stats', 'cgsvmc_accumulate',
+    'cgsvmc_energy_stats', 'cgsvmc_accumulate', 'cgsvmc_batch_step',
 ]
 
 
@@ -76,6 +78,7 @@ def load():
   lib.cgsvmc_weighted_grad_sum.argtypes = [vp, vp, vp, i64, i32, vp, vp]
   lib.cgsvmc_energy_stats.argtypes = [vp, i64, vp, vp]
   lib.cgsvmc_accumulate.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp]
+  lib.cgsvmc_batch_step.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, i32, u64, u64, u64, vp, vp, vp]
   for name in EXPORTS:
     fn = getattr(lib, name)
     if name not in ('cgsvmc_last_error', 'cgsvmc_ansatz_num_params'):
@@ -273,6 +276,31 @@ class Ansatz:
     check(load().cgsvmc_accumulate(self._handle, ham._handle, _ptr(packed), b,
                                    _ptr(e_loc_out), _ptr(log_amp_out), _ptr(sums),
                                    _ptr(stats), _stream()))
+
+  def batch_step(self, ham, packed, sums, stats, n_steps, seed, walker_id0=0, step0=0,
+                 step_counter=None, accept_count=None, e_loc_out=None, log_amp_out=None):
+    """accumulate() on the current configurations followed by n_steps
+    Metropolis steps (one batch iteration of run_optimization_epoch,
+    training.py:614-617); one kernel for the pure RBM.  With `step_counter`
+    (int64 [1] device tensor) the Philox offset is read from and advanced on
+    the device (CUDA-graph safe)."""
+    self._sync_params()
+    b = packed.shape[0]
+    _want(packed, torch.int64, (b, n_words(self.n_sites)), 'packed')
+    _want(sums, torch.float32, (2, self.num_params), 'sums')
+    _want(stats, torch.float64, (4,), 'stats')
+    if step_counter is not None:
+      _want(step_counter, torch.int64, (1,), 'step_counter')
+    if accept_count is not None:
+      _want(accept_count, torch.int64, (1,), 'accept_count')
+    if e_loc_out is not None:
+      _want(e_loc_out, torch.float32, (b,), 'e_loc_out')
+    if log_amp_out is not None:
+      _want(log_amp_out, torch.float32, (b,), 'log_amp_out')
+    check(load().cgsvmc_batch_step(self._handle, ham._handle, _ptr(packed), b, _ptr(e_loc_out),
+                                   _ptr(log_amp_out), _ptr(sums), _ptr(stats), int(n_steps),
+                                   int(seed), int(walker_id0), int(step0), _ptr(step_counter),
+                                   _ptr(accept_count), _stream()))
 
 
 class Hamiltonian:

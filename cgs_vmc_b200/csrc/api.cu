@@ -383,6 +383,34 @@ int cgsvmc_accumulate(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_
   return launch_energy_stats(w + B, B, stats, st);
 }
 
+int cgsvmc_batch_step(const cgsvmc_ansatz* a, const cgsvmc_ham* h, uint64_t* packed, int64_t B,
+                      float* e_loc_out, float* log_amp_out, float* sums, double* stats,
+                      int32_t n_steps, uint64_t seed, uint64_t walker_id0, uint64_t step0,
+                      uint64_t* step_counter, unsigned long long* accept_count, void* stream) {
+  if (int rc = check_ready(a)) return rc;
+  if (h == nullptr) return invalid("batch_step: NULL hamiltonian");
+  if (h->n_sites != a->desc.n_sites) return invalid("batch_step: hamiltonian and ansatz n_sites differ");
+  if (B < 0 || n_steps < 0) return invalid("batch_step: negative size");
+  if (B == 0) return CGSVMC_OK;
+  if (packed == nullptr || sums == nullptr || stats == nullptr) return invalid("batch_step: NULL buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rbm2_supported(a, h)) {
+    cgsvmc_ansatz* am = const_cast<cgsvmc_ansatz*>(a);
+    Rbm2Sweep sw = {n_steps, seed, walker_id0, step_counter != nullptr ? 0 : step0, accept_count,
+                    step_counter};   // the reduction kernel advances the counter
+    am->step_counter_dev = step_counter;
+    const int rc = rbm2_walker(am, h, packed, B, e_loc_out, log_amp_out, nullptr, nullptr, true, nullptr, 2,
+                               sums, stats, st, &sw);
+    am->step_counter_dev = nullptr;
+    return rc;
+  }
+  if (int rc = cgsvmc_accumulate(a, h, packed, B, e_loc_out, log_amp_out, sums, stats, stream)) return rc;
+  if (step_counter != nullptr)
+    return cgsvmc_mc_steps_graph(a, packed, B, n_steps, seed, walker_id0, step_counter, accept_count,
+                                 nullptr, stream);
+  return cgsvmc_mc_steps(a, packed, B, n_steps, seed, walker_id0, step0, accept_count, nullptr, stream);
+}
+
 int cgsvmc_energy_stats(const float* e_loc, int64_t B, double* stats, void* stream) {
   if (B < 0) return invalid("energy_stats: n_walkers < 0");
   if (B > 0 && (e_loc == nullptr || stats == nullptr)) return invalid("energy_stats: NULL buffer");

@@ -89,9 +89,18 @@ int rbm2_mc_steps(cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int n_steps, ui
 // One pass over the walkers: local energy when h != NULL (e_loc / log_amp /
 // diag / off nullable), weighted gradient sums when do_grad (weights NULL =>
 // rows (1, E_loc); out [K, P] +=; stats nullable double[4] +=).
+// sweep != NULL fuses sweep->n_steps Metropolis steps after the estimators
+// (`packed` is then written): one batch iteration in one launch.
+struct Rbm2Sweep {
+  int n_steps;
+  uint64_t seed, walker0, step0;
+  unsigned long long* accept_count;
+  uint64_t* advance_counter;   // device step counter to advance by n_steps afterwards, or NULL
+};
 int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, int64_t B,
                 float* e_loc, float* log_amp, float* diag, float* off, bool do_grad,
-                const float* weights, int K, float* out, double* stats, cudaStream_t s);
+                const float* weights, int K, float* out, double* stats, cudaStream_t s,
+                const Rbm2Sweep* sweep = nullptr);
 
 // ---- conv_1d / conv_2d forward on the tensor cores (conv_tc.cu): tcgen05 + TMEM ----
 bool conv_tc_supported(const cgsvmc_ansatz* a, const cgsvmc_ham* h);

@@ -12,7 +12,7 @@ namespace {
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // One block per site (rows of the tables + row sums), then one block per 128
-// hidden units (column sums).
+// hidden units (column sums), one block for the select table and one for max |W|.
 __global__ void __launch_bounds__(128)
 prep_kernel(Image im, const float* __restrict__ a, const float* __restrict__ a0,
             const float* __restrict__ W, const float* __restrict__ c, float* __restrict__ img) {
@@ -36,6 +36,22 @@ prep_kernel(Image im, const float* __restrict__ a, const float* __restrict__ a0,
       img[im.off_a2 + i] = 2.885390081777927f * (a[i] - total);
       img[im.off_a + i] = a[i];
     }
+  } else if (blockIdx.x == gridDim.x - 2) {
+    uint8_t* lut = reinterpret_cast<uint8_t*>(img + im.off_lut);
+    for (int e = tid; e < 2048; e += 128) lut[e] = lut_entry(e);
+  } else if (blockIdx.x == gridDim.x - 1) {
+    // max |W|: bounds the growth of the sampler's unnormalised state
+    float mx = 0.f;
+    for (int e = tid; e < im.N * im.H; e += 128) mx = fmaxf(mx, fabsf(W[e]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(CGSVMC_FULL_MASK, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+      img[im.off_a0 + 1] = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+      img[im.off_a0 + 2] = 0.f;
+      img[im.off_a0 + 3] = 0.f;
+    }
   } else {
     const int j = ((int)blockIdx.x - im.N) * 128 + tid;
     if (j < im.HP) {
@@ -45,27 +61,38 @@ prep_kernel(Image im, const float* __restrict__ a, const float* __restrict__ a0,
       img[im.off_base + j] = (j < im.H ? c[j] : 0.f) - cs;
     }
     if ((int)blockIdx.x == im.N) {
-      if (tid < 4) img[im.off_a0 + tid] = a0[0];
+      if (tid == 0) img[im.off_a0] = a0[0];
       for (int i = im.N + tid; i < im.NP; i += 128) { img[im.off_a2 + i] = 0.f; img[im.off_a + i] = 0.f; }
     }
   }
 }
 
 // out[f] += sum_c partials[c][f] in a fixed order: 32 outputs x 8 CTA slices
-// per block (the partials were just written and sit in L2).  Also folds the
-// per-CTA energy sums into stats.
+// per block (the partials were just written and sit in L2); every thread has
+// all of its loads in flight before the first add.  Also folds the per-CTA
+// energy sums into stats and, when asked, advances the device-side Philox
+// step counter of a captured batch step (the producer kernel has read it).
 __global__ void __launch_bounds__(256)
 reduce_kernel(const float* __restrict__ partials, int n_cta, int64_t stride, int64_t n_out,
               float* __restrict__ out, const double* __restrict__ stat_partials, int64_t B,
-              double* __restrict__ stats) {
+              double* __restrict__ stats, uint64_t* counter, uint64_t advance) {
   __shared__ float sm[8][32];
+  constexpr int U = 19;                       // 8 x 19 = 152 >= 148 CTAs in one sweep
   const int col = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int64_t f = (int64_t)blockIdx.x * 32 + col;
   float s = 0.f;
   if (f < n_out) {
     const float* src = partials + f;
-#pragma unroll 4
-    for (int c = slice; c < n_cta; c += 8) s += __ldcg(src + (size_t)c * stride);
+    for (int c0 = slice; c0 < n_cta; c0 += 8 * U) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int c = c0 + 8 * u;
+        v[u] = c < n_cta ? __ldcg(src + (size_t)c * stride) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) s += v[u];
+    }
   }
   sm[slice][col] = s;
   __syncthreads();
@@ -83,6 +110,7 @@ reduce_kernel(const float* __restrict__ partials, int n_cta, int64_t stride, int
       stats[2] += (double)B;
     }
   }
+  if (blockIdx.x == 0 && threadIdx.x == 32 && counter != nullptr) *counter += advance;
 }
 
 Image make_image(int N, int H, int HP) {
@@ -96,17 +124,20 @@ Image make_image(int N, int H, int HP) {
   im.off_base = im.off_a2 + im.NP;
   im.off_a = im.off_base + HP;
   im.off_a0 = im.off_a + im.NP;
-  im.total = im.off_a0 + 4;
+  im.off_lut = im.off_a0 + 4;          // 2048 bytes: select-in-byte table
+  im.total = im.off_lut + 512;
   return im;
 }
 
-size_t walker_smem_bytes(const Image& im, int slots, bool ws, bool do_eloc, int n_bonds, bool do_grad) {
+size_t walker_smem_bytes(const Image& im, int slots, bool ws, bool do_eloc, int n_bonds, bool do_grad,
+                         bool mc = false) {
   const int NP4 = round_up(im.N + 1, 4);
   size_t b = ws ? (size_t)im.total * 4 : 0;
   b += 16;
-  if (do_eloc) b += (size_t)n_bonds * 16 + (size_t)slots * round_up(n_bonds, 8) * 2;
+  if (do_eloc) b += (size_t)n_bonds * 16 + (size_t)slots * round_up(n_bonds, 8) * 4;
   if (do_grad) b += (size_t)slots * im.HP * 4 + (size_t)slots * 2 * NP4 * 4;
   b += (size_t)slots * 4;
+  if (mc && !ws) b += 2048;
   return b;
 }
 
@@ -155,7 +186,7 @@ int build_image(cgsvmc_ansatz* a, const Plan& pl, cudaStream_t st) {
   }
   if (a->track_params && a->tables_valid) return CGSVMC_OK;
   const float* p = a->params;
-  const int blocks = pl.im.N + (pl.im.HP + 127) / 128;
+  const int blocks = pl.im.N + (pl.im.HP + 127) / 128 + 2;
   prep_kernel<<<blocks, 128, 0, st>>>(pl.im, p + a->offsets[0], p + a->offsets[1], p + a->offsets[2],
                                       p + a->offsets[3], a->tables);
   a->tables_valid = true;
@@ -174,7 +205,7 @@ bool rbm2_supported(const cgsvmc_ansatz* a, const cgsvmc_ham* h) {
   const int nb = h != nullptr ? h->n_bonds : 0;
   if (nb >= 65535) return false;
   // the largest launch (accumulate) must fit with the image left in global memory
-  return walker_smem_bytes(pl.im, slots, false, h != nullptr, nb, true) <= (size_t)a->max_smem_optin;
+  return walker_smem_bytes(pl.im, slots, false, h != nullptr, nb, true, true) <= (size_t)a->max_smem_optin;
 }
 
 int rbm2_mc_steps(cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int n_steps, uint64_t seed,
@@ -183,8 +214,8 @@ int rbm2_mc_steps(cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int n_steps, ui
   Plan pl;
   if (!base_plan(a, B, &pl)) { set_error("rbm2: unsupported ansatz"); return CGSVMC_ERR_UNSUPPORTED; }
   const size_t img_bytes = (size_t)pl.im.total * 4;
-  pl.ws = img_bytes + 2048 + 16 <= (size_t)a->max_smem_optin;
-  pl.mc_smem = (pl.ws ? img_bytes : 0) + 2048 + 16;
+  pl.ws = img_bytes + 16 <= (size_t)a->max_smem_optin;
+  pl.mc_smem = (pl.ws ? img_bytes : 2048) + 16;
   pl.step0_dev = a->step_counter_dev;
   if (int rc = build_image(a, pl, st)) return rc;
   switch (pl.nw) {
@@ -196,14 +227,16 @@ int rbm2_mc_steps(cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int n_steps, ui
 
 int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, int64_t B,
                 float* e_loc, float* log_amp, float* diag, float* off, bool do_grad,
-                const float* weights, int K, float* out, double* stats, cudaStream_t st) {
+                const float* weights, int K, float* out, double* stats, cudaStream_t st,
+                const Rbm2Sweep* sweep) {
   Plan pl;
   if (!base_plan(a, B, &pl)) { set_error("rbm2: unsupported ansatz"); return CGSVMC_ERR_UNSUPPORTED; }
   const bool do_eloc = h != nullptr;
+  const bool mc = sweep != nullptr;
   const int slots = pl.slots;
   const int nb = do_eloc ? h->n_bonds : 0;
-  pl.ws = walker_smem_bytes(pl.im, slots, true, do_eloc, nb, do_grad) <= (size_t)a->max_smem_optin;
-  pl.walker_smem = walker_smem_bytes(pl.im, slots, pl.ws, do_eloc, nb, do_grad);
+  pl.ws = walker_smem_bytes(pl.im, slots, true, do_eloc, nb, do_grad, mc) <= (size_t)a->max_smem_optin;
+  pl.walker_smem = walker_smem_bytes(pl.im, slots, pl.ws, do_eloc, nb, do_grad, mc);
   if (pl.walker_smem > (size_t)a->max_smem_optin) {
     set_error("rbm2: problem does not fit in shared memory");
     return CGSVMC_ERR_UNSUPPORTED;
@@ -218,6 +251,11 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
   A.e_loc = e_loc; A.log_amp = log_amp; A.diag = diag; A.off = off;
   A.do_grad = do_grad ? 1 : 0;
   A.weights = weights; A.K = K; A.P = P;
+  if (mc) {
+    A.packed_rw = const_cast<uint64_t*>(packed);
+    A.n_steps = sweep->n_steps; A.seed = sweep->seed; A.walker0 = sweep->walker0;
+    A.step0 = sweep->step0; A.step0_dev = a->step_counter_dev; A.accept_count = sweep->accept_count;
+  }
   if (do_grad) {
     const size_t part_bytes = (size_t)pl.grid * 2 * P * sizeof(float);
     const size_t part_pad = (part_bytes + 15) / 16 * 16;
@@ -236,7 +274,9 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
   if (do_grad) {
     const int64_t n_out = (int64_t)K * P;
     const int blocks = (int)((n_out + 31) / 32);
-    reduce_kernel<<<blocks, 256, 0, st>>>(A.partials, pl.grid, 2 * P, n_out, out, A.stat_partials, B, stats);
+    uint64_t* counter = mc ? sweep->advance_counter : nullptr;
+    reduce_kernel<<<blocks, 256, 0, st>>>(A.partials, pl.grid, 2 * P, n_out, out, A.stat_partials, B, stats,
+                                          counter, mc ? (uint64_t)sweep->n_steps : 0ull);
     return cuda_fail(cudaGetLastError(), "rbm2 reduce launch");
   }
   return CGSVMC_OK;

@@ -7,11 +7,11 @@ namespace cgsvmc {
 namespace rbm2 {
 
 // Parameter image (float offsets), built by prep_kernel from the flat
-// parameter buffer: [2W | e^{4W} | e^{-4W} | A2 | base | a | a0].
+// parameter buffer: [2W | e^{4W} | e^{-4W} | A2 | base | a | a0, max|W| | select table].
 struct Image {
   int N, H, HP, NP;
   int words;   // 64-bit words per walker in the packed layout (stride)
-  int off_w2, off_f, off_g, off_a2, off_base, off_a, off_a0, total;
+  int off_w2, off_f, off_g, off_a2, off_base, off_a, off_a0, off_lut, total;
 };
 
 struct Plan {

@@ -34,6 +34,24 @@
 namespace cgsvmc {
 namespace rbm2 {
 
+// Development aid (-DCGSVMC_RBM2_TIMING, profiles/run_rbm2_phases.py): thread 0
+// of every CTA stamps %globaltimer / clock64 at the phase boundaries.
+#ifdef CGSVMC_RBM2_TIMING
+#define RBM2_TIMING_MARKS 12
+static __device__ unsigned long long g_phase_marks[2][160][RBM2_TIMING_MARKS][2];
+#define RBM2_MARK(KERN, K)                                                            \
+  do {                                                                                \
+    if (threadIdx.x == 0 && blockIdx.x < 160) {                                       \
+      unsigned long long gt_;                                                         \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                         \
+      g_phase_marks[KERN][blockIdx.x][K][0] = gt_;                                    \
+      g_phase_marks[KERN][blockIdx.x][K][1] = (unsigned long long)clock64();          \
+    }                                                                                 \
+  } while (0)
+#else
+#define RBM2_MARK(KERN, K) do {} while (0)
+#endif
+
 // ---------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------
@@ -55,6 +73,26 @@ __device__ __forceinline__ float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+}
+
+// Packed FP32 (sm_100 FMUL2 / FFMA2 / FADD2): two IEEE operations per issue
+// slot -- the ratio loops are issue-bound, not FMA-pipe bound
+// (profiles/microbench/fp32_pipes.cu).
+__device__ __forceinline__ void mul2(float& o0, float& o1, float a0, float a1, float b0, float b1) {
+  asm("{ .reg .b64 ra, rb; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};\n"
+      "  mul.rn.f32x2 ra, ra, rb; mov.b64 {%0, %1}, ra; }"
+      : "=f"(o0), "=f"(o1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fma2(float& o0, float& o1, float a0, float a1, float b0, float b1,
+                                     float c0, float c1) {
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7};\n"
+      "  fma.rn.f32x2 ra, ra, rb, rc; mov.b64 {%0, %1}, ra; }"
+      : "=f"(o0), "=f"(o1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void add2(float& o0, float& o1, float a0, float a1, float b0, float b1) {
+  asm("{ .reg .b64 ra, rb; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};\n"
+      "  add.rn.f32x2 ra, ra, rb; mov.b64 {%0, %1}, ra; }"
+      : "=f"(o0), "=f"(o1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
 // VW consecutive floats (VW = 4: LDS.128, 2: LDS.64)
@@ -120,14 +158,17 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 }
 
 // select-in-byte table: lut[v * 8 + r] = index of the r-th set bit of v
+__device__ __forceinline__ uint8_t lut_entry(int e) {
+  const int v = e >> 3, r = e & 7;
+  int pos = 0, seen = 0;
+  for (int b = 0; b < 8; ++b)
+    if ((v >> b) & 1) { if (seen == r) pos = b; ++seen; }
+  return (uint8_t)(r < seen ? pos : 0);
+}
+// The table travels inside the parameter image (prep_kernel) when the image
+// is copied to shared memory; otherwise the CTA builds its own copy.
 __device__ __forceinline__ void build_lut(uint8_t* lut) {
-  for (int e = threadIdx.x; e < 2048; e += blockDim.x) {
-    const int v = e >> 3, r = e & 7;
-    int pos = 0, seen = 0;
-    for (int b = 0; b < 8; ++b)
-      if ((v >> b) & 1) { if (seen == r) pos = b; ++seen; }
-    lut[e] = (uint8_t)(r < seen ? pos : 0);
-  }
+  for (int e = threadIdx.x; e < 2048; e += blockDim.x) lut[e] = lut_entry(e);
 }
 
 struct Tables {
@@ -137,7 +178,7 @@ struct Tables {
   const float* a2;    // [NP]     2 log2(e) (a_i - sum_j W_ij)
   const float* base;  // [HP]     c_j - sum_i W_ij
   const float* a;     // [NP]
-  const float* a0;    // [4]
+  const float* a0;    // [4]: a0, max |W|, 0, 0
 };
 
 __device__ __forceinline__ Tables tables_at(const float* img, const Image& im) {
@@ -176,30 +217,37 @@ __device__ __forceinline__ float init_state(const Tables& t, const Image& im, co
   }
 #pragma unroll
   for (int w = 0; w < NW; ++w) {
-    uint64_t bits = s[w];
-    while (bits) {
-      const int i = 64 * w + __ffsll((long long)bits) - 1;
-      bits &= bits - 1;
-      const float* row = t.w2 + i * HP + VW * sub;
 #pragma unroll
-      for (int q = 0; q < KJV; ++q) {
-        float v[VW];
-        ldv<VW, WS>(row + 32 * q, v);
+    for (int h = 0; h < 2; ++h) {
+      uint32_t bits = (uint32_t)(s[w] >> (32 * h));
+      const float* rows = t.w2 + (64 * w + 32 * h) * HP + VW * sub;
+      while (bits) {
+        const int i = __ffs((int)bits) - 1;
+        bits &= bits - 1;
+        const float* row = rows + i * HP;
 #pragma unroll
-        for (int c = 0; c < VW; ++c) th[VW * q + c] += v[c];
+        for (int q = 0; q < KJV; ++q) {
+          float v[VW];
+          ldv<VW, WS>(row + 32 * q, v);
+#pragma unroll
+          for (int c = 0; c < VW; c += 2)
+            add2(th[VW * q + c], th[VW * q + c + 1], th[VW * q + c], th[VW * q + c + 1], v[c], v[c + 1]);
+        }
       }
     }
   }
   float zpart = 0.f;
 #pragma unroll
   for (int k = 0; k < KJ; ++k) {
+    // e = exp(-2|theta|) in (0, 1]; the MUFU approximations are good to ~2^-22
+    // relative (ex2, rcp) / absolute (lg2 on [1, 2]) -- float32 rounding level
     const float ax = fabsf(th[k]);
-    const float e = expf(-2.f * ax);
-    const float r = 1.f / (1.f + e);
+    const float e = ex2_approx(-2.885390081777927f * ax);
+    const float r = rcp_approx(1.f + e);
     const float big = r, small = e * r;
     p[k] = th[k] >= 0.f ? big : small;
     m[k] = th[k] >= 0.f ? small : big;
-    if (want_z) zpart += ax + log1pf(e) - 0.6931471805599453f;
+    if (want_z) zpart += fmaf(lg2_approx(1.f + e), 0.6931471805599453f, ax - 0.6931471805599453f);
   }
   if (want_z) {
     for (int i = sub; i < im.N; i += LPW) {
@@ -210,13 +258,18 @@ __device__ __forceinline__ float init_state(const Tables& t, const Image& im, co
   return zpart;
 }
 
-// log2(psi'/psi) for "raise site d, lower site u" (uniform within the lane
-// group).  KEEP: also return tq[k] = F[d][j] G[u][j] for the acceptance update.
-template <int LPW, int KJV, bool WS, bool KEEP>
-__device__ __forceinline__ float exchange_log2_ratio(const Tables& t, int d, int u, int sub,
-                                                     const float (&p)[32 / LPW * KJV],
-                                                     const float (&m)[32 / LPW * KJV],
-                                                     float (&tq)[32 / LPW * KJV]) {
+// This lane's share of sum_j log2(p_j F[d][j] G[u][j] + m_j) for "raise site d,
+// lower site u" (uniform within the lane group).  KEEP: also return tq[k] =
+// F[d][j] G[u][j] for the acceptance update.  The fast form takes one lg2 per
+// FOUR hidden units, on the product of their terms; with very large weights
+// (or a far-from-normalised sampler state) that product can leave the float32
+// range, so callers re-evaluate with SAFE = true (one lg2 per term) whenever a
+// group total comes out non-finite.
+template <int LPW, int KJV, bool WS, bool KEEP, bool SAFE = false>
+__device__ __forceinline__ float exchange_log2_partial(const Tables& t, int d, int u, int sub,
+                                                       const float (&p)[32 / LPW * KJV],
+                                                       const float (&m)[32 / LPW * KJV],
+                                                       float (&tq)[32 / LPW * KJV]) {
   constexpr int VW = 32 / LPW, KJ = VW * KJV, HP = 32 * KJV;
   const float* fr = t.f + d * HP + VW * sub;
   const float* gr = t.g + u * HP + VW * sub;
@@ -227,23 +280,108 @@ __device__ __forceinline__ float exchange_log2_ratio(const Tables& t, int d, int
     ldv<VW, WS>(fr + 32 * q, f);
     ldv<VW, WS>(gr + 32 * q, g);
 #pragma unroll
-    for (int c = 0; c < VW; ++c) {
-      const float fg = f[c] * g[c];
-      if (KEEP) tq[VW * q + c] = fg;
-      n[VW * q + c] = fmaf(p[VW * q + c], fg, m[VW * q + c]);
+    for (int c = 0; c < VW; c += 2) {
+      const int k = VW * q + c;
+      float fg0, fg1;
+      mul2(fg0, fg1, f[c], f[c + 1], g[c], g[c + 1]);
+      if (KEEP) { tq[k] = fg0; tq[k + 1] = fg1; }
+      fma2(n[k], n[k + 1], p[k], p[k + 1], fg0, fg1, m[k], m[k + 1]);
     }
   }
-  // products of four terms, one lg2 each
   float lsum = 0.f;
+  if (SAFE) {
+#pragma unroll
+    for (int k = 0; k < KJ; ++k) lsum += lg2_approx(n[k]);
+    return lsum;
+  }
+  // products of four terms, one lg2 each
 #pragma unroll
   for (int k = 0; k < KJ; k += 4) {
-    float pr = n[k];
-#pragma unroll
-    for (int c = 1; c < 4; ++c) if (k + c < KJ) pr *= n[k + c];
+    float pr;
+    if (k + 3 < KJ) {
+      float q0, q1;
+      mul2(q0, q1, n[k], n[k + 1], n[k + 2], n[k + 3]);
+      pr = q0 * q1;
+    } else {
+      pr = n[k] * n[k + 1];
+    }
     lsum += lg2_approx(pr);
   }
-  lsum = group_sum<LPW>(lsum);
+  return lsum;
+}
+
+// log2(psi'/psi) of the exchange, reduced over the lane group.
+template <int LPW, int KJV, bool WS, bool KEEP>
+__device__ __forceinline__ float exchange_log2_ratio(const Tables& t, int d, int u, int sub,
+                                                     const float (&p)[32 / LPW * KJV],
+                                                     const float (&m)[32 / LPW * KJV],
+                                                     float (&tq)[32 / LPW * KJV]) {
+  const float lsum = group_sum<LPW>(exchange_log2_partial<LPW, KJV, WS, KEEP>(t, d, u, sub, p, m, tq));
   return lsum + (ld1<WS>(t.a2 + d) - ld1<WS>(t.a2 + u));
+}
+
+// Butterfly transpose-reduce over a lane group: on entry part[i] is this
+// lane's share of quantity i (i < LPW); on exit part[0] of lane `sub` is the
+// group total of quantity `sub`.  LPW - 1 shuffles for LPW sums (a plain
+// all-reduce of each would take LPW log2 LPW).
+template <int LPW>
+__device__ __forceinline__ void transpose_reduce(float (&part)[LPW], int sub) {
+#pragma unroll
+  for (int o = LPW / 2; o > 0; o >>= 1) {
+    const bool upper = (sub & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = upper ? part[i] : part[i + o];
+      const float keep = upper ? part[i + o] : part[i];
+      part[i] = keep + __shfl_xor_sync(CGSVMC_FULL_MASK, send, o);
+    }
+  }
+}
+
+// One round of the local-energy off-diagonal sum: R (= LPW or LPW / 2) listed
+// bonds of this walker starting at it0.  list entry = site to raise | site to
+// lower << 8 | bond index << 16; bond_s[k].z = j_x bits.  Returns this lane's
+// share of sum_k 0.5 j_x psi(flip_k) / psi (operators.py:168-169).
+template <int R, int LPW, int KJV, bool WS>
+__device__ __forceinline__ float ratio_round(const Tables& t, const uint32_t* list, const int4* bond_s,
+                                             int it0, int cnt, int sub,
+                                             const float (&p)[32 / LPW * KJV],
+                                             const float (&m)[32 / LPW * KJV]) {
+  float part[R], tdummy[32 / LPW * KJV];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const uint32_t ent = it0 + i < cnt ? list[it0 + i] : 0u;
+    part[i] = exchange_log2_partial<LPW, KJV, WS, false>(t, (int)(ent & 0xffu), (int)((ent >> 8) & 0xffu),
+                                                         sub, p, m, tdummy);
+  }
+  if (R < LPW) {   // half round: fold the two half groups first
+#pragma unroll
+    for (int i = 0; i < R; ++i) part[i] += __shfl_xor_sync(CGSVMC_FULL_MASK, part[i], R);
+  }
+  transpose_reduce<R>(part, sub & (R - 1));
+  const int it = it0 + (sub & (R - 1));
+  const bool mine = it < cnt && sub < R;
+  const uint32_t ent = mine ? list[it] : 0u;
+  const int dn = (int)(ent & 0xffu), up = (int)((ent >> 8) & 0xffu);
+  float total = part[0];
+  // rare: a four-term product left the float32 range -- redo this lane's bond term by term
+  const uint32_t bad = __ballot_sync(CGSVMC_FULL_MASK, mine && !(fabsf(total) <= 3.0e38f));
+  if (bad != 0u) {
+    constexpr uint32_t REP = LPW == 4 ? 0x11111111u : LPW == 8 ? 0x01010101u : LPW == 16 ? 0x00010001u : 1u;
+    for (int l = 0; l < LPW; ++l) {
+      if ((bad & (REP << l)) == 0u) continue;                       // warp-uniform
+      const uint32_t e2 = __shfl_sync(CGSVMC_FULL_MASK, ent, l, LPW);
+      const float v = group_sum<LPW>(exchange_log2_partial<LPW, KJV, WS, false, true>(
+          t, (int)(e2 & 0xffu), (int)((e2 >> 8) & 0xffu), sub, p, m, tdummy));
+      if (sub == l && ((bad >> (threadIdx.x & 31)) & 1u)) total = v;
+    }
+  }
+  float term = 0.f;
+  if (mine) {
+    const float l2 = total + (ld1<WS>(t.a2 + dn) - ld1<WS>(t.a2 + up));
+    term = 0.5f * __int_as_float(bond_s[ent >> 16].z) * ex2_approx(l2);
+  }
+  return term;
 }
 
 // ---------------------------------------------------------------------------
@@ -273,8 +411,17 @@ struct SitePicker {
   static constexpr int CB = 64 * NW / LPW;
   int word, shift, sub;
   uint32_t vchunk;
+  uint64_t vword;
+  static __device__ __forceinline__ int select_in_word(uint64_t w, int r, const uint8_t* lut) {
+    uint32_t c = (uint32_t)w;
+    int base = 0;
+    const int pl = __popc(c);
+    if (r >= pl) { r -= pl; c = (uint32_t)(w >> 32); base = 32; }
+    return base + select_in_chunk<32>(c, r, lut);
+  }
   __device__ __forceinline__ void setup(int n_sites, int sub_) {
     sub = sub_;
+    vword = valid_mask_word(n_sites, 0);
     word = (CB * sub) >> 6;
     shift = (CB * sub) & 63;
     const uint64_t vm = valid_mask_word(n_sites, word);
@@ -282,6 +429,16 @@ struct SitePicker {
   }
   __device__ __forceinline__ void pick(const uint64_t (&s)[NW], int k_up, int k_dn,
                                        const uint8_t* lut, int& up, int& dn) const {
+    if (NW == 1) {
+      // one word: popcount bisection + the select-in-byte table, no prefix scan
+      // (the lower half of the lane group resolves the up site, the upper
+      // half the down site: one select per lane, two broadcasts)
+      const bool lower = sub < LPW / 2;
+      const int r = select_in_word((lower ? s[0] : ~s[0]) & vword, lower ? k_up : k_dn, lut);
+      up = __shfl_sync(CGSVMC_FULL_MASK, r, 0, LPW);
+      dn = __shfl_sync(CGSVMC_FULL_MASK, r, LPW / 2, LPW);
+      return;
+    }
     uint64_t wv = s[0];
 #pragma unroll
     for (int i = 1; i < NW; ++i) if (word == i) wv = s[i];
@@ -319,6 +476,103 @@ struct Geometry {
   static constexpr int WARPS = THREADS / 32, SLOTS = WARPS * WPW;
 };
 
+// n_steps Metropolis exchange steps of one walker (graph_builders.py:54-89),
+// run by its lane group.  On entry (p, m) is the normalised state of `s`; on
+// exit `s` holds the new configuration and (p, m) an unnormalised state.
+// Returns the number of accepted moves.
+template <int NW, int LPW, int KJV, bool WS>
+__device__ __forceinline__ unsigned int mc_sweep(const Tables& t, const Image& im,
+                                                 const SitePicker<NW, LPW>& picker, const uint8_t* lut,
+                                                 uint64_t (&s)[NW], float (&p)[32 / LPW * KJV],
+                                                 float (&m)[32 / LPW * KJV], int sub, bool valid,
+                                                 int n_steps, uint64_t seed, uint64_t walker,
+                                                 uint64_t step0) {
+  constexpr int KJ = 32 / LPW * KJV;
+  float tq[KJ];
+  // an accepted move scales p_j by at most 2^(8 log2(e) max|W|); keep the
+  // growth between renormalisations below 2^30
+  // (2^30 per element: the ratio loop multiplies four terms before its lg2)
+  const float wbits = 11.541560327111707f * ld1<WS>(t.a0 + 1);
+  const int renorm_window = max(1, min(32, (int)((30.f - wbits) / (wbits + 1e-6f))));
+  unsigned int n_acc = 0;
+  int n_up = 0;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) n_up += __popcll(s[w]);
+  const int n_dn = im.N - n_up;
+  const bool can_move = valid && n_up > 0 && n_dn > 0;
+  // Between renormalisations the state is kept UNNORMALISED: an accepted
+  // move only scales p_j by F[d][j] G[u][j] (m_j is untouched), and
+  // lnorm = sum_j log2(p_j + m_j) -- which is exactly the log-sum of the move
+  // just accepted -- is subtracted from the next proposals' sums.  One FMUL
+  // per hidden unit per accepted move instead of {FMUL, FADD, RCP, 2 FMUL}.
+  float lnorm = 0.f;
+  int since_norm = 0;
+  // lane `sub` draws the Philox block of step (LPW q + sub); the block of the
+  // NEXT step is broadcast while the current ratio is in flight, so the
+  // shuffles stay off the accept -> propose dependency chain
+  Philox4 rnd = walker_step_random(seed, walker, step0 + (uint64_t)sub);
+  uint32_t r0 = __shfl_sync(CGSVMC_FULL_MASK, rnd.x, 0, LPW);
+  uint32_t r1 = __shfl_sync(CGSVMC_FULL_MASK, rnd.y, 0, LPW);
+  uint32_t r2 = __shfl_sync(CGSVMC_FULL_MASK, rnd.z, 0, LPW);
+  for (int step = 0; step < n_steps; ++step) {
+    // uniformly random up site and uniformly random down site
+    // (argmax / argmin of sigma * u, graph_builders.py:59-65)
+    const int k_up = (int)__umulhi(r0, (uint32_t)n_up);
+    const int k_dn = (int)__umulhi(r1, (uint32_t)n_dn);
+    const float u_acc = u32_to_unit(r2);
+    int up, dn;
+    picker.pick(s, k_up, k_dn, lut, up, dn);
+    if (!can_move) { up = 0; dn = 0; }
+    const float lpart = exchange_log2_partial<LPW, KJV, WS, true>(t, dn, up, sub, p, m, tq);
+    const float da2 = ld1<WS>(t.a2 + dn) - ld1<WS>(t.a2 + up);
+    {
+      const int nxt = step + 1;
+      if ((nxt & (LPW - 1)) == 0) rnd = walker_step_random(seed, walker, step0 + (uint64_t)(nxt + sub));
+      const int src = nxt & (LPW - 1);
+      r0 = __shfl_sync(CGSVMC_FULL_MASK, rnd.x, src, LPW);
+      r1 = __shfl_sync(CGSVMC_FULL_MASK, rnd.y, src, LPW);
+      r2 = __shfl_sync(CGSVMC_FULL_MASK, rnd.z, src, LPW);
+    }
+    float lfull = group_sum<LPW>(lpart);
+    // rare: a four-term product (or the unnormalised state) left the float32
+    // range -- rebuild the normalised state from the spins and evaluate this
+    // proposal term by term; warp-uniform
+    if (__any_sync(CGSVMC_FULL_MASK, !(fabsf(lfull) <= 3.0e38f))) {
+      init_state<NW, LPW, KJV, WS>(t, im, s, sub, p, m, false);
+      lnorm = 0.f;
+      since_norm = 0;
+      lfull = group_sum<LPW>(exchange_log2_partial<LPW, KJV, WS, true, true>(t, dn, up, sub, p, m, tq));
+    }
+    const float l2 = (lfull - lnorm) + da2;
+    // accept iff |psi'/psi| > sqrt(u)  <=>  (psi'/psi)^2 > u   (strict; NaN rejects)
+    const float prob = ex2_approx(2.f * l2);
+    if (can_move && prob > u_acc) {
+#pragma unroll
+      for (int k = 0; k < KJ; k += 2) mul2(p[k], p[k + 1], p[k], p[k + 1], tq[k], tq[k + 1]);
+      lnorm = lfull;
+      flip_bit<NW>(s, up);
+      flip_bit<NW>(s, dn);
+      ++n_acc;
+    }
+    // renormalise (p + m = 1, lnorm = 0) before the scale can overflow
+    // (every `renorm_window` steps, from max |W|) or cost precision in
+    // lfull - lnorm (|lnorm| large); warp-uniform
+    if (++since_norm >= renorm_window || __any_sync(CGSVMC_FULL_MASK, fabsf(lnorm) > 48.f)) {
+      since_norm = 0;
+      lnorm = 0.f;
+#pragma unroll
+      for (int k = 0; k < KJ; k += 2) {
+        float s0, s1;
+        add2(s0, s1, p[k], p[k + 1], m[k], m[k + 1]);
+        const float r0 = rcp_approx(s0), r1 = rcp_approx(s1);
+        mul2(p[k], p[k + 1], p[k], p[k + 1], r0, r1);
+        mul2(m[k], m[k + 1], m[k], m[k + 1], r0, r1);
+      }
+    }
+  }
+  return n_acc;
+}
+
 template <int NW, int LPW, int KJV, bool WS>
 __global__ void __launch_bounds__((Geometry<LPW, KJV>::THREADS), 1)
 mc_kernel(Image im, const float* __restrict__ img_g, uint64_t* __restrict__ packed, int64_t B,
@@ -326,19 +580,27 @@ mc_kernel(Image im, const float* __restrict__ img_g, uint64_t* __restrict__ pack
           const uint64_t* __restrict__ step0_dev, unsigned long long* accept_count,
           float* __restrict__ log_amp_out) {
   using Geo = Geometry<LPW, KJV>;
+  RBM2_MARK(0, 0);
   if (step0_dev != nullptr) step0 += *step0_dev;
   constexpr int WPW = Geo::WPW, KJ = Geo::KJ;
   extern __shared__ __align__(16) float smem[];
   float* img_s = smem;
-  uint8_t* lut = reinterpret_cast<uint8_t*>(smem + (WS ? im.total : 0));
-  uint64_t* bar = reinterpret_cast<uint64_t*>(lut + 2048);
-  if (WS) bulk_load(img_s, img_g, (uint32_t)im.total * 4u, bar);
-  build_lut(lut);
-  __syncthreads();
-  const Tables t = tables_at(WS ? img_s : img_g, im);
-
+  uint8_t* lut = reinterpret_cast<uint8_t*>(smem + (WS ? im.off_lut : 0));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (WS ? im.total : 512));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane & (LPW - 1), grp = lane / LPW;
+  // configurations of the first batch: requested before the table copy
+  uint64_t s_first[NW];
+  {
+    const int64_t b = min((int64_t)blockIdx.x * wpc + min(warp * WPW + grp, wpc - 1), B - 1);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s_first[w] = w < im.words ? packed[b * im.words + w] : 0ull;
+  }
+  if (WS) bulk_load(img_s, img_g, (uint32_t)im.total * 4u, bar);
+  else build_lut(lut);
+  __syncthreads();
+  RBM2_MARK(0, 1);
+  const Tables t = tables_at(WS ? img_s : img_g, im);
   SitePicker<NW, LPW> picker;
   picker.setup(im.N, sub);
   unsigned int n_acc = 0;
@@ -349,46 +611,19 @@ mc_kernel(Image im, const float* __restrict__ img_g, uint64_t* __restrict__ pack
     const bool valid = slot < wpc && b < B;
     const int64_t bb = valid ? b : B - 1;
     uint64_t s[NW];
+    if (batch == blockIdx.x && valid) {
 #pragma unroll
-    for (int w = 0; w < NW; ++w) s[w] = w < im.words ? packed[bb * im.words + w] : 0ull;
-    float p[KJ], m[KJ], tq[KJ];
-    init_state<NW, LPW, KJV, WS>(t, im, s, sub, p, m, false);
-    int n_up = 0;
+      for (int w = 0; w < NW; ++w) s[w] = s_first[w];
+    } else {
 #pragma unroll
-    for (int w = 0; w < NW; ++w) n_up += __popcll(s[w]);
-    const int n_dn = im.N - n_up;
-    const bool can_move = valid && n_up > 0 && n_dn > 0;
-    Philox4 rnd = {0, 0, 0, 0};
-    for (int step = 0; step < n_steps; ++step) {
-      if ((step & (LPW - 1)) == 0)   // lane `sub` draws the block of step + sub
-        rnd = walker_step_random(seed, walker0 + (uint64_t)bb, step0 + (uint64_t)(step + sub));
-      const int src = step & (LPW - 1);
-      const uint32_t r0 = __shfl_sync(CGSVMC_FULL_MASK, rnd.x, src, LPW);
-      const uint32_t r1 = __shfl_sync(CGSVMC_FULL_MASK, rnd.y, src, LPW);
-      const uint32_t r2 = __shfl_sync(CGSVMC_FULL_MASK, rnd.z, src, LPW);
-      // uniformly random up site and uniformly random down site
-      // (argmax / argmin of sigma * u, graph_builders.py:59-65)
-      const int k_up = (int)__umulhi(r0, (uint32_t)n_up);
-      const int k_dn = (int)__umulhi(r1, (uint32_t)n_dn);
-      int up, dn;
-      picker.pick(s, k_up, k_dn, lut, up, dn);
-      if (!can_move) { up = 0; dn = 0; }
-      const float l2 = exchange_log2_ratio<LPW, KJV, WS, true>(t, dn, up, sub, p, m, tq);
-      // accept iff |psi'/psi| > sqrt(u)  <=>  (psi'/psi)^2 > u   (strict; NaN rejects)
-      const float prob = ex2_approx(2.f * l2);
-      if (can_move && prob > u32_to_unit(r2)) {
-#pragma unroll
-        for (int k = 0; k < KJ; ++k) {
-          const float y = p[k] * tq[k];
-          const float r = rcp_approx(y + m[k]);
-          p[k] = y * r;
-          m[k] = m[k] * r;
-        }
-        flip_bit<NW>(s, up);
-        flip_bit<NW>(s, dn);
-        ++n_acc;
-      }
+      for (int w = 0; w < NW; ++w) s[w] = w < im.words ? packed[bb * im.words + w] : 0ull;
     }
+    float p[KJ], m[KJ];
+    init_state<NW, LPW, KJV, WS>(t, im, s, sub, p, m, false);
+    RBM2_MARK(0, 2);
+    n_acc += mc_sweep<NW, LPW, KJV, WS>(t, im, picker, lut, s, p, m, sub, valid, n_steps, seed,
+                                        walker0 + (uint64_t)bb, step0);
+    RBM2_MARK(0, 3);
     if (valid && sub == 0) {
 #pragma unroll
       for (int w = 0; w < NW; ++w) if (w < im.words) packed[b * im.words + w] = s[w];
@@ -405,6 +640,7 @@ mc_kernel(Image im, const float* __restrict__ img_g, uint64_t* __restrict__ pack
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(CGSVMC_FULL_MASK, mine, o);
     if (lane == 0 && mine) atomicAdd(accept_count, (unsigned long long)mine);
   }
+  RBM2_MARK(0, 4);
 }
 
 // ---------------------------------------------------------------------------
@@ -430,9 +666,21 @@ struct WalkerArgs {
   float* partials;        // [grid][2][P]
   double* stat_partials;  // [grid][2] or NULL
   int64_t P;
+  // fused Metropolis sweep after the estimators (MC kernels only): one batch
+  // iteration of run_optimization_epoch (training.py:614-617) in one launch
+  uint64_t* packed_rw;
+  int n_steps;
+  uint64_t seed, walker0, step0;
+  const uint64_t* step0_dev;
+  unsigned long long* accept_count;
 };
 
-template <int NW, int LPW, int KJV, bool WS>
+// MC: after the estimators of a walker are done (and its gradient inputs are
+// staged in shared memory) its lane group continues with n_steps Metropolis
+// steps from the state (p, m) it already holds, and writes the configuration
+// back; the CTA-wide gradient tiles follow.  Saves a launch, a second table
+// load and a second state build per batch iteration.
+template <int NW, int LPW, int KJV, bool WS, bool MC>
 __global__ void __launch_bounds__((Geometry<LPW, KJV>::THREADS), 1)
 walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
   using Geo = Geometry<LPW, KJV>;
@@ -445,13 +693,30 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(cur); cur += 16;
   int4* bond_s = reinterpret_cast<int4*>(cur); cur += (size_t)(A.do_eloc ? A.n_bonds : 0) * 16;
   const int list_ld = (A.n_bonds + 7) / 8 * 8;
-  uint16_t* list_s = reinterpret_cast<uint16_t*>(cur); cur += (size_t)(A.do_eloc ? SLOTS * list_ld : 0) * 2;
+  uint32_t* list_s = reinterpret_cast<uint32_t*>(cur); cur += (size_t)(A.do_eloc ? SLOTS * list_ld : 0) * 4;
   const int NP4 = (im.N + 1 + 3) / 4 * 4;
   float* T_s = reinterpret_cast<float*>(cur); cur += (size_t)(A.do_grad ? SLOTS * HP : 0) * 4;
   float* ws_s = reinterpret_cast<float*>(cur); cur += (size_t)(A.do_grad ? SLOTS * 2 * NP4 : 0) * 4;
-  float* e_s = reinterpret_cast<float*>(cur);
+  float* e_s = reinterpret_cast<float*>(cur); cur += (size_t)SLOTS * 4;
+  // select table: inside the image when it is in shared memory, else 2048 bytes here (MC only)
+  uint8_t* lut = WS ? reinterpret_cast<uint8_t*>(img_s + im.off_lut) : reinterpret_cast<uint8_t*>(cur);
 
+  RBM2_MARK(1, 0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & (LPW - 1), grp = lane / LPW;
+  const int slot = warp * WPW + grp;
+  // configurations of the first batch: requested before the table copy so that
+  // the global-memory latency overlaps it (grid <= n_batches, so b0 < B)
+  uint64_t s_first[NW];
+  {
+    const int64_t b0 = (int64_t)blockIdx.x * A.wpc;
+    const int n_valid = (int)min((int64_t)A.wpc, A.B - b0);
+    const int64_t bb = b0 + min(slot, n_valid - 1);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s_first[w] = w < im.words ? A.packed[bb * im.words + w] : 0ull;
+  }
   if (WS) bulk_load(img_s, img_g, (uint32_t)im.total * 4u, bar);
+  else if (MC) build_lut(lut);
   if (A.do_eloc) {
     for (int k = threadIdx.x; k < A.n_bonds; k += THREADS) {
       const int2 ij = A.bonds_ij[k];
@@ -459,19 +724,24 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
     }
   }
   __syncthreads();
+  RBM2_MARK(1, 1);
   const Tables t = tables_at(WS ? img_s : img_g, im);
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane & (LPW - 1), grp = lane / LPW;
-  const int slot = warp * WPW + grp;
+  SitePicker<NW, LPW> picker;
+  if (MC) picker.setup(im.N, sub);
+  unsigned int n_acc = 0;
+  const uint64_t mc_step0 = MC ? A.step0 + (A.step0_dev != nullptr ? *A.step0_dev : 0ull) : 0ull;
 
   // gradient tiles: 4 rows (sites, row N = the "ones" row of c) x 4 hidden units
   constexpr int CT = HP / 4;
   const int RT = NP4 / 4;
   const int n_tiles = RT * CT;
   const int n_pass = (n_tiles + THREADS - 1) / THREADS;
-  float acc_a[2] = {0.f, 0.f};   // entries threadIdx.x (+ THREADS) of the [2][NP4] a-gradient
-  double sum_e = 0.0, sum_e2 = 0.0;   // thread 0 only
+  // The a-gradient (entries rev (+ THREADS) of [2][NP4]) and the energy
+  // statistics are taken from the END of the CTA: with fewer tiles than
+  // threads those warps have no tile work.
+  const int rev = THREADS - 1 - (int)threadIdx.x;
+  float acc_a[2] = {0.f, 0.f};
+  double sum_e = 0.0, sum_e2 = 0.0;   // lane 0 of the last warp only
   float* part = A.partials + (size_t)blockIdx.x * 2 * A.P;
   int batch_no = 0;
 
@@ -485,31 +755,38 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
       const int64_t bb = valid ? b : b0 + n_valid - 1;
       uint64_t s[NW];
 #pragma unroll
-      for (int w = 0; w < NW; ++w) s[w] = w < im.words ? A.packed[bb * im.words + w] : 0ull;
-      float p[KJ], m[KJ], tdummy[KJ];
+      for (int w = 0; w < NW; ++w)
+        s[w] = batch_no == 0 ? s_first[w] : (w < im.words ? A.packed[bb * im.words + w] : 0ull);
+      float p[KJ], m[KJ];
       const bool want_z = A.log_amp != nullptr;
       float z = init_state<NW, LPW, KJV, WS>(t, im, s, sub, p, m, want_z);
       if (want_z) {
         z = group_sum<LPW>(z) + ld1<WS>(t.a0);
         if (valid && sub == 0) A.log_amp[b] = z;
       }
+      RBM2_MARK(1, 2);
       float e_val = 0.f;
       if (A.do_eloc) {
         // ---- enumerate antiparallel bonds (operators.py:154-167) ----
-        uint16_t* list = list_s + slot * list_ld;
+        // list entry = site to raise | site to lower << 8 | bond index << 16
+        uint32_t* list = list_s + slot * list_ld;
         float diag = 0.f;
         int cnt = 0;
         for (int k0 = 0; k0 < A.n_bonds; k0 += LPW) {
           const int k = k0 + sub;
           bool anti = false;
+          uint32_t ent = 0;
           if (k < A.n_bonds) {
             const int4 bd = bond_s[k];
-            anti = spin_bit<NW>(s, bd.x) != spin_bit<NW>(s, bd.y);
+            const int bi = spin_bit<NW>(s, bd.x);
+            anti = bi != spin_bit<NW>(s, bd.y);
             diag += (anti ? -0.25f : 0.25f) * __int_as_float(bd.w);   // operators.py:165,169
+            const int up = bi ? bd.x : bd.y, dn = bi ? bd.y : bd.x;
+            ent = (uint32_t)dn | ((uint32_t)up << 8) | ((uint32_t)k << 16);
           }
           const uint32_t vote = __ballot_sync(CGSVMC_FULL_MASK, anti);
           const uint32_t gbits = (vote >> (grp * LPW)) & ((1u << LPW) - 1u);
-          if (anti) list[cnt + __popc(gbits & ((1u << sub) - 1u))] = (uint16_t)k;
+          if (anti) list[cnt + __popc(gbits & ((1u << sub) - 1u))] = ent;
           cnt += __popc(gbits);
         }
         diag = group_sum<LPW>(diag);
@@ -518,17 +795,22 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
 #pragma unroll
         for (int o = LPW; o < 32; o <<= 1) n_max = max(n_max, __shfl_xor_sync(CGSVMC_FULL_MASK, n_max, o));
         // ---- off-diagonal terms: jx/2 psi(flip)/psi on active bonds only ----
-        float off = 0.f;
-        for (int it = 0; it < n_max; ++it) {
-          const bool act = it < cnt;
-          const int k = act ? (int)list[it] : 0;
-          const int4 bd = bond_s[k];
-          const int bi = spin_bit<NW>(s, bd.x);
-          const int up = bi ? bd.x : bd.y, dn = bi ? bd.y : bd.x;
-          const float l2 = exchange_log2_ratio<LPW, KJV, WS, false>(t, dn, up, sub, p, m, tdummy);
-          if (act) off = fmaf(0.5f * __int_as_float(bd.z), ex2_approx(l2), off);   // operators.py:168-169
-        }
+        // LPW bonds per round: the lanes' partial sums of the LPW log-ratios are
+        // transpose-reduced so that lane `sub` ends up with the total of bond
+        // it0 + sub and finishes it (a2 terms, ex2, coupling) alone; the LPW
+        // ratio evaluations of a round are independent instruction streams.
+        // Rounds are branch-free (list slots past cnt evaluate the dummy move
+        // 0 -> 0) so that the compiler interleaves the evaluations; a remainder
+        // of at most LPW / 2 bonds takes a half round.
+        float off_lane = 0.f;
+        int it0 = 0;
+        for (; n_max - it0 > LPW / 2; it0 += LPW)
+          off_lane += ratio_round<LPW, LPW, KJV, WS>(t, list, bond_s, it0, cnt, sub, p, m);
+        if (it0 < n_max)
+          off_lane += ratio_round<LPW / 2, LPW, KJV, WS>(t, list, bond_s, it0, cnt, sub, p, m);
+        const float off = group_sum<LPW>(off_lane);
         e_val = diag + off;
+        RBM2_MARK(1, 3);
         if (valid && sub == 0) {
           if (A.e_loc) A.e_loc[b] = e_val;
           if (A.diag) A.diag[b] = diag;
@@ -562,9 +844,20 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
         }
         if (sub == 0) e_s[slot] = e_val;
       }
+      RBM2_MARK(1, 4);
+      if (MC) {
+        n_acc += mc_sweep<NW, LPW, KJV, WS>(t, im, picker, lut, s, p, m, sub, valid, A.n_steps, A.seed,
+                                            A.walker0 + (uint64_t)bb, mc_step0);
+        if (valid && sub == 0) {
+#pragma unroll
+          for (int w = 0; w < NW; ++w) if (w < im.words) A.packed_rw[b * im.words + w] = s[w];
+        }
+      }
+      RBM2_MARK(1, 5);
     }
     if (A.do_grad) {
       __syncthreads();
+      RBM2_MARK(1, 6);
       for (int pass = 0; pass < n_pass; ++pass) {
         const int tile = threadIdx.x + pass * THREADS;
         if (tile < n_tiles) {
@@ -578,6 +871,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
             for (int r = 0; r < 4; ++r)
 #pragma unroll
               for (int c = 0; c < 4; ++c) acc[k][r][c] = 0.f;
+#pragma unroll 4
           for (int sb = 0; sb < n_valid; ++sb) {
             const float4 T = *reinterpret_cast<const float4*>(T_s + sb * HP + 4 * ct);
             const float4 s0 = *reinterpret_cast<const float4*>(ws_s + (size_t)sb * 2 * NP4 + 4 * rt);
@@ -612,34 +906,47 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
       }
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
-        const int e = threadIdx.x + h2 * THREADS;
-        if (e < 2 * NP4)
+        const int e = rev + h2 * THREADS;
+        if (e < 2 * NP4) {
+#pragma unroll 4
           for (int sb = 0; sb < n_valid; ++sb) acc_a[h2] += ws_s[(size_t)sb * 2 * NP4 + e];
-      }
-      if (threadIdx.x == 0 && A.stat_partials != nullptr) {
-        for (int sb = 0; sb < n_valid; ++sb) {
-          const double e = (double)e_s[sb];
-          sum_e += e;
-          sum_e2 += e * e;
         }
       }
+      if (warp == THREADS / 32 - 1 && A.stat_partials != nullptr) {
+        double e1 = 0.0, e2 = 0.0;
+        for (int sb = lane; sb < n_valid; sb += 32) {
+          const double e = (double)e_s[sb];
+          e1 += e;
+          e2 += e * e;
+        }
+        sum_e += warp_sum(e1);
+        sum_e2 += warp_sum(e2);
+      }
+      RBM2_MARK(1, 7);
       __syncthreads();
     }
+  }
+  if (MC && A.accept_count != nullptr) {
+    unsigned int mine = sub == 0 ? n_acc : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(CGSVMC_FULL_MASK, mine, o);
+    if (lane == 0 && mine) atomicAdd(A.accept_count, (unsigned long long)mine);
   }
   if (A.do_grad) {
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2) {
-      const int e = threadIdx.x + h2 * THREADS;
+      const int e = rev + h2 * THREADS;
       if (e < 2 * NP4) {
         const int k = e / NP4, i = e - k * NP4;
         if (i <= im.N) part[(size_t)k * A.P + i] = acc_a[h2];   // a_i (i < N) and a0 (i == N)
       }
     }
-    if (threadIdx.x == 0 && A.stat_partials != nullptr) {
+    if (threadIdx.x == THREADS - 32 && A.stat_partials != nullptr) {
       A.stat_partials[2 * blockIdx.x] = sum_e;
       A.stat_partials[2 * blockIdx.x + 1] = sum_e2;
     }
   }
+  RBM2_MARK(1, 8);
 }
 
 // ---------------------------------------------------------------------------
@@ -676,15 +983,16 @@ int launch_mc_variant(const Plan& pl, const float* img, uint64_t* packed, int64_
 template <int NW, int LPW, int KJV>
 int launch_walker_variant(const Plan& pl, const float* img, const WalkerArgs& A, cudaStream_t st) {
   constexpr int THREADS = Geometry<LPW, KJV>::THREADS;
-  if (pl.ws) {
-    auto kern = walker_kernel<NW, LPW, KJV, true>;
-    if (int rc = opt_in_smem(kern, pl.walker_smem)) return rc;
-    kern<<<pl.grid, THREADS, pl.walker_smem, st>>>(pl.im, img, A);
-  } else {
-    auto kern = walker_kernel<NW, LPW, KJV, false>;
-    if (int rc = opt_in_smem(kern, pl.walker_smem)) return rc;
-    kern<<<pl.grid, THREADS, pl.walker_smem, st>>>(pl.im, img, A);
-  }
+  const bool mc = A.packed_rw != nullptr;
+#define RBM2_LAUNCH_WALKER(WSV, MCV)                                              \
+  do {                                                                            \
+    auto kern = walker_kernel<NW, LPW, KJV, WSV, MCV>;                            \
+    if (int rc = opt_in_smem(kern, pl.walker_smem)) return rc;                    \
+    kern<<<pl.grid, THREADS, pl.walker_smem, st>>>(pl.im, img, A);                \
+  } while (0)
+  if (pl.ws) { if (mc) RBM2_LAUNCH_WALKER(true, true); else RBM2_LAUNCH_WALKER(true, false); }
+  else { if (mc) RBM2_LAUNCH_WALKER(false, true); else RBM2_LAUNCH_WALKER(false, false); }
+#undef RBM2_LAUNCH_WALKER
   return cuda_fail(cudaGetLastError(), "rbm2 walker launch");
 }
 

@@ -20,3 +20,15 @@ int launch_walker_nw1(const Plan& pl, const float* img, const WalkerArgs& A, cud
 
 }  // namespace rbm2
 }  // namespace cgsvmc
+
+#ifdef CGSVMC_RBM2_TIMING
+// Development build only: copies the phase marks of the NW = 1 kernels
+// ([kernel 0 = mc, 1 = walker][cta][mark][globaltimer ns, clock64]) to the host.
+extern "C" int cgsvmc_debug_rbm2_marks(unsigned long long* host_out) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess)
+    e = cudaMemcpyFromSymbol(host_out, cgsvmc::rbm2::g_phase_marks, sizeof(cgsvmc::rbm2::g_phase_marks));
+  return e == cudaSuccess ? 0 : -2;
+}
+#endif
+

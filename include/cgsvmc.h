@@ -228,6 +228,24 @@ int cgsvmc_accumulate(const cgsvmc_ansatz* ansatz, const cgsvmc_ham* ham,
                       const uint64_t* packed, int64_t n_walkers, float* e_loc_out,
                       float* log_amp_out, float* sums, double* stats, void* stream);
 
+/* One batch iteration of EnergyGradientOptimizer.run_optimization_epoch
+ * (training.py:614-617): session.run(accumulate_gradients) on the current
+ * configurations, then num_monte_carlo_sweeps * num_sites x session.run(mc_step)
+ * -- cgsvmc_accumulate followed by cgsvmc_mc_steps (same arguments, same
+ * results).  For the pure RBM both run in ONE kernel: the walker state built
+ * for the local energy is reused by the sampler and the ratio tables are
+ * loaded into shared memory once.  step_counter, when non-NULL, is a device
+ * uint64 holding the Philox step offset (step0 is then ignored); it is
+ * advanced by n_steps on the stream, which makes the call CUDA-graph safe
+ * (cf. cgsvmc_mc_steps_graph). */
+int cgsvmc_batch_step(const cgsvmc_ansatz* ansatz, const cgsvmc_ham* ham,
+                      uint64_t* packed_inout, int64_t n_walkers,
+                      float* e_loc_out, float* log_amp_out, float* sums,
+                      double* stats, int32_t n_steps, uint64_t seed,
+                      uint64_t walker_id0, uint64_t step0,
+                      uint64_t* step_counter, unsigned long long* accept_count,
+                      void* stream);
+
 /* Replaces tf.metrics.mean(local_energy) bookkeeping (training.py:555):
  * stats (double [4], device) += { sum e, sum e^2, B, 0 }. */
 int cgsvmc_energy_stats(const float* e_loc, int64_t n_walkers, double* stats,

@@ -290,3 +290,26 @@ def test_energy_gradient_and_swo_golden(native, name):
   grad = a.weighted_grad_sum(packed, w)[0].cpu().numpy()
   ref = g['swo_gradient']
   assert np.linalg.norm(grad - ref) <= 1e-3 * np.linalg.norm(ref) + 1e-6
+
+
+def test_batch_step_generic_ansatz(native):
+  """cgsvmc_batch_step on an ansatz without a fused kernel (fully_connected)
+  is cgsvmc_accumulate followed by cgsvmc_mc_steps."""
+  from cgs_vmc_b200 import engine
+  from gpu_util import make_native
+  spec = oansatz.AnsatzSpec('fully_connected', 12, num_layers=2, layer_size=16)
+  a = make_native(spec, oansatz.flatten(oansatz.init_params(spec, seed=3, bias_scale=0.1)).numpy())
+  ij, jx, jz = lattices.heisenberg_couplings(lattices.chain_bonds(12))
+  ham = native.Hamiltonian(ij, jx, jz, 12)
+  s1 = engine.WalkerState(200, 12, seed=4)
+  s2 = engine.WalkerState(200, 12, seed=4)
+  sums1 = engine.EnergyGradientSums(a, 200)
+  sums2 = engine.EnergyGradientSums(a, 200)
+  for _ in range(2):
+    sums1.batch_step(ham, s1, 12)
+    sums2.accumulate(ham, s2.packed)
+    s2.mc_steps(a, 12)
+  assert torch.equal(s1.packed, s2.packed)
+  assert torch.equal(sums1.sums, sums2.sums) and torch.equal(sums1.stats, sums2.stats)
+  assert torch.equal(s1.accept_count, s2.accept_count)
+

@@ -538,6 +538,108 @@ def test_graphed_batch_step_equals_separate_launches(native):
   assert s1.step == s2.step and int(s1.step_dev.item()) == s1.step
 
 
+@pytest.mark.parametrize('n_side,hidden,batch,j1j2', [(6, 144, 777, False), (4, 24, 130, True),
+                                                      (16, 256, 300, False), (10, 64, 257, True)])
+def test_batch_step_equals_accumulate_then_sweep(native, n_side, hidden, batch, j1j2):
+  """cgsvmc_batch_step (estimators + sweep fused in one kernel for the pure
+  RBM) against cgsvmc_accumulate followed by cgsvmc_mc_steps: identical
+  configurations, acceptance counts, local energies and sums."""
+  from cgs_vmc_b200 import engine
+  n = n_side * n_side
+  spec = oansatz.AnsatzSpec('rbm', n, num_layers=0, layer_size=hidden, size_x=n_side, size_y=n_side)
+  a, _, _ = _setup(spec, seed=11, batch=1)
+  if j1j2:
+    ij, jx, jz = lattices.j1j2_couplings(n_side, 0.5)
+  else:
+    ij, jx, jz = lattices.heisenberg_couplings(lattices.square_nn_bonds(n_side))
+  ham = native.Hamiltonian(ij, jx, jz, n)
+  s1 = engine.WalkerState(batch, n, seed=9, walker_id0=3)
+  s2 = engine.WalkerState(batch, n, seed=9, walker_id0=3)
+  sums1 = engine.EnergyGradientSums(a, batch, want_log_amp=True)
+  sums2 = engine.EnergyGradientSums(a, batch, want_log_amp=True)
+  for n_steps in (n, 5, 0):
+    e1 = sums1.batch_step(ham, s1, n_steps).clone()
+    e2 = sums2.accumulate(ham, s2.packed).clone()
+    s2.mc_steps(a, n_steps)
+    assert torch.equal(s1.packed, s2.packed)
+    assert torch.equal(e1, e2)
+  assert torch.equal(s1.accept_count, s2.accept_count) and s1.step == s2.step
+  np.testing.assert_allclose(sums1.sums.cpu().numpy(), sums2.sums.cpu().numpy(), rtol=1e-6, atol=1e-6)
+  assert torch.equal(sums1.stats, sums2.stats)
+  assert torch.equal(sums1.log_amp, sums2.log_amp)
+
+
+def test_host_fed_batch_step(native):
+  """engine.HostFedBatchStep (pinned host configurations in, estimator sums
+  out, one graph per buffer slot) gives the sums of accumulate() on the same
+  configurations, batch after batch, including after a parameter update."""
+  from cgs_vmc_b200 import engine
+  spec = _c2_spec()
+  a, _, _ = _setup(spec, seed=3, batch=1)
+  ij, jx, jz = lattices.heisenberg_couplings(lattices.square_nn_bonds(6))
+  ham = native.Hamiltonian(ij, jx, jz, 36)
+  B = 600
+  s1 = engine.WalkerState(B, 36, seed=5)
+  sums1 = engine.EnergyGradientSums(a, B)
+  fed = engine.HostFedBatchStep(s1, a, ham, sums1, 36)
+  ref_sums = engine.EnergyGradientSums(a, B)
+  gen = np.random.default_rng(0)
+  for k in range(5):
+    if k == 3:
+      a.params.mul_(0.95)
+    cfg = bits.random_sz0_configs(36, B, gen).astype(np.float32)
+    host = torch.from_numpy(cfg).pin_memory()
+    fed.submit(host)
+    got_sums, got_stats = fed.result()
+    ref_sums.accumulate(ham, native.pack_configs(torch.from_numpy(cfg).cuda()))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(got_sums.numpy(), ref_sums.sums.cpu().numpy(), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(got_stats.numpy(), ref_sums.stats.cpu().numpy(), rtol=1e-12)
+  assert fed.outstanding() == 0 and s1.step == 5 * 36
+  assert int(s1.step_dev.item()) == s1.step
+
+
+@pytest.mark.parametrize('scale', [6.0, 20.0])
+def test_large_weights_take_the_safe_path(native, scale):
+  """Weights far beyond the initialisation scale (|W| up to ~2 / ~7): the
+  four-term products of the fast ratio loop and the unnormalised sampler
+  state overflow float32, and the kernels must fall back to term-by-term
+  evaluation.  Local energies stay finite and match the float64 oracle where
+  it is finite itself; the sampler keeps Sz and matches replayed oracle ratios."""
+  from gpu_util import packed_cuda, unpack_np
+  spec = _c2_spec()
+  a, params, cfg = _setup(spec, seed=17, batch=96, scale=scale)
+  ij, jx, jz = lattices.heisenberg_couplings(lattices.square_nn_bonds(6))
+  ham = native.Hamiltonian(ij, jx, jz, 36)
+  packed = packed_cuda(cfg)
+  e, z = a.local_energy(ham, packed)
+  fn = lambda c: oansatz.log_amp(spec, params, c)
+  cfg64 = torch.from_numpy(cfg).to(F64)
+  eo = hamiltonian.local_energy(cfg64, ij, jx, jz, fn).numpy()
+  eabs = hamiltonian.local_energy(cfg64, ij, np.abs(jx), np.abs(jz), fn).numpy()
+  ok = np.isfinite(eo) & (np.abs(eabs) < 1e30)
+  assert ok.sum() > 0
+  got = e.cpu().numpy()
+  assert np.all(np.isfinite(got[ok]))
+  assert np.all(np.abs(got[ok] - eo[ok]) <= 1e-4 * (np.abs(eabs[ok]) + 20.0)), np.abs(got[ok] - eo[ok]).max()
+  # sampler: run, then check conservation and that it moved at all
+  before = packed.clone()
+  acc = torch.zeros(1, dtype=torch.int64, device='cuda')
+  a.mc_steps(packed, 200, seed=3, accept_count=acc)
+  after = unpack_np(packed, 36)
+  assert np.all(after.sum(axis=1) == 0)
+  assert int(acc.item()) > 0 and not torch.equal(before, packed)
+  # fused path agrees with the split one under the same conditions
+  from cgs_vmc_b200 import engine
+  s1 = engine.WalkerState(96, 36, seed=5, packed=before.clone())
+  s2 = engine.WalkerState(96, 36, seed=5, packed=before.clone())
+  sums1, sums2 = engine.EnergyGradientSums(a, 96), engine.EnergyGradientSums(a, 96)
+  e1 = sums1.batch_step(ham, s1, 36).clone()
+  e2 = sums2.accumulate(ham, s2.packed).clone()
+  s2.mc_steps(a, 36)
+  assert torch.equal(s1.packed, s2.packed) and torch.equal(e1, e2)
+
+
 def test_energy_stats(native):
   e = torch.randn(100003, device='cuda')
   stats = native.energy_stats(e)
