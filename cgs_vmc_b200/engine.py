@@ -156,17 +156,22 @@ class GraphedBatchStep:
     # capture does not execute: nothing to undo, but the tables the handle now
     # believes valid were never built -- force the rebuilding graph first
     self._params_version = None
+    self._expected_step = state.step
 
   def _body(self):
     self.sums.batch_step(self.ham, self.state, self.n_steps, on_device_counter=True)
 
   def replay(self):
+    if self.state.step != self._expected_step:
+      # steps were taken outside the graph (equilibration): resync the device counter
+      self.state.step_dev.fill_(self.state.step)
     version = self.ansatz.params._version
     if version != self._params_version:
       self.graph_rebuild.replay()
       self._params_version = version
     else:
       self.graph.replay()
+    self._expected_step = self.state.step + self.n_steps
     self.sums.n_batches += 1
     self.state.step += self.n_steps
     self.state.proposed += self.n_steps * self.state.batch_size
@@ -220,6 +225,7 @@ class HostFedBatchStep:
           self._body(slot)
         self.graphs[(rebuild, slot)] = g
     self._params_version = None
+    self._expected_step = state.step
     main = torch.cuda.current_stream()
     for ev in self.consumed:
       ev.record(main)
@@ -234,6 +240,9 @@ class HostFedBatchStep:
     """host_configs: pinned float32 [B, N] of +-1.  Asynchronous."""
     slot = self._submitted & 1
     main = torch.cuda.current_stream()
+    if self.state.step != self._expected_step:
+      self.state.step_dev.fill_(self.state.step)
+    self._expected_step = self.state.step + self.n_steps
     with torch.cuda.stream(self.copy_stream):
       self.copy_stream.wait_event(self.consumed[slot])
       self.dev_cfg[slot].copy_(host_configs, non_blocking=True)

@@ -108,6 +108,8 @@ class WavefunctionOptimizer:
 class EnergyGradientOptimizer(WavefunctionOptimizer):
   """Energy-gradient optimisation, training.py:506-623."""
 
+  use_cuda_graph = True     # replay accumulate + sweep as one captured graph per batch
+
   def build_opt_ops(self, wavefunction, hamiltonian, hparams, shared_resources):
     n_sites = hparams.num_sites
     local_batch, walker_id0 = distributed.shard(hparams.batch_size)
@@ -142,6 +144,18 @@ class EnergyGradientOptimizer(WavefunctionOptimizer):
       state['reduced'] = False
 
     self.sums = sums
+    n_sweep_steps = hparams.num_monte_carlo_sweeps * n_sites
+    graphed = {}
+
+    def batch_step():
+      """accumulate_gradients followed by one sweep group (training.py:614-617)
+      as one replayed CUDA graph around cgsvmc_batch_step."""
+      if 'g' not in graphed:
+        graphed['g'] = engine.GraphedBatchStep(configs.state, ansatz, ham, sums, n_sweep_steps)
+      graphed['g'].replay()
+      state['reduced'] = False
+
+    self._batch_step = Op(batch_step, 'batch_step') if self.use_cuda_graph else None
     return TrainOpsTraditional(
         accumulate_gradients=Op(accumulate, 'accumulate_gradients'),
         apply_gradients=Op(apply_gradients, 'apply_gradients'),
@@ -158,10 +172,14 @@ class EnergyGradientOptimizer(WavefunctionOptimizer):
     if train_ops.update_wf_norm is not None:
       session.run(train_ops.update_wf_norm)
     session.run(train_ops.reset_gradients)
+    fused = getattr(self, '_batch_step', None)
     for _ in range(hparams.num_batches_per_epoch):
-      session.run(train_ops.accumulate_gradients)
-      session.run(train_ops.mc_step,
-                  n_steps=hparams.num_monte_carlo_sweeps * hparams.num_sites)
+      if fused is not None:       # the same two ops, fused and graph-replayed
+        session.run(fused)
+      else:
+        session.run(train_ops.accumulate_gradients)
+        session.run(train_ops.mc_step,
+                    n_steps=hparams.num_monte_carlo_sweeps * hparams.num_sites)
     session.run(train_ops.apply_gradients)
     energy = session.run(train_ops.metrics)
     session.run(train_ops.reset_gradients)
