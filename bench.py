@@ -229,6 +229,11 @@ def run_ours(args, rank, world, local_rank):
   for _ in range(max(args.warmup, 3)):
     step()
     flush.zero_()
+  if world > 1:
+    for _ in range(3):               # one-time NCCL channel set-up happens here, not in the timed region
+      dist.all_reduce(payload)
+    sums.reset()
+  counter[0] = 0
   torch.cuda.synchronize()
   if world > 1:
     dist.barrier()
@@ -333,15 +338,23 @@ def run_ours(args, rank, world, local_rank):
   fp32_peak = 148 * 128 * 2 * f_hz / 1e12                      # TFLOP/s, derived
   mufu_peak = 148 * 16 * f_hz / 1e12                           # T transcendental/s, derived
   smem_peak = 148 * 128 * f_hz / 1e12                          # TB/s, derived (128 B/clk/SM)
+  # shared-memory bytes the algorithm needs per launch: two table rows per
+  # amplitude ratio (E_loc bond flips + sampler proposals) and one 2W row per up
+  # site for the state build; measured on B200: 128 B / clk / SM
+  # (profiles/r01u_fp32_pipes_microbench.txt)
+  smem_alg = ratios * tab_bytes + B * (N // 2) * H * 4
   roofline = {
-      'kernel': kernel, 'bound': 'fp32 issue / shared-memory bandwidth (SM-resident state; SURVEY.md 8(d))',
-      'achieved': flop / t_k / 1e12, 'peak': fp32_peak, 'unit': 'TFLOP/s',
-      'frac': flop / t_k / 1e12 / fp32_peak, 'traffic': None,
-      'peak_source': 'derived: 148 SM x 128 FP32 lanes x 2 x sm_max_mhz (%s); neither HBM nor the '
-                     'tensor pipe bounds this kernel' % pk['source'],
-      'smem': {'achieved': ratios * tab_bytes / t_k / 1e12, 'peak': smem_peak, 'unit': 'TB/s',
-               'frac': ratios * tab_bytes / t_k / 1e12 / smem_peak,
-               'what': 'ratio-table rows read from shared memory (2 x H x 4 B per ratio)'},
+      'kernel': kernel,
+      'bound': 'shared-memory bandwidth (walker state and ratio tables are SM-resident; neither HBM nor '
+               'the tensor pipe bounds this kernel, SURVEY.md 8(d))',
+      'achieved': smem_alg / t_k / 1e12, 'peak': smem_peak, 'unit': 'TB/s',
+      'frac': smem_alg / t_k / 1e12 / smem_peak, 'traffic': None,
+      'peak_source': 'derived: 148 SM x 128 B/clk x sm_max_mhz (%s clock; 128 B/clk/SM confirmed by '
+                     'profiles/microbench/fp32_pipes.cu)' % pk['source'],
+      'what': 'algorithmic shared-memory bytes: 2 x H x 4 B per amplitude ratio + N/2 x H x 4 B per state build',
+      'fp32': {'achieved': flop / t_k / 1e12, 'peak': fp32_peak, 'unit': 'TFLOP/s',
+               'frac': flop / t_k / 1e12 / fp32_peak,
+               'peak_source': 'derived: 148 SM x 128 FP32 lanes x 2 x sm_max_mhz'},
       'mufu': {'achieved': mufu / t_k / 1e12, 'peak': mufu_peak, 'unit': 'Ttranscendental/s',
                'frac': mufu / t_k / 1e12 / mufu_peak},
       'hbm': {'achieved': bytes_alg / t_k / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
@@ -395,7 +408,21 @@ def run_ours(args, rank, world, local_rank):
     dist.destroy_process_group()
 
 
+def _claim_stdout():
+  """Returns a file object on the real stdout and points fd 1 at stderr, so
+  that library banners (NCCL prints its version on stdout) cannot get in front
+  of the one JSON line the driver parses."""
+  sys.stdout.flush()
+  real = os.fdopen(os.dup(1), 'w')
+  os.dup2(2, 1)
+  return real
+
+
 def main():
+  global print
+  out = _claim_stdout()
+  _print = print
+  print = lambda *a, **k: (_print(*a, **dict(k, file=out)), out.flush())
   args = parse_args()
   rank = int(os.environ.get('RANK', '0'))
   world = int(os.environ.get('WORLD_SIZE', '1'))
