@@ -26,7 +26,14 @@ def run():
   w = torch.stack([torch.ones_like(e), e])
   s = a.weighted_grad_sum(packed, w)
   stats = _native.energy_stats(e)
+  # the fused batch step (estimators + sweep in one kernel) on a copy of the walkers
+  from cgs_vmc_b200 import engine
+  state = engine.WalkerState(256, 36, packed=packed.clone())
+  sums = engine.EnergyGradientSums(a, 256)
+  e_fused = sums.batch_step(ham, state, 36).clone()
   torch.cuda.synchronize()
+  assert torch.equal(e_fused, e), 'fused batch step: local energies differ from cgsvmc_local_energy'
+  assert torch.allclose(sums.sums, s, rtol=1e-5, atol=1e-5), 'fused batch step: gradient sums differ'
 
   cfg = bits.unpack(packed.cpu().numpy().view(np.uint64), 36)
   assert np.all(cfg.sum(axis=1) == 0), 'Sz not conserved'
