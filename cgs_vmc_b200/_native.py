@@ -28,6 +28,7 @@ EXPORTS = [
     'cgsvmc_log_amp', 'cgsvmc_mc_steps', 'cgsvmc_mc_steps_graph', 'cgsvmc_mc_step_replay',
     'cgsvmc_flip_enum', 'cgsvmc_local_energy', 'cgsvmc_weighted_grad_sum',
     'cgsvmc_energy_stats', 'cgsvmc_accumulate', 'cgsvmc_batch_step',
+    'cgsvmc_propose_exchange', 'cgsvmc_accept_exchange', 'cgsvmc_local_energy_from_amps',
 ]
 
 
@@ -79,6 +80,9 @@ def load():
   lib.cgsvmc_energy_stats.argtypes = [vp, i64, vp, vp]
   lib.cgsvmc_accumulate.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp]
   lib.cgsvmc_batch_step.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, i32, u64, u64, u64, vp, vp, vp]
+  lib.cgsvmc_propose_exchange.argtypes = [vp, i64, i32, u64, u64, u64, vp, vp, vp]
+  lib.cgsvmc_accept_exchange.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]
+  lib.cgsvmc_local_energy_from_amps.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
   for name in EXPORTS:
     fn = getattr(lib, name)
     if name not in ('cgsvmc_last_error', 'cgsvmc_ansatz_num_params'):
@@ -385,3 +389,56 @@ def energy_stats(e_loc, stats=None):
     stats = torch.zeros(4, dtype=torch.float64, device=e_loc.device)
   check(load().cgsvmc_energy_stats(_ptr(e_loc), e_loc.numel(), _ptr(stats), _stream()))
   return stats
+
+
+def propose_exchange(packed, n_sites, seed, walker_id0, step):
+  """One exchange proposal per walker (graph_builders.py:59-73) with the Philox
+  convention of the fused samplers.  Returns (proposed packed, u_acc)."""
+  require_cuda()
+  b = packed.shape[0]
+  _want(packed, torch.int64, (b, n_words(n_sites)), 'packed')
+  proposed = torch.empty_like(packed)
+  u_acc = torch.empty(b, dtype=torch.float32, device=packed.device)
+  check(load().cgsvmc_propose_exchange(_ptr(packed), b, n_sites, int(seed), int(walker_id0), int(step),
+                                       _ptr(proposed), _ptr(u_acc), _stream()))
+  return proposed, u_acc
+
+
+def accept_exchange(packed, proposed, n_sites, logabs, sign, logabs_new, sign_new, u_acc,
+                    accept_count=None):
+  """Metropolis accept / reject in the log domain (graph_builders.py:74-89);
+  updates packed, logabs and sign in place."""
+  b = packed.shape[0]
+  _want(packed, torch.int64, (b, n_words(n_sites)), 'packed')
+  _want(proposed, torch.int64, (b, n_words(n_sites)), 'proposed')
+  for name, t in (('logabs', logabs), ('logabs_new', logabs_new), ('u_acc', u_acc)):
+    _want(t, torch.float32, (b,), name)
+  if sign is not None:
+    _want(sign, torch.float32, (b,), 'sign')
+    _want(sign_new, torch.float32, (b,), 'sign_new')
+  if accept_count is not None:
+    _want(accept_count, torch.int64, (1,), 'accept_count')
+  check(load().cgsvmc_accept_exchange(_ptr(packed), _ptr(proposed), b, n_sites, _ptr(logabs), _ptr(sign),
+                                      _ptr(logabs_new), _ptr(sign_new), _ptr(u_acc),
+                                      _ptr(accept_count), _stream()))
+
+
+def local_energy_from_amps(ham, packed, logabs, sign, flipped_logabs, flipped_sign, want_parts=False):
+  """E_loc from externally evaluated amplitudes (operators.py:165-169, 241-259)."""
+  b = packed.shape[0]
+  _want(packed, torch.int64, (b, n_words(ham.n_sites)), 'packed')
+  _want(logabs, torch.float32, (b,), 'logabs')
+  _want(flipped_logabs, torch.float32, (b, ham.n_bonds), 'flipped_logabs')
+  if sign is not None:
+    _want(sign, torch.float32, (b,), 'sign')
+  if flipped_sign is not None:
+    _want(flipped_sign, torch.float32, (b, ham.n_bonds), 'flipped_sign')
+  dev = packed.device
+  e = torch.empty(b, dtype=torch.float32, device=dev)
+  diag = torch.empty(b, dtype=torch.float32, device=dev) if want_parts else None
+  off = torch.empty(b, dtype=torch.float32, device=dev) if want_parts else None
+  check(load().cgsvmc_local_energy_from_amps(ham._handle, _ptr(packed), b, _ptr(logabs), _ptr(sign),
+                                             _ptr(flipped_logabs), _ptr(flipped_sign), _ptr(e),
+                                             _ptr(diag), _ptr(off), _stream()))
+  return (e, diag, off) if want_parts else e
+

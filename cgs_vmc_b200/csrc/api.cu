@@ -411,6 +411,39 @@ int cgsvmc_batch_step(const cgsvmc_ansatz* a, const cgsvmc_ham* h, uint64_t* pac
   return cgsvmc_mc_steps(a, packed, B, n_steps, seed, walker_id0, step0, accept_count, nullptr, stream);
 }
 
+int cgsvmc_propose_exchange(const uint64_t* packed, int64_t B, int32_t N, uint64_t seed,
+                            uint64_t walker_id0, uint64_t step, uint64_t* proposed, float* u_acc,
+                            void* stream) {
+  if (B < 0 || N < 2 || N > CGSVMC_MAX_SITES) return invalid("propose_exchange: bad shape");
+  if (B > 0 && (packed == nullptr || proposed == nullptr || u_acc == nullptr))
+    return invalid("propose_exchange: NULL buffer");
+  return launch_propose_exchange(packed, B, N, seed, walker_id0, step, proposed, u_acc, (cudaStream_t)stream);
+}
+
+int cgsvmc_accept_exchange(uint64_t* packed, const uint64_t* proposed, int64_t B, int32_t N,
+                           float* logabs, float* sign, const float* logabs_new, const float* sign_new,
+                           const float* u_acc, unsigned long long* accept_count, void* stream) {
+  if (B < 0 || N < 2 || N > CGSVMC_MAX_SITES) return invalid("accept_exchange: bad shape");
+  if (B > 0 && (packed == nullptr || proposed == nullptr || logabs == nullptr || logabs_new == nullptr ||
+                u_acc == nullptr))
+    return invalid("accept_exchange: NULL buffer");
+  if ((sign == nullptr) != (sign_new == nullptr)) return invalid("accept_exchange: sign and sign_new go together");
+  return launch_accept_exchange(packed, proposed, B, N, logabs, sign, logabs_new, sign_new, u_acc,
+                                accept_count, (cudaStream_t)stream);
+}
+
+int cgsvmc_local_energy_from_amps(const cgsvmc_ham* h, const uint64_t* packed, int64_t B,
+                                  const float* logabs, const float* sign, const float* flipped_logabs,
+                                  const float* flipped_sign, float* e_loc, float* diag_out,
+                                  float* offdiag_ratio_out, void* stream) {
+  if (h == nullptr) return invalid("local_energy_from_amps: NULL hamiltonian");
+  if (B < 0) return invalid("local_energy_from_amps: n_walkers < 0");
+  if (B > 0 && (packed == nullptr || logabs == nullptr || (h->n_bonds > 0 && flipped_logabs == nullptr)))
+    return invalid("local_energy_from_amps: NULL buffer");
+  return launch_eloc_from_amps(h, packed, B, logabs, sign, flipped_logabs, flipped_sign, e_loc, diag_out,
+                               offdiag_ratio_out, (cudaStream_t)stream);
+}
+
 int cgsvmc_energy_stats(const float* e_loc, int64_t B, double* stats, void* stream) {
   if (B < 0) return invalid("energy_stats: n_walkers < 0");
   if (B > 0 && (e_loc == nullptr || stats == nullptr)) return invalid("energy_stats: NULL buffer");

@@ -59,6 +59,14 @@ int launch_random_configs(uint64_t* packed, int64_t B, int N, uint64_t seed, uin
 int launch_flip_enum(const cgsvmc_ham* h, const uint64_t* packed, int64_t B, uint64_t* flipped,
                      uint32_t* mask, cudaStream_t s);
 int launch_advance_counter(uint64_t* counter, uint64_t by, cudaStream_t s);
+int launch_propose_exchange(const uint64_t* packed, int64_t B, int N, uint64_t seed, uint64_t walker0,
+                            uint64_t step, uint64_t* proposed, float* u_acc, cudaStream_t s);
+int launch_accept_exchange(uint64_t* packed, const uint64_t* proposed, int64_t B, int N, float* logabs,
+                           float* sign, const float* logabs_new, const float* sign_new,
+                           const float* u_acc, unsigned long long* accept_count, cudaStream_t s);
+int launch_eloc_from_amps(const cgsvmc_ham* h, const uint64_t* packed, int64_t B, const float* logabs,
+                          const float* sign, const float* flipped_logabs, const float* flipped_sign,
+                          float* e_loc, float* diag, float* off, cudaStream_t s);
 int launch_fill(float* dst, int64_t n, float value, cudaStream_t s);
 int launch_energy_stats(const float* e, int64_t B, double* stats, cudaStream_t s);
 int launch_reduce_partials(const float* partials, int n_parts, int64_t n, float* out,

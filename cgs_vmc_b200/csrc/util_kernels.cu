@@ -150,6 +150,112 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
   }
 }
 
+// ---------------------------------------------------------------------------
+// Amplitude-agnostic forms of the sampler and of the local energy, for
+// wavefunctions whose amplitude is not one fused kernel: signed output
+// activations (layers.py:13-21) and the sum / difference / product composites
+// (wavefunctions.py:61-165).  The caller evaluates (log|psi|, sign psi) of the
+// proposed / bond-flipped configurations with cgsvmc_log_amp of the parts.
+// ---------------------------------------------------------------------------
+// graph_builders.py:59-73: a uniformly random up site and a uniformly random
+// down site are exchanged.  Same Philox convention as the fused samplers
+// (k_up = mulhi(r.x, n_up), k_dn = mulhi(r.y, n_dn), u = (r.z >> 8) 2^-24), so a
+// walker sees the same proposals on either path.  One warp per walker.
+template <int NW>
+__global__ void propose_exchange_kernel(const uint64_t* __restrict__ packed, int64_t B, int N, int W,
+                                        uint64_t seed, uint64_t walker0, uint64_t step,
+                                        uint64_t* __restrict__ proposed, float* __restrict__ u_acc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = warp; b < B; b += n_warps) {
+    uint64_t s[NW], up_mask[NW], dn_mask[NW];
+    int n_up = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      s[w] = w < W ? packed[b * W + w] : 0ull;
+      up_mask[w] = s[w] & valid_mask_word(N, w);
+      dn_mask[w] = ~s[w] & valid_mask_word(N, w);
+      n_up += __popcll(up_mask[w]);
+    }
+    const int n_dn = N - n_up;
+    const Philox4 r = walker_step_random(seed, walker0 + (uint64_t)b, step);
+    if (n_up > 0 && n_dn > 0) {
+      const int up = select_kth_bit<NW>(up_mask, (int)__umulhi(r.x, (uint32_t)n_up), lane);
+      const int dn = select_kth_bit<NW>(dn_mask, (int)__umulhi(r.y, (uint32_t)n_dn), lane);
+      flip_bit<NW>(s, up);
+      flip_bit<NW>(s, dn);
+    }
+    if (lane == 0) {
+      for (int w = 0; w < W; ++w) proposed[b * W + w] = s[w];
+      u_acc[b] = u32_to_unit(r.z);
+    }
+  }
+}
+
+// graph_builders.py:74-89: accept iff (psi'/psi)^2 > u (strict; NaN rejects),
+// in the log domain; accepted walkers take the proposed configuration and
+// amplitude.
+__global__ void accept_exchange_kernel(uint64_t* __restrict__ packed, const uint64_t* __restrict__ proposed,
+                                       int64_t B, int W, float* __restrict__ logabs,
+                                       float* __restrict__ sign, const float* __restrict__ logabs_new,
+                                       const float* __restrict__ sign_new, const float* __restrict__ u_acc,
+                                       unsigned long long* accept_count) {
+  unsigned int mine = 0;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B;
+       b += (int64_t)gridDim.x * blockDim.x) {
+    const float prob = expf(2.f * (logabs_new[b] - logabs[b]));
+    bool changed = false;
+    for (int w = 0; w < W; ++w) changed |= packed[b * W + w] != proposed[b * W + w];
+    if (changed && prob > u_acc[b]) {
+      for (int w = 0; w < W; ++w) packed[b * W + w] = proposed[b * W + w];
+      logabs[b] = logabs_new[b];
+      if (sign != nullptr) sign[b] = sign_new[b];
+      ++mine;
+    }
+  }
+  mine = (unsigned int)warp_sum((float)mine);
+  if ((threadIdx.x & 31) == 0 && mine && accept_count != nullptr)
+    atomicAdd(accept_count, (unsigned long long)mine);
+}
+
+// operators.py:165-169, 241-259 from amplitudes: one warp per walker, lanes
+// stride over the bonds.  flipped_* are [B, n_bonds]; entries of parallel
+// bonds are ignored (their mask is zero in the reference).
+__global__ void eloc_from_amps_kernel(const int2* __restrict__ ij, const float* __restrict__ jx,
+                                      const float* __restrict__ jz, int n_bonds,
+                                      const uint64_t* __restrict__ packed, int64_t B, int W,
+                                      const float* __restrict__ logabs, const float* __restrict__ sign,
+                                      const float* __restrict__ flipped_logabs,
+                                      const float* __restrict__ flipped_sign, float* __restrict__ e_loc,
+                                      float* __restrict__ diag_out, float* __restrict__ off_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = warp; b < B; b += n_warps) {
+    const float la = logabs[b], sg = sign != nullptr ? sign[b] : 1.f;
+    float diag = 0.f, off = 0.f;
+    for (int k = lane; k < n_bonds; k += 32) {
+      const int2 bd = ij[k];
+      const uint64_t wi = packed[b * W + (bd.x >> 6)], wj = packed[b * W + (bd.y >> 6)];
+      const bool anti = (((wi >> (bd.x & 63)) ^ (wj >> (bd.y & 63))) & 1ull) != 0;
+      diag += (anti ? -0.25f : 0.25f) * jz[k];
+      if (anti) {
+        const int64_t e = b * n_bonds + k;
+        const float sf = flipped_sign != nullptr ? flipped_sign[e] : 1.f;
+        off += 0.5f * jx[k] * sf * sg * expf(flipped_logabs[e] - la);
+      }
+    }
+    diag = warp_sum(diag);
+    off = warp_sum(off);
+    if (lane == 0) {
+      if (e_loc != nullptr) e_loc[b] = diag + off;
+      if (diag_out != nullptr) diag_out[b] = diag;
+      if (off_out != nullptr) off_out[b] = off;
+    }
+  }
+}
+
 int blocks_for(int64_t work_items, int per_block) {
   const int64_t need = (work_items + per_block - 1) / per_block;
   return (int)std::max<int64_t>(1, std::min<int64_t>(need, 148 * 16));
@@ -216,6 +322,36 @@ int launch_reduce_partials(const float* partials, int n_parts, int64_t n, float*
                            cudaStream_t s) {
   reduce_partials_kernel<<<blocks_for(n, 32), kThreads, 0, s>>>(partials, n_parts, n, out);
   return cuda_fail(cudaGetLastError(), "reduce_partials launch");
+}
+
+int launch_propose_exchange(const uint64_t* packed, int64_t B, int N, uint64_t seed, uint64_t walker0,
+                            uint64_t step, uint64_t* proposed, float* u_acc, cudaStream_t s) {
+  if (B == 0) return CGSVMC_OK;
+  const int W = n_words(N);
+  const int blocks = blocks_for(B, kThreads / 32);
+  if (W == 1) propose_exchange_kernel<1><<<blocks, kThreads, 0, s>>>(packed, B, N, W, seed, walker0, step, proposed, u_acc);
+  else if (W == 2) propose_exchange_kernel<2><<<blocks, kThreads, 0, s>>>(packed, B, N, W, seed, walker0, step, proposed, u_acc);
+  else propose_exchange_kernel<4><<<blocks, kThreads, 0, s>>>(packed, B, N, W, seed, walker0, step, proposed, u_acc);
+  return cuda_fail(cudaGetLastError(), "propose_exchange launch");
+}
+
+int launch_accept_exchange(uint64_t* packed, const uint64_t* proposed, int64_t B, int N, float* logabs,
+                           float* sign, const float* logabs_new, const float* sign_new,
+                           const float* u_acc, unsigned long long* accept_count, cudaStream_t s) {
+  if (B == 0) return CGSVMC_OK;
+  accept_exchange_kernel<<<blocks_for(B, kThreads), kThreads, 0, s>>>(
+      packed, proposed, B, n_words(N), logabs, sign, logabs_new, sign_new, u_acc, accept_count);
+  return cuda_fail(cudaGetLastError(), "accept_exchange launch");
+}
+
+int launch_eloc_from_amps(const cgsvmc_ham* h, const uint64_t* packed, int64_t B, const float* logabs,
+                          const float* sign, const float* flipped_logabs, const float* flipped_sign,
+                          float* e_loc, float* diag, float* off, cudaStream_t s) {
+  if (B == 0) return CGSVMC_OK;
+  eloc_from_amps_kernel<<<blocks_for(B, kThreads / 32), kThreads, 0, s>>>(
+      h->ij, h->jx, h->jz, h->n_bonds, packed, B, n_words(h->n_sites), logabs, sign, flipped_logabs,
+      flipped_sign, e_loc, diag, off);
+  return cuda_fail(cudaGetLastError(), "eloc_from_amps launch");
 }
 
 }  // namespace cgsvmc

@@ -85,10 +85,29 @@ def build_monte_carlo_sampling(inputs, wavefunction, psi=None):
   state = inputs.state
   last = {'before': 0}
 
+  def generic_steps(n_steps):
+    """Signed / composite amplitudes: propose on the device, evaluate
+    (log|psi|, sign) of the proposals through the parts' kernels, accept."""
+    n = state.n_sites
+    wavefunction.connect(n)
+    logabs, sign = wavefunction.amplitudes(state.packed)
+    logabs, sign = logabs.float().contiguous().clone(), sign.float().contiguous().clone()
+    for _ in range(int(n_steps)):
+      proposed, u_acc = _native.propose_exchange(state.packed, n, state.seed, state.walker_id0,
+                                                 state.step)
+      la_new, s_new = wavefunction.amplitudes(proposed)
+      _native.accept_exchange(state.packed, proposed, n, logabs, sign, la_new.float().contiguous(),
+                              s_new.float().contiguous(), u_acc, state.accept_count)
+      state.step += 1
+    state.proposed += int(n_steps) * state.batch_size
+
   def mc_step(n_steps=1):
     last['before'] = None
     last['mark'] = state.accept_count.clone()
-    state.mc_steps(wavefunction.native(state.n_sites), n_steps)
+    if wavefunction.fast_path:
+      state.mc_steps(wavefunction.native(state.n_sites), n_steps)
+    else:
+      generic_steps(n_steps)
     return inputs
 
   def acceptance_count():

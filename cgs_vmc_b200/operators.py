@@ -42,28 +42,42 @@ class _BondListOperator(Operator):
     return self._native[n_sites]
 
   def _evaluate(self, wavefunction, inputs):
+    """(E_loc, log|psi|, sign psi, diag, offdiag / psi) on the device."""
     from . import graph_builders
     n = inputs.shape[1]
-    a = wavefunction.native(n)
     packed = graph_builders.as_packed(inputs, n)
-    e, z, diag, off = a.local_energy(self.native(n), packed, want_parts=True)
-    return e, z - wavefunction._exp_norm_shift, diag, off
+    ham = self.native(n)
+    if wavefunction.fast_path:          # fused local-energy kernels
+      a = wavefunction.native(n)
+      e, z, diag, off = a.local_energy(ham, packed, want_parts=True)
+      return e, z - wavefunction._exp_norm_shift, torch.ones_like(z), diag, off
+    # signed / composite amplitudes: psi on the bond-flipped configurations of
+    # cgsvmc_flip_enum through the parts' kernels, combined on the device
+    wavefunction.connect(n)
+    b = packed.shape[0]
+    logabs, sign = wavefunction.amplitudes(packed)
+    _, flipped = ham.flip_enum(packed, want_flipped=True)
+    fl, fs = wavefunction.amplitudes(flipped.reshape(b * ham.n_bonds, -1))
+    logabs, sign = logabs.float().contiguous(), sign.float().contiguous()
+    e, diag, off = _native.local_energy_from_amps(
+        ham, packed, logabs, sign, fl.float().reshape(b, ham.n_bonds).contiguous(),
+        fs.float().reshape(b, ham.n_bonds).contiguous(), want_parts=True)
+    return e, logabs, sign, diag, off
 
   def build(self, wavefunction, inputs, psi=None):
     """(diagonal matrix element, off-diagonal term) of <R|O|psi>
     (operators.py:137-169, 227-247)."""
-    _, logpsi, diag, off = self._evaluate(wavefunction, inputs)
-    return diag, off * torch.exp(logpsi)
+    _, logpsi, sign, diag, off = self._evaluate(wavefunction, inputs)
+    return diag, off * sign * torch.exp(logpsi)
 
   def local_value(self, wavefunction, inputs, psi=None):
     """<R|O|psi> / <R|psi> (operators.py:171-181, 249-259)."""
-    e, _, _, _ = self._evaluate(wavefunction, inputs)
-    return e
+    return self._evaluate(wavefunction, inputs)[0]
 
   def apply_in_place(self, wavefunction, inputs, psi=None):
     """<R|O|psi> (operators.py:183-193, 261-271)."""
-    e, logpsi, _, _ = self._evaluate(wavefunction, inputs)
-    return e * torch.exp(logpsi)
+    e, logpsi, sign, _, _ = self._evaluate(wavefunction, inputs)
+    return e * sign * torch.exp(logpsi)
 
   def apply(self, wavefunction):
     raise NotImplementedError('Operator.apply builds a TransformedWavefunction (operators.py:90-125); '

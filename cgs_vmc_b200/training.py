@@ -15,7 +15,7 @@ import math
 
 import torch
 
-from . import distributed, engine, graph_builders, wavefunctions
+from . import _native, distributed, engine, graph_builders, wavefunctions
 from .session import Op
 
 TrainOpsTraditional = collections.namedtuple('TrainingOpsTraditional', [
@@ -95,6 +95,78 @@ def _epoch_increment():
   return Op(run, 'epoch_increment')
 
 
+class _Model:
+  """What an optimizer needs from a wavefunction, on either evaluation route
+  (wavefunctions.py: `fast_path` = one ansatz with exp output on the fused
+  kernels; otherwise signed / composite amplitudes through amplitudes()):
+  (log|psi|, sign), the estimator primitive S_k = sum_b w_kb O_b over all
+  trainable parameters, and the parameter update, leaf by leaf."""
+
+  def __init__(self, wavefunction, n_sites, hparams=None):
+    wavefunction.connect(n_sites)
+    self.wavefunction = wavefunction
+    self.fast = bool(wavefunction.fast_path)
+    self.leaves = wavefunction.leaves()
+    self.leaf_params = [leaf.native().params for leaf in self.leaves]
+    self.num_params = sum(int(p.numel()) for p in self.leaf_params)
+    self.device = self.leaf_params[0].device
+    self.optimizers = ([create_sgd_optimizer(hparams) for _ in self.leaves]
+                       if hparams is not None else None)
+    self.ansatz = wavefunction.native(n_sites) if self.fast else None
+
+  def log_psi(self, packed):
+    """(log|psi|, sign psi), float32 [B] each."""
+    if self.fast:
+      z = self.ansatz.log_amp(packed) - self.wavefunction._exp_norm_shift
+      return z, torch.ones_like(z)
+    logabs, sign = self.wavefunction.amplitudes(packed)
+    return logabs.float(), sign.float()
+
+  def weighted_grad_sum(self, packed, weights, out):
+    """out[K, P] += sum_b weights[k, b] d log psi_b / d params."""
+    weights = weights.reshape(-1, packed.shape[0]).float().contiguous()
+    if self.fast:
+      self.ansatz.weighted_grad_sum(packed, weights, out=out)
+    else:
+      out.add_(self.wavefunction.weighted_grad_sum(packed, weights))
+    return out
+
+  def apply_gradients(self, flat_grad):
+    off = 0
+    for params, optimizer in zip(self.leaf_params, self.optimizers):
+      n = int(params.numel())
+      optimizer.apply_gradients(params, flat_grad[off:off + n])
+      off += n
+
+
+class _GenericEnergyGradientSums:
+  """engine.EnergyGradientSums for signed / composite wavefunctions: the local
+  energy through Operator.local_value (amplitude-agnostic route), then the two
+  gradient sums and the energy statistics."""
+
+  def __init__(self, model, hamiltonian, configs):
+    self.model, self.hamiltonian, self.configs = model, hamiltonian, configs
+    self.sums = torch.zeros(2, model.num_params, dtype=torch.float32, device=model.device)
+    self.stats = torch.zeros(4, dtype=torch.float64, device=model.device)
+    self.n_batches = 0
+
+  def reset(self):
+    self.sums.zero_()
+    self.stats.zero_()
+    self.n_batches = 0
+
+  def accumulate(self, ham=None, packed=None):
+    packed = self.configs.packed
+    e = self.hamiltonian.local_value(self.model.wavefunction, self.configs).float().contiguous()
+    self.model.weighted_grad_sum(packed, torch.stack([torch.ones_like(e), e]), self.sums)
+    _native.energy_stats(e, self.stats)
+    self.n_batches += 1
+    return e
+
+  mean_energy = engine.EnergyGradientSums.mean_energy
+  gradient = engine.EnergyGradientSums.gradient
+
+
 class WavefunctionOptimizer:
   """Parent class for ground state optimizers (training.py:94-132)."""
 
@@ -117,10 +189,11 @@ class EnergyGradientOptimizer(WavefunctionOptimizer):
                                          walker_id0=walker_id0)
     mc_step, acc_rate = graph_builders.get_monte_carlo_sampling(
         shared_resources, configs, wavefunction)
-    ansatz = wavefunction.native(n_sites)
+    model = _Model(wavefunction, n_sites, hparams)
+    ansatz = model.ansatz
     ham = hamiltonian.native(n_sites)
-    sums = engine.EnergyGradientSums(ansatz, local_batch)
-    optimizer = create_sgd_optimizer(hparams)
+    sums = (engine.EnergyGradientSums(ansatz, local_batch) if model.fast
+            else _GenericEnergyGradientSums(model, hamiltonian, configs))
     state = {'reduced': False}
 
     def accumulate():                      # training.py:539-558, one batch
@@ -133,7 +206,7 @@ class EnergyGradientOptimizer(WavefunctionOptimizer):
 
     def apply_gradients():                 # training.py:562-567
       reduce_once()
-      optimizer.apply_gradients(ansatz.params, sums.gradient())
+      model.apply_gradients(sums.gradient())
 
     def metrics():                         # mean_energy, training.py:555, 582
       reduce_once()
@@ -155,7 +228,7 @@ class EnergyGradientOptimizer(WavefunctionOptimizer):
       graphed['g'].replay()
       state['reduced'] = False
 
-    self._batch_step = Op(batch_step, 'batch_step') if self.use_cuda_graph else None
+    self._batch_step = Op(batch_step, 'batch_step') if (self.use_cuda_graph and model.fast) else None
     return TrainOpsTraditional(
         accumulate_gradients=Op(accumulate, 'accumulate_gradients'),
         apply_gradients=Op(apply_gradients, 'apply_gradients'),
@@ -197,17 +270,16 @@ class SupervisedWavefunctionOptimizer:
                                          walker_id0=walker_id0)
     mc_step, acc_rate = graph_builders.get_monte_carlo_sampling(
         shared_resources, configs, wavefunction)
-    ansatz = wavefunction.native(n_sites)
-    target = target_wavefunction.native(n_sites)
-    optimizer = create_sgd_optimizer(hparams)
-    grad = torch.zeros(1, ansatz.num_params, dtype=torch.float32, device=ansatz.params.device)
+    model = _Model(wavefunction, n_sites, hparams)
+    target = _Model(target_wavefunction, n_sites)
+    grad = torch.zeros(1, model.num_params, dtype=torch.float32, device=model.device)
     log_norm = 0.5 * n_sites * math.log(2.0)       # sqrt(2^N), training.py:170
 
     def loss_and_weights():
       # ratio = psi_target * sqrt(2^N) / psi, formed in the log domain
-      z = ansatz.log_amp(configs.packed) - wavefunction._exp_norm_shift
-      zt = target.log_amp(configs.packed) - target_wavefunction._exp_norm_shift
-      ratio = torch.exp(zt + log_norm - z)
+      z, sg = model.log_psi(configs.packed)
+      zt, st = target.log_psi(configs.packed)
+      ratio = sg * st * torch.exp(zt + log_norm - z)
       total = float(hparams.batch_size)
       loss = ((1.0 - ratio) ** 2).sum() / total        # mean (psi - t)^2 / sg(psi)^2
       weights = (2.0 * (1.0 - ratio) / total).reshape(1, -1).contiguous()
@@ -216,9 +288,9 @@ class SupervisedWavefunctionOptimizer:
     def train_step():                      # optimizer.minimize(loss), training.py:175
       loss, weights = loss_and_weights()
       grad.zero_()
-      ansatz.weighted_grad_sum(configs.packed, weights, out=grad)
+      model.weighted_grad_sum(configs.packed, weights, grad)
       distributed.allreduce_(grad)
-      optimizer.apply_gradients(ansatz.params, grad[0])
+      model.apply_gradients(grad[0])
       return loss
 
     def metrics():
@@ -250,9 +322,9 @@ class _OverlapSums:
   accumulate calls, tf.metrics.mean over samples).  One packed float32 buffer
   [2P + 4] = [S_1 | S_r | sum r, sum e, n, 0] is the all-reduce payload."""
 
-  def __init__(self, ansatz, local_batch):
-    dev = ansatz.params.device
-    self.ansatz, self.P = ansatz, ansatz.num_params
+  def __init__(self, model, local_batch):
+    dev = model.device
+    self.model, self.P = model, model.num_params
     self.buf = torch.zeros(2 * self.P + 4, dtype=torch.float32, device=dev)
     self.sums = self.buf[:2 * self.P].view(2, self.P)
     self.tail = self.buf[2 * self.P:]
@@ -269,7 +341,7 @@ class _OverlapSums:
   def accumulate(self, packed, ratio, energy=None):
     self.weights[1].copy_(ratio)
     self.scratch.zero_()
-    self.ansatz.weighted_grad_sum(packed, self.weights, out=self.scratch)
+    self.model.weighted_grad_sum(packed, self.weights, self.scratch)
     self.sums.add_(self.scratch)
     self.tail[0] += ratio.sum()
     if energy is not None:
@@ -305,18 +377,17 @@ class LogOverlapSWO:
                                          walker_id0=walker_id0)
     mc_step, acc_rate = graph_builders.get_monte_carlo_sampling(
         shared_resources, configs, wavefunction)
-    ansatz = wavefunction.native(n_sites)
-    target = target_wavefunction.native(n_sites)
-    optimizer = create_sgd_optimizer(hparams)
-    sums = _OverlapSums(ansatz, local_batch)
+    model = _Model(wavefunction, n_sites, hparams)
+    target = _Model(target_wavefunction, n_sites)
+    sums = _OverlapSums(model, local_batch)
 
     def accumulate():                      # ratio = psi_target / psi, training.py:339
-      z = ansatz.log_amp(configs.packed) - wavefunction._exp_norm_shift
-      zt = target.log_amp(configs.packed) - target_wavefunction._exp_norm_shift
-      sums.accumulate(configs.packed, torch.exp(zt - z))
+      z, sg = model.log_psi(configs.packed)
+      zt, st = target.log_psi(configs.packed)
+      sums.accumulate(configs.packed, sg * st * torch.exp(zt - z))
 
     def apply_gradients():                 # training.py:358-362
-      optimizer.apply_gradients(ansatz.params, sums.gradient())
+      model.apply_gradients(sums.gradient())
 
     self.sums = sums
     return TrainOpsSupervised(
@@ -358,11 +429,9 @@ class DualSamplingSWO:
     target_mc_step, target_acc = graph_builders.build_monte_carlo_sampling(
         target_configs, target_wavefunction)
     psi_mc_step, psi_acc = graph_builders.build_monte_carlo_sampling(psi_configs, wavefunction)
-    ansatz = wavefunction.native(n_sites)
-    target = target_wavefunction.native(n_sites)
-    optimizer = create_sgd_optimizer(hparams)
-    dev = ansatz.params.device
-    grad = torch.zeros(1, ansatz.num_params, dtype=torch.float32, device=dev)
+    model = _Model(wavefunction, n_sites, hparams)
+    target = _Model(target_wavefunction, n_sites)
+    grad = torch.zeros(1, model.num_params, dtype=torch.float32, device=model.device)
     log_norm = 0.5 * n_sites * math.log(2.0)       # sqrt(2^N), training.py:451
     total = float(2 * local_half * distributed.world_size())
 
@@ -375,8 +444,10 @@ class DualSamplingSWO:
 
     def loss_and_weights():
       packed = torch.cat([psi_configs.packed, target_configs.packed], dim=0)
-      psi = torch.exp(ansatz.log_amp(packed) - wavefunction._exp_norm_shift)
-      t = torch.exp(target.log_amp(packed) - target_wavefunction._exp_norm_shift + log_norm)
+      z, sg = model.log_psi(packed)
+      zt, st = target.log_psi(packed)
+      psi = sg * torch.exp(z)
+      t = st * torch.exp(zt + log_norm)
       diff = psi - t
       loss = (diff * diff).sum() / total                 # training.py:461-463
       weights = (2.0 * diff * psi / total).reshape(1, -1).contiguous()
@@ -385,16 +456,16 @@ class DualSamplingSWO:
     def train_step():                      # optimizer.minimize(loss), training.py:466
       packed, loss, weights = loss_and_weights()
       grad.zero_()
-      ansatz.weighted_grad_sum(packed, weights, out=grad)
+      model.weighted_grad_sum(packed, weights, grad)
       distributed.allreduce_(grad)
-      optimizer.apply_gradients(ansatz.params, grad[0])
+      model.apply_gradients(grad[0])
       return loss
 
     def metrics():
       _, loss, _ = loss_and_weights()
       return float(distributed.allreduce_(loss.clone()).item())
 
-    self.loss_and_weights = loss_and_weights
+    self.loss_and_weights, self.model = loss_and_weights, model
     return TrainOpsSupervised(
         accumulate_gradients=None, apply_gradients=Op(train_step, 'train_step'),
         reset_gradients=None, mc_step=Op(mc_step, 'mc_step'), acc_rate=Op(acc_rate, 'acc_rate'),
@@ -423,24 +494,22 @@ class LogOverlapImaginaryTimeSWO(WavefunctionOptimizer):
                                          walker_id0=walker_id0)
     mc_step, acc_rate = graph_builders.get_monte_carlo_sampling(
         shared_resources, configs, wavefunction)
-    ansatz = wavefunction.native(n_sites)
+    model = _Model(wavefunction, n_sites, hparams)
     wf_omega = copy.deepcopy(wavefunction)        # supervisor, training.py:661
-    omega = wf_omega.native(n_sites)
-    ham = hamiltonian.native(n_sites)
+    wf_omega.connect(n_sites)
     beta = float(hparams.time_evolution_beta)
-    optimizer = create_sgd_optimizer(hparams)
-    sums = _OverlapSums(ansatz, local_batch)
+    sums = _OverlapSums(model, local_batch)
 
     def accumulate():
       # H psi_O = E_loc[psi_O] psi_O (apply_in_place, operators.py:261-271), so
-      # ratio = (psi_O - beta H psi_O) / psi = exp(z_O - z) (1 - beta E_O)
-      e_omega, z_omega = omega.local_energy(ham, configs.packed)
-      z = ansatz.log_amp(configs.packed) - wavefunction._exp_norm_shift
-      ratio = torch.exp(z_omega - wf_omega._exp_norm_shift - z) * (1.0 - beta * e_omega)
+      # ratio = (psi_O - beta H psi_O) / psi = (psi_O / psi) (1 - beta E_O)
+      e_omega, z_omega, s_omega, _, _ = hamiltonian._evaluate(wf_omega, configs)
+      z, sg = model.log_psi(configs.packed)
+      ratio = sg * s_omega * torch.exp(z_omega - z) * (1.0 - beta * e_omega)
       sums.accumulate(configs.packed, ratio, energy=e_omega)
 
     def apply_gradients():                 # training.py:693-701
-      optimizer.apply_gradients(ansatz.params, sums.gradient())
+      model.apply_gradients(sums.gradient())
 
     self.sums, self.supervisor = sums, wf_omega
     return TrainOpsSWO(

@@ -1,10 +1,19 @@
 """Mirror of the reference's wavefunctions.py for the in-scope ansaetze
-(fully_connected, rbm, conv_1d, conv_2d) on the CUDA library.
+(fully_connected, rbm, conv_1d, conv_2d) on the CUDA library, including the
+signed output activations (layers.py:13-21) and the sum / difference / product
+composites (wavefunctions.py:61-165, 1178-1194).
 
 Same class names, constructor arguments, `from_hparams`, registry and error
-behaviour (wavefunctions.py:21-615, 1157-1211).  Amplitudes are evaluated in
-the log domain on the device; `__call__` returns the reference's float32
-psi = exp(z - exp_norm_shift) (wavefunctions.py:206-232).
+behaviour (wavefunctions.py:21-615, 1157-1211).  Amplitudes are carried as
+(log|psi|, sign psi) on the device; `__call__` returns the reference's float32
+psi (= exp(z - exp_norm_shift) for output_activation = exp,
+wavefunctions.py:206-232).
+
+Two evaluation routes: a wavefunction with `fast_path` (one ansatz, exp output)
+runs on the fused sampler / local-energy / estimator kernels; everything else
+goes through `amplitudes()` -- cgsvmc_log_amp of the parts, combined here -- and
+the amplitude-agnostic entry points cgsvmc_propose_exchange /
+cgsvmc_accept_exchange / cgsvmc_local_energy_from_amps.
 """
 import copy
 import math
@@ -119,6 +128,32 @@ class Wavefunction:
   def flat_parameters(self):
     return self.native().params
 
+  # ---- (log|psi|, sign) interface used by the amplitude-agnostic route ---------
+  fast_path = False        # one native ansatz with exp output: fused kernels apply
+
+  def connect(self, n_sites):
+    """Creates the device parameters for `n_sites` (Sonnet creates variables
+    at first connection) and returns self."""
+    raise NotImplementedError
+
+  def leaves(self):
+    """The parameterised ansaetze of this wavefunction, in
+    get_trainable_variables order."""
+    raise NotImplementedError
+
+  def amplitudes(self, packed):
+    """(log|psi| float32 [B], sign float32 [B] of +-1 (0 where psi = 0))."""
+    raise NotImplementedError
+
+  def weighted_grad_sum(self, packed, weights):
+    """[K, P_total] = sum_b weights[k, b] d log psi_b / d params, concatenated
+    over leaves()."""
+    raise NotImplementedError
+
+  @property
+  def num_params(self):
+    return sum(leaf.native().num_params for leaf in self.leaves())
+
   def __deepcopy__(self, memo):
     """wavefunctions.py:177-204: a structurally identical module with its own
     (freshly initialised) variables, named 'dc_<name>'."""
@@ -148,6 +183,9 @@ class Wavefunction:
     """Op that raises exp_norm_shift iff max psi > max_value
     (wavefunctions.py:261-288).  `batch_of_amplitudes` may be a tensor or a
     callable returning the current amplitudes (graph semantics)."""
+    if not self.fast_path:          # no exp_norm_shift without the exp output
+      return None
+
     def run():
       amps = batch_of_amplitudes() if callable(batch_of_amplitudes) else batch_of_amplitudes
       log_max = float(torch.log(torch.as_tensor(amps).max()))
@@ -158,10 +196,16 @@ class Wavefunction:
     return Op(run, 'update_norm')
 
   def __add__(self, other):
-    raise NotImplementedError('sum / difference / product wavefunctions need signed '
-                              'amplitudes: not built in the CUDA path (SURVEY.md 8(f) rank 3)')
-  __sub__ = __add__
-  __mul__ = __add__
+    """wavefunctions.py:61-99."""
+    return SumOfWavefunctions(self, other)
+
+  def __mul__(self, other):
+    """wavefunctions.py:101-161: other is a Wavefunction or a float."""
+    return ProductOfWavefunctions(self, other)
+
+  def __sub__(self, other):
+    """wavefunctions.py:163-165."""
+    return self.__add__(other * -1.)
 
   @classmethod
   def from_hparams(cls, hparams, name=''):
@@ -171,23 +215,192 @@ class Wavefunction:
 def module_transfer_ops(source_module, target_module):
   """wavefunctions.py:300-325: op copying every variable of source to target."""
   def run():
-    src, dst = source_module.native(), target_module.native(source_module._n_sites)
-    if src.num_params != dst.num_params:
+    target_module.connect(source_module._n_sites)
+    src, dst = source_module.leaves(), target_module.leaves()
+    if len(src) != len(dst) or any(a.native().num_params != b.native().num_params
+                                   for a, b in zip(src, dst)):
       raise ValueError('`target_module` does not have the same structure as source.')
-    dst.params.copy_(src.params)
+    for a, b in zip(src, dst):
+      b.native().params.copy_(a.native().params)
   return Op(run, 'module_transfer')
 
 
 def _check_exp(output_activation):
-  if output_activation not in ('exp', None):
-    raise NotImplementedError(
-        'output_activation=%r: only exp (positive amplitudes, log domain) is built in '
-        'the CUDA path (SURVEY.md 8(f) rank 3)' % (output_activation,))
+  if output_activation not in layers.NONLINEARITIES:
+    raise ValueError('unknown output_activation %r' % (output_activation,))
+
+
+def _output_value_and_slope(name, z):
+  """f(z) and f'(z) for the output activations of layers.py:13-21."""
+  if name == 'identity':
+    return z, torch.ones_like(z)
+  if name == 'tanh':
+    v = torch.tanh(z)
+    return v, 1.0 - v * v
+  if name == 'sigmoid':
+    v = torch.sigmoid(z)
+    return v, v * (1.0 - v)
+  if name == 'relu':
+    return torch.relu(z), (z > 0).to(z.dtype)
+  if name == 'cos':
+    return torch.cos(z), -torch.sin(z)
+  if name == 'tan':
+    v = torch.tan(z)
+    return v, 1.0 + v * v
+  raise ValueError('unknown output_activation %r' % (name,))
 
 
 class _ExpAnsatz(Wavefunction):
+  """One native ansatz z(sigma) followed by the output activation:
+  psi = exp(z - exp_norm_shift) (wavefunctions.py:206-232, 350-353) or
+  psi = f(z) without a shift for the other activations."""
+
+  @property
+  def fast_path(self):
+    return getattr(self, '_output_activation', 'exp') in ('exp', None)
+
+  def connect(self, n_sites):
+    self.native(n_sites)
+    return self
+
+  def leaves(self):
+    return [self]
+
+  def _z(self, packed):
+    return self.native().log_amp(packed)
+
+  def amplitudes(self, packed):
+    z = self._z(packed)
+    if self.fast_path:
+      return z - self._exp_norm_shift, torch.ones_like(z)
+    v, _ = _output_value_and_slope(self._output_activation, z)
+    return torch.log(torch.abs(v)), torch.sign(v)
+
+  def weighted_grad_sum(self, packed, weights):
+    weights = weights.reshape(-1, packed.shape[0])
+    if not self.fast_path:        # d log psi = f'(z) / f(z) dz
+      v, dv = _output_value_and_slope(self._output_activation, self._z(packed))
+      weights = weights * (dv / v)
+    return self.native().weighted_grad_sum(packed, weights.float().contiguous())
+
   def _build(self, inputs):
-    return torch.exp(self.log_amplitude(inputs))
+    if self.fast_path:
+      return torch.exp(self.log_amplitude(inputs))
+    from . import graph_builders
+    n = inputs.shape[1]
+    self.native(n)
+    v, _ = _output_value_and_slope(self._output_activation,
+                                   self._z(graph_builders.as_packed(inputs, n)))
+    return v
+
+
+class _Composite(Wavefunction):
+  """Common part of the sum / product wrappers (wavefunctions.py:61-161)."""
+
+  def connect(self, n_sites):
+    self._n_sites = int(n_sites)
+    for sub in self._sub_wavefunctions:
+      sub.connect(n_sites)
+    return self
+
+  def native(self, n_sites=None):
+    raise NotImplementedError('a composite wavefunction has no single device ansatz; '
+                              'use leaves() / amplitudes()')
+
+  def leaves(self):
+    out = []
+    for sub in self._sub_wavefunctions:
+      out += sub.leaves()
+    return out
+
+  def get_trainable_variables(self):
+    out = []
+    for sub in self._sub_wavefunctions:
+      out += sub.get_trainable_variables()
+    return out
+
+  def _build(self, inputs):
+    from . import graph_builders
+    n = inputs.shape[1]
+    self.connect(n)
+    logabs, sign = self.amplitudes(graph_builders.as_packed(inputs, n))
+    return sign * torch.exp(logabs)
+
+  def update_norm(self, batch_of_amplitudes, max_value=1e10):
+    return None          # no exp_norm_shift of its own (wavefunctions.py:261-270)
+
+  def __deepcopy__(self, memo):
+    raise NotImplementedError('deepcopy of composite wavefunctions is not supported '
+                              '(the reference falls back to inspect-based copying, wavefunctions.py:177-204)')
+
+  @classmethod
+  def from_hparams(cls, hparams, name=''):
+    raise ValueError('Hparams initialization is not supported for %s.' % cls._what)
+
+
+class SumOfWavefunctions(_Composite):
+  """wavefunctions.py:64-97: psi = psi_a + psi_b."""
+  _what = 'sum'
+
+  def __init__(self, wf_a, wf_b, name='sum_of_wavefunctions'):
+    name = '_plus_'.join([wf_a._unique_name, wf_b._unique_name])
+    super().__init__(name=name)
+    self._wf_a, self._wf_b = wf_a, wf_b
+    self._sub_wavefunctions += [wf_a, wf_b]
+
+  def _parts(self, packed):
+    la, sa = self._wf_a.amplitudes(packed)
+    lb, sb = self._wf_b.amplitudes(packed)
+    m = torch.maximum(la, lb)
+    m = torch.where(torch.isfinite(m), m, torch.zeros_like(m))
+    va, vb = sa * torch.exp(la - m), sb * torch.exp(lb - m)
+    return va, vb, m
+
+  def amplitudes(self, packed):
+    va, vb, m = self._parts(packed)
+    v = va + vb
+    return m + torch.log(torch.abs(v)), torch.sign(v)
+
+  def weighted_grad_sum(self, packed, weights):
+    # d log(psi_a + psi_b) = (psi_a / psi) d log psi_a + (psi_b / psi) d log psi_b
+    weights = weights.reshape(-1, packed.shape[0])
+    va, vb, _ = self._parts(packed)
+    v = va + vb
+    return torch.cat([self._wf_a.weighted_grad_sum(packed, weights * (va / v)),
+                      self._wf_b.weighted_grad_sum(packed, weights * (vb / v))], dim=1)
+
+
+class ProductOfWavefunctions(_Composite):
+  """wavefunctions.py:104-159: psi = psi_a * psi_b with psi_b a Wavefunction
+  or a float factor."""
+  _what = 'product'
+
+  def __init__(self, wf_a, wf_b, name='product_of_wavefunctions'):
+    if isinstance(wf_b, Wavefunction):
+      name = '_times_'.join([wf_b._unique_name, wf_a._unique_name])
+      components = [wf_a, wf_b]
+    elif isinstance(wf_b, (float, int)):
+      name = '_times_'.join([str(float(wf_b)).replace('-', 'neg_'), wf_a._unique_name])
+      components = [wf_a]
+    else:
+      raise ValueError('Type of other is not supported.')
+    super().__init__(name=name)
+    self._wf_a, self._wf_b = wf_a, wf_b
+    self._sub_wavefunctions += components
+
+  def amplitudes(self, packed):
+    la, sa = self._wf_a.amplitudes(packed)
+    if isinstance(self._wf_b, Wavefunction):
+      lb, sb = self._wf_b.amplitudes(packed)
+      return la + lb, sa * sb
+    c = float(self._wf_b)
+    return la + (math.log(abs(c)) if c != 0.0 else -math.inf), sa * float(np.sign(c))
+
+  def weighted_grad_sum(self, packed, weights):
+    out = [self._wf_a.weighted_grad_sum(packed, weights)]
+    if isinstance(self._wf_b, Wavefunction):
+      out.append(self._wf_b.weighted_grad_sum(packed, weights))
+    return torch.cat(out, dim=1)
 
 
 class FullyConnectedNetwork(_ExpAnsatz):
@@ -342,7 +555,22 @@ def build_wavefunction(hparams):
   wavefunction_type = hparams.wavefunction_type
   if wavefunction_type in WAVEFUNCTION_TYPES:
     return WAVEFUNCTION_TYPES[wavefunction_type].from_hparams(hparams)
-  if wavefunction_type in _UNBUILT or wavefunction_type in ('sum', 'diff', 'prod'):
+  if wavefunction_type in ('sum', 'diff', 'prod'):       # wavefunctions.py:1178-1194
+    wf_type_a, wf_type_b = hparams.composite_wavefunction_types
+    activation_a, activation_b = hparams.composite_output_activations
+    wf_a_hparams, wf_b_hparams = copy.copy(hparams), copy.copy(hparams)
+    wf_a_hparams.set_hparam('output_activation', activation_a)
+    wf_a_hparams.set_hparam('wavefunction_type', wf_type_a)
+    wf_b_hparams.set_hparam('output_activation', activation_b)
+    wf_b_hparams.set_hparam('wavefunction_type', wf_type_b)
+    wf_a = WAVEFUNCTION_TYPES[wf_type_a].from_hparams(wf_a_hparams)
+    wf_b = WAVEFUNCTION_TYPES[wf_type_b].from_hparams(wf_b_hparams)
+    if wavefunction_type == 'sum':
+      return wf_a + wf_b
+    if wavefunction_type == 'diff':
+      return wf_a - wf_b
+    return wf_a * wf_b
+  if wavefunction_type in _UNBUILT:
     raise NotImplementedError(
         'wavefunction_type=%r exists in the reference but is outside the CUDA hot path '
         '(SURVEY.md section 2 rows 12-17)' % wavefunction_type)

@@ -246,6 +246,43 @@ int cgsvmc_batch_step(const cgsvmc_ansatz* ansatz, const cgsvmc_ham* ham,
                       uint64_t* step_counter, unsigned long long* accept_count,
                       void* stream);
 
+/* ---- amplitude-agnostic sampler / local energy ------------------------- */
+/* For wavefunctions whose amplitude is not a single fused kernel: output
+ * activations other than exp (layers.py:13-21, wavefunctions.py:350-353) give
+ * signed amplitudes, and the sum / difference / product composites
+ * (wavefunctions.py:61-165, 1178-1194) combine two ansaetze.  The caller
+ * evaluates (log|psi|, sign psi) with cgsvmc_log_amp of the parts and combines
+ * them; these three calls do the integer / reduction work around it.
+ *
+ * cgsvmc_propose_exchange replaces graph_builders.py:59-73 for one step:
+ * proposed[b] = packed[b] with a uniformly random up site and a uniformly
+ * random down site exchanged, u_acc[b] = the acceptance uniform; Philox
+ * convention of cgsvmc_mc_steps (same proposals for the same seed, walker,
+ * step).
+ * cgsvmc_accept_exchange replaces graph_builders.py:74-89: walkers with
+ * exp(2 (logabs_new - logabs)) > u_acc take the proposed configuration,
+ * logabs (and sign when given); *accept_count += accepted.
+ * cgsvmc_local_energy_from_amps replaces operators.py:165-169, 241-259:
+ *   e_loc[b] = sum_k [ jz_k/4 s_i s_j + jx_k/2 [s_i != s_j] sign' sign exp(logabs' - logabs) ]
+ * with flipped_logabs / flipped_sign float32 [B, n_bonds] for the configurations
+ * of cgsvmc_flip_enum (entries of parallel bonds are ignored); sign arrays may
+ * be NULL (all +1). */
+int cgsvmc_propose_exchange(const uint64_t* packed, int64_t n_walkers,
+                            int32_t n_sites, uint64_t seed, uint64_t walker_id0,
+                            uint64_t step, uint64_t* proposed, float* u_acc,
+                            void* stream);
+int cgsvmc_accept_exchange(uint64_t* packed_inout, const uint64_t* proposed,
+                           int64_t n_walkers, int32_t n_sites, float* logabs_inout,
+                           float* sign_inout, const float* logabs_new,
+                           const float* sign_new, const float* u_acc,
+                           unsigned long long* accept_count, void* stream);
+int cgsvmc_local_energy_from_amps(const cgsvmc_ham* ham, const uint64_t* packed,
+                                  int64_t n_walkers, const float* logabs,
+                                  const float* sign, const float* flipped_logabs,
+                                  const float* flipped_sign, float* e_loc,
+                                  float* diag_out, float* offdiag_ratio_out,
+                                  void* stream);
+
 /* Replaces tf.metrics.mean(local_energy) bookkeeping (training.py:555):
  * stats (double [4], device) += { sum e, sum e^2, B, 0 }. */
 int cgsvmc_energy_stats(const float* e_loc, int64_t n_walkers, double* stats,

@@ -25,7 +25,7 @@ def _names():
 
 def golden_names():
   """Cases of make_golden.py (amplitudes, sampler, Hamiltonian, EnergyGradient, SWO)."""
-  return [n for n in _names() if not n.startswith('opt_')]
+  return [n for n in _names() if not n.startswith(('opt_', 'cmp_'))]
 
 
 def opt_golden_names():
@@ -46,6 +46,32 @@ def load_golden(name):
 def golden(request):
   spec, data = load_golden(request.param)
   return request.param, spec, data
+
+
+def cmp_golden_names():
+  """Cases of make_golden_composites.py (signed outputs, sum / diff / prod)."""
+  return [n for n in _names() if n.startswith('cmp_')]
+
+
+def load_cmp_golden(name):
+  """Returns (kind, oracle leaves (float64), hparams overrides, arrays)."""
+  import torch
+  from oracle import ansatz, composite
+  data = dict(np.load(os.path.join(GOLDEN_DIR, name + '.npz')))
+  case = json.loads(str(data.pop('case_json')))
+  hp = case['hparams']
+  kind = hp['wavefunction_type'] if hp['wavefunction_type'] in ('sum', 'diff', 'prod') else 'single'
+  acts = hp.get('composite_output_activations') or [hp.get('output_activation', 'exp')]
+  leaves, off = [], 0
+  for k, spec_d in enumerate(case['leaf_specs']):
+    spec = ansatz.AnsatzSpec(**spec_d)
+    n = int(data['leaf_sizes'][k])
+    flat = torch.from_numpy(data['leaf_params_flat'][off:off + n]).to(torch.float64)
+    off += n
+    shift = float(data['leaf_shifts'][k])
+    leaves.append(composite.Leaf(spec, ansatz.unflatten(spec, flat), acts[k],
+                                 shift if acts[k] == 'exp' else None))
+  return kind, leaves, hp, data
 
 
 @pytest.fixture(params=opt_golden_names())

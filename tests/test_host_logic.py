@@ -65,8 +65,23 @@ def test_registries_and_error_types():
     wavefunctions.build_wavefunction(utils.create_hparams(wavefunction_type='mps'))
   with pytest.raises(NotImplementedError):
     training.GROUND_STATE_OPTIMIZERS['ITSWO']()
-  with pytest.raises(NotImplementedError):
-    wavefunctions.FullyConnectedNetwork(2, 8, output_activation='cos')
+  # signed output activations and composites are built (amplitude-agnostic route)
+  assert not wavefunctions.FullyConnectedNetwork(2, 8, output_activation='cos').fast_path
+  assert wavefunctions.FullyConnectedNetwork(2, 8).fast_path
+  with pytest.raises(ValueError):
+    wavefunctions.FullyConnectedNetwork(2, 8, output_activation='softplus')
+  a, b = wavefunctions.RestrictedBoltzmannNetwork(0, 8), wavefunctions.FullyConnectedNetwork(1, 4)
+  assert (a + b)._unique_name == 'restricted_boltzmann_network_plus_fully_connected_network'
+  assert (a * b)._unique_name == 'fully_connected_network_times_restricted_boltzmann_network'
+  assert (a * -1.)._unique_name == 'neg_1.0_times_restricted_boltzmann_network'      # wavefunctions.py:130-133
+  assert [type(w).__name__ for w in (a - b)._sub_wavefunctions] == [
+      'RestrictedBoltzmannNetwork', 'ProductOfWavefunctions']
+  with pytest.raises(ValueError, match='not supported'):
+    type(a + b).from_hparams(utils.create_hparams())
+  comp = wavefunctions.build_wavefunction(utils.create_hparams(
+      wavefunction_type='diff', composite_wavefunction_types=('rbm', 'fully_connected'),
+      composite_output_activations=('exp', 'tanh'), num_sites=8))
+  assert not comp.fast_path and len(comp._sub_wavefunctions) == 2
   wf = wavefunctions.build_wavefunction(utils.create_hparams(
       wavefunction_type='conv_2d', num_sites=36, size_x=6, size_y=6))
   assert wf._n_sites == 36 and wf._param_shapes(36)[0] == (5, 5, 1, 16)
