@@ -286,7 +286,10 @@ def run_ours(args, rank, world, local_rank):
     for k in range(n):
       fed.submit(host_cfg)
       if fed.outstanding() > 1:
-        fed.result()                                              # host consumes step k - 1
+        fed.result()                                              # host consumes the energy of step k - 1
+      if (k + 1) % EPOCH_BATCHES == 0:
+        fed.fetch_sums()                                          # epoch end: the [2, P] gradient sums
+        sums.reset()
     while fed.outstanding():
       fed.result()
 
@@ -390,7 +393,10 @@ def run_ours(args, rank, world, local_rank):
       'e2e': {'value': walkers_total * SWEEP_STEPS * args.steps / e2e_s, 'unit': 'walker-steps/s',
               'eloc_evals_per_sec': walkers_total * args.steps / e2e_s,
               'ms_per_step': e2e_s / args.steps * 1e3,
-              'h2d_bytes_per_step': fed.h2d_bytes, 'd2h_bytes_per_step': fed.d2h_bytes},
+              'h2d_bytes_per_step': fed.h2d_bytes,
+              'd2h_bytes_per_step': fed.d2h_bytes_stats + fed.d2h_bytes_sums / EPOCH_BATCHES,
+              'd2h': 'energy statistics every step; the [2, P] gradient sums once per epoch of %d steps '
+                     '(training.py:562-568 reads them once per epoch)' % EPOCH_BATCHES},
       'gpu_launches': n_launch,
       'clocks': clocks,
       'wall_s_timed_region': wall,

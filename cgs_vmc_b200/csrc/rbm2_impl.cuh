@@ -380,8 +380,10 @@ __device__ __forceinline__ float ratio_round(const Tables& t, const uint32_t* li
   }
   float term = 0.f;
   if (mine) {
-    const float l2 = total + (ld1<WS>(t.a2 + dn) - ld1<WS>(t.a2 + up));
-    term = 0.5f * __int_as_float(bond_s[ent >> 16].z) * ex2_approx(l2);
+    // (explicit roundings: no FMA contraction, so the fused, split and
+    // gradient-less instantiations give bit-identical local energies)
+    const float l2 = __fadd_rn(total, __fsub_rn(ld1<WS>(t.a2 + dn), ld1<WS>(t.a2 + up)));
+    term = __fmul_rn(0.5f * __int_as_float(bond_s[ent >> 16].z), ex2_approx(l2));
   }
   return term;
 }
@@ -782,7 +784,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
             const int4 bd = bond_s[k];
             const int bi = spin_bit<NW>(s, bd.x);
             anti = bi != spin_bit<NW>(s, bd.y);
-            diag += (anti ? -0.25f : 0.25f) * __int_as_float(bd.w);   // operators.py:165,169
+            diag = __fmaf_rn(anti ? -0.25f : 0.25f, __int_as_float(bd.w), diag);   // operators.py:165,169
             const int up = bi ? bd.x : bd.y, dn = bi ? bd.y : bd.x;
             ent = (uint32_t)dn | ((uint32_t)up << 8) | ((uint32_t)k << 16);
           }
@@ -810,11 +812,11 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
         float off_lane = 0.f;
         int it0 = 0;
         for (; n_max - it0 > RND / 2; it0 += RND)
-          off_lane += ratio_round<RND, LPW, KJV, WS>(t, list, bond_s, it0, cnt, sub, p, m);
+          off_lane = __fadd_rn(off_lane, ratio_round<RND, LPW, KJV, WS>(t, list, bond_s, it0, cnt, sub, p, m));
         if (it0 < n_max)
-          off_lane += ratio_round<RND / 2, LPW, KJV, WS>(t, list, bond_s, it0, cnt, sub, p, m);
+          off_lane = __fadd_rn(off_lane, ratio_round<RND / 2, LPW, KJV, WS>(t, list, bond_s, it0, cnt, sub, p, m));
         const float off = group_sum<LPW>(off_lane);
-        e_val = diag + off;
+        e_val = __fadd_rn(diag, off);
         RBM2_MARK(1, 3);
         if (valid && sub == 0) {
           if (A.e_loc) A.e_loc[b] = e_val;
@@ -892,7 +894,23 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
                 acc[1][r][c] = fmaf(a1v[r], tv[c], acc[1][r][c]);
               }
           }
-          // row i < N: W[i][j]; row N: c[j]
+          // row i < N: W[i][j]; row N: c[j].  When the CTA's slice already holds
+          // sums (later batches of a launch) all of the old values are requested
+          // before the first store -- a load-add-store chain per element would
+          // pay the memory latency 32 times.
+          if (batch_no != 0) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const int i = min(4 * rt + r, im.N);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const int j = min(4 * ct + c, im.H - 1);
+                  acc[k][r][c] += __ldcg(part + (size_t)k * A.P + im.N + 1 + (size_t)i * im.H + j);
+                }
+              }
+          }
 #pragma unroll
           for (int k = 0; k < 2; ++k)
 #pragma unroll
@@ -903,8 +921,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
               for (int c = 0; c < 4; ++c) {
                 const int j = 4 * ct + c;
                 if (j >= im.H) continue;
-                float* dst = part + (size_t)k * A.P + im.N + 1 + (size_t)i * im.H + j;
-                *dst = batch_no == 0 ? acc[k][r][c] : *dst + acc[k][r][c];
+                part[(size_t)k * A.P + im.N + 1 + (size_t)i * im.H + j] = acc[k][r][c];
               }
             }
         }

@@ -90,15 +90,12 @@ class EnergyGradientSums:
     (training.py:614-617) through cgsvmc_batch_step: one fused kernel for the
     pure RBM, the two calls otherwise."""
     e_row = self.weights[1]
-    if on_device_counter:      # capturable: the caller keeps state.step in sync
-      self.ansatz.batch_step(ham, state.packed, self.sums, self.stats, n_steps, state.seed,
-                             state.walker_id0, step_counter=state.step_dev,
-                             accept_count=state.accept_count, e_loc_out=e_row,
-                             log_amp_out=self.log_amp)
-      return e_row
+    counter = dict(step_counter=state.step_dev) if on_device_counter else dict(step0=state.step)
     self.ansatz.batch_step(ham, state.packed, self.sums, self.stats, n_steps, state.seed,
-                           state.walker_id0, step0=state.step, accept_count=state.accept_count,
-                           e_loc_out=e_row, log_amp_out=self.log_amp)
+                           state.walker_id0, accept_count=state.accept_count, e_loc_out=e_row,
+                           log_amp_out=self.log_amp, **counter)
+    if on_device_counter:      # capturable: the caller keeps state.step in sync
+      return e_row
     self.n_batches += 1
     state.step += int(n_steps)
     state.proposed += int(n_steps) * state.batch_size
@@ -115,117 +112,107 @@ class EnergyGradientSums:
     return self.sums[1] / nb - self.mean_energy().float() * self.sums[0] / nb
 
 
-class GraphedBatchStep:
-  """One batch iteration of EnergyGradientOptimizer.run_optimization_epoch
-  (training.py:614-617) -- accumulate_gradients followed by
-  num_monte_carlo_sweeps * num_sites Metropolis steps -- captured once as a
-  CUDA graph (cgsvmc_batch_step: table build, fused estimator + sweep kernel,
-  reduction, step-counter advance) and replayed: one graph launch instead of a
-  Python dispatch per kernel (the reference pays one session.run per
-  Metropolis step).
+class _CapturedStep:
+  """Shared machinery of the captured batch steps: warm-up on a side stream
+  (sizes every scratch buffer), undo, two captures per variant -- with the
+  parameter-table build (replayed after a parameter update, detected through
+  the torch version counter of the parameter buffer) and without it -- and the
+  bookkeeping of the device-side Philox step counter."""
 
-  The graph is captured twice, with and without the parameter-table build;
-  replay() picks the rebuilding one whenever the parameter buffer was written
-  since the last replay (torch version counter), so in-place optimizer updates
-  are picked up.  The Philox step offset lives in device memory and is
-  advanced by the graph itself."""
-
-  def __init__(self, state, ansatz, ham, sums, n_steps):
+  def _prepare(self, state, ansatz, ham, sums, n_steps, variants):
     self.state, self.ansatz, self.ham, self.sums, self.n_steps = state, ansatz, ham, sums, int(n_steps)
+    dev = state.packed.device
     state.step_dev.fill_(state.step)
     saved = (sums.sums.clone(), sums.stats.clone(), state.packed.clone(), state.accept_count.clone())
-    side = torch.cuda.Stream(device=state.packed.device)
+    side = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):           # warm-up: sizes every scratch buffer
-      self._body()
+    with torch.cuda.stream(side):
+      self._body(variants[0])
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     # undo the warm-up so that capture + replays see the caller's state
     sums.sums.copy_(saved[0]); sums.stats.copy_(saved[1])
     state.packed.copy_(saved[2]); state.accept_count.copy_(saved[3])
     state.step_dev.fill_(state.step)
-    # two captures: with the table build (replayed after a parameter update)
-    # and without it (the tables of the previous replay are still valid)
-    self.graph_rebuild = torch.cuda.CUDAGraph()
-    _native.check(_native.load().cgsvmc_ansatz_params_changed(ansatz._handle))   # capture the table build
-    with torch.cuda.graph(self.graph_rebuild):
-      self._body()
-    self.graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(self.graph):
-      self._body()
+    self.graphs = {}
+    for rebuild in (True, False):
+      for v in variants:
+        if rebuild:
+          _native.check(_native.load().cgsvmc_ansatz_params_changed(ansatz._handle))
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+          self._body(v)
+        self.graphs[(rebuild, v)] = g
     # capture does not execute: nothing to undo, but the tables the handle now
-    # believes valid were never built -- force the rebuilding graph first
+    # believes valid were never built -- the first replay must be a rebuilding one
     self._params_version = None
     self._expected_step = state.step
 
-  def _body(self):
-    self.sums.batch_step(self.ham, self.state, self.n_steps, on_device_counter=True)
-
-  def replay(self):
+  def _replay(self, variant):
     if self.state.step != self._expected_step:
       # steps were taken outside the graph (equilibration): resync the device counter
       self.state.step_dev.fill_(self.state.step)
     version = self.ansatz.params._version
-    if version != self._params_version:
-      self.graph_rebuild.replay()
-      self._params_version = version
-    else:
-      self.graph.replay()
+    rebuild = version != self._params_version
+    self._params_version = version
+    self.graphs[(rebuild, variant)].replay()
     self._expected_step = self.state.step + self.n_steps
     self.sums.n_batches += 1
     self.state.step += self.n_steps
     self.state.proposed += self.n_steps * self.state.batch_size
 
 
-class HostFedBatchStep:
+class GraphedBatchStep(_CapturedStep):
+  """One batch iteration of EnergyGradientOptimizer.run_optimization_epoch
+  (training.py:614-617) -- accumulate_gradients followed by
+  num_monte_carlo_sweeps * num_sites Metropolis steps -- captured once as a
+  CUDA graph and replayed: one graph launch instead of a Python dispatch per
+  kernel (the reference pays one session.run per Metropolis step).
+
+  The graph holds cgsvmc_batch_step: the fused estimator + sweep kernel and the
+  deterministic reduction (which also advances the Philox step counter)."""
+
+  def __init__(self, state, ansatz, ham, sums, n_steps):
+    self._prepare(state, ansatz, ham, sums, n_steps, (0,))
+
+  def _body(self, variant):
+    self.sums.batch_step(self.ham, self.state, self.n_steps, on_device_counter=True)
+
+  def replay(self):
+    self._replay(0)
+
+
+class HostFedBatchStep(_CapturedStep):
   """The batch step for a caller that keeps the reference's float32 [B, N]
   configuration tensor in HOST memory (graph_builders.py:92-125 viewed from
   outside the session): every submit() uploads one pinned host batch on a copy
   stream (double-buffered, so the upload of batch k overlaps the compute of
   batch k - 1), then replays one captured graph per buffer slot --
-  cgsvmc_pack_configs, cgsvmc_batch_step, and the device->host copy of the
-  [2, P] estimator sums and the energy statistics into pinned host buffers.
-  result() blocks until the oldest outstanding batch has landed on the host."""
+  cgsvmc_pack_configs, the batch step, and the device->host copy of the step's
+  result, the energy statistics (sum E, sum E^2, n: the metric the reference
+  reads back, training.py:619-620), into pinned host memory.  result() blocks
+  until the oldest outstanding batch has landed.  The [2, P] gradient sums are
+  accumulated on the device like the reference's local variables and read with
+  fetch_sums() when the optimizer needs them (once per epoch)."""
 
   def __init__(self, state, ansatz, ham, sums, n_steps):
     dev = state.packed.device
-    self.state, self.ansatz, self.ham, self.sums, self.n_steps = state, ansatz, ham, sums, int(n_steps)
     B, N, P = state.batch_size, state.n_sites, ansatz.num_params
     self.copy_stream = torch.cuda.Stream(device=dev)
     self.dev_cfg = [torch.empty(B, N, dtype=torch.float32, device=dev) for _ in range(2)]
-    self.host_sums = [torch.empty(2, P, dtype=torch.float32).pin_memory() for _ in range(2)]
     self.host_stats = [torch.empty(4, dtype=torch.float64).pin_memory() for _ in range(2)]
+    self.host_sums = torch.empty(2, P, dtype=torch.float32).pin_memory()
     self.uploaded = [torch.cuda.Event() for _ in range(2)]
     self.consumed = [torch.cuda.Event() for _ in range(2)]
     self.landed = [torch.cuda.Event() for _ in range(2)]
     self.h2d_bytes = B * N * 4
-    self.d2h_bytes = 2 * P * 4 + 32
+    self.d2h_bytes_stats = 32
+    self.d2h_bytes_sums = 2 * P * 4
     self._submitted = 0
     self._collected = 0
-    state.step_dev.fill_(state.step)
-    saved = (sums.sums.clone(), sums.stats.clone(), state.packed.clone(), state.accept_count.clone())
     for c in self.dev_cfg:
       c.copy_(state.configs())
-    side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):           # warm-up: sizes every scratch buffer, builds the tables
-      self._body(0)
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    sums.sums.copy_(saved[0]); sums.stats.copy_(saved[1])
-    state.packed.copy_(saved[2]); state.accept_count.copy_(saved[3])
-    state.step_dev.fill_(state.step)
-    self.graphs = {}
-    for rebuild in (True, False):           # with / without the parameter-table build
-      for slot in range(2):
-        if rebuild:
-          _native.check(_native.load().cgsvmc_ansatz_params_changed(ansatz._handle))
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-          self._body(slot)
-        self.graphs[(rebuild, slot)] = g
-    self._params_version = None
-    self._expected_step = state.step
+    self._prepare(state, ansatz, ham, sums, n_steps, (0, 1))
     main = torch.cuda.current_stream()
     for ev in self.consumed:
       ev.record(main)
@@ -233,41 +220,38 @@ class HostFedBatchStep:
   def _body(self, slot):
     _native.pack_configs(self.dev_cfg[slot], out=self.state.packed)
     self.sums.batch_step(self.ham, self.state, self.n_steps, on_device_counter=True)
-    self.host_sums[slot].copy_(self.sums.sums, non_blocking=True)
     self.host_stats[slot].copy_(self.sums.stats, non_blocking=True)
 
   def submit(self, host_configs):
     """host_configs: pinned float32 [B, N] of +-1.  Asynchronous."""
     slot = self._submitted & 1
     main = torch.cuda.current_stream()
-    if self.state.step != self._expected_step:
-      self.state.step_dev.fill_(self.state.step)
-    self._expected_step = self.state.step + self.n_steps
     with torch.cuda.stream(self.copy_stream):
       self.copy_stream.wait_event(self.consumed[slot])
       self.dev_cfg[slot].copy_(host_configs, non_blocking=True)
       self.uploaded[slot].record(self.copy_stream)
     main.wait_event(self.uploaded[slot])
-    version = self.ansatz.params._version
-    rebuild = version != self._params_version
-    self._params_version = version
-    self.graphs[(rebuild, slot)].replay()
+    self._replay(slot)
     self.consumed[slot].record(main)      # the packed copy is taken: the slot may be refilled
     self.landed[slot].record(main)
     self._submitted += 1
-    self.sums.n_batches += 1
-    self.state.step += self.n_steps
-    self.state.proposed += self.n_steps * self.state.batch_size
 
   def outstanding(self):
     return self._submitted - self._collected
 
   def result(self):
-    """(host sums [2, P], host stats [4]) of the oldest outstanding batch."""
+    """Host energy statistics [sum E, sum E^2, n, 0] (cumulative since the last
+    reset) as of the oldest outstanding batch."""
     if self._collected >= self._submitted:
       raise RuntimeError('no batch outstanding')
     slot = self._collected & 1
     self.landed[slot].synchronize()
     self._collected += 1
-    return self.host_sums[slot], self.host_stats[slot]
+    return self.host_stats[slot]
 
+  def fetch_sums(self):
+    """The [2, P] gradient sums accumulated so far, in pinned host memory
+    (synchronises)."""
+    self.host_sums.copy_(self.sums.sums, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return self.host_sums

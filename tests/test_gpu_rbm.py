@@ -452,10 +452,13 @@ def test_accumulate_equals_separate_calls(native, spec):
     e_out = torch.empty(batch, device='cuda')
     z_out = torch.empty(batch, device='cuda')
     a.accumulate(ham, packed, sums, stats, e_loc_out=e_out, log_amp_out=z_out)
-    assert torch.equal(e_out, e) and torch.equal(z_out, z)
+    # (the two calls may place the tables differently -- shared vs global memory --
+    # and then sum the bond terms in rounds of different size)
+    assert torch.equal(z_out, z)
+    np.testing.assert_allclose(e_out.cpu().numpy(), e.cpu().numpy(), rtol=3e-6, atol=3e-5)
     scale = ref.abs().max().item() + 1.0
     assert float((sums - ref).abs().max()) <= 2e-6 * scale * max(1.0, batch ** 0.5)
-    np.testing.assert_allclose(stats.cpu().numpy(), st_ref.cpu().numpy(), rtol=1e-12)
+    np.testing.assert_allclose(stats.cpu().numpy(), st_ref.cpu().numpy(), rtol=2e-7)   # from e_out vs e
     a.accumulate(ham, packed, sums, stats)
     assert float((sums - 2 * ref).abs().max()) <= 4e-6 * scale * max(1.0, batch ** 0.5)
     assert stats[2].item() == 2 * batch
@@ -538,6 +541,12 @@ def test_graphed_batch_step_equals_separate_launches(native):
   assert s1.step == s2.step and int(s1.step_dev.item()) == s1.step
 
 
+def _close_sums(got, ref):
+  """Same float32 sums up to the summation order: 2e-6 of the largest entry."""
+  ref = ref.cpu().numpy()
+  np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=0, atol=2e-6 * np.abs(ref).max() + 1e-6)
+
+
 @pytest.mark.parametrize('n_side,hidden,batch,j1j2', [(6, 144, 777, False), (4, 24, 130, True),
                                                       (16, 256, 300, False), (10, 64, 257, True)])
 def test_batch_step_equals_accumulate_then_sweep(native, n_side, hidden, batch, j1j2):
@@ -570,9 +579,10 @@ def test_batch_step_equals_accumulate_then_sweep(native, n_side, hidden, batch, 
 
 
 def test_host_fed_batch_step(native):
-  """engine.HostFedBatchStep (pinned host configurations in, estimator sums
-  out, one graph per buffer slot) gives the sums of accumulate() on the same
-  configurations, batch after batch, including after a parameter update."""
+  """engine.HostFedBatchStep (pinned host configurations in, energy statistics
+  out every batch, gradient sums on request; one graph per buffer slot) gives
+  the statistics and sums of accumulate() on the same configurations, batch
+  after batch, including after a parameter update."""
   from cgs_vmc_b200 import engine
   spec = _c2_spec()
   a, _, _ = _setup(spec, seed=3, batch=1)
@@ -590,11 +600,12 @@ def test_host_fed_batch_step(native):
     cfg = bits.random_sz0_configs(36, B, gen).astype(np.float32)
     host = torch.from_numpy(cfg).pin_memory()
     fed.submit(host)
-    got_sums, got_stats = fed.result()
+    got_stats = fed.result()
     ref_sums.accumulate(ham, native.pack_configs(torch.from_numpy(cfg).cuda()))
     torch.cuda.synchronize()
-    np.testing.assert_allclose(got_sums.numpy(), ref_sums.sums.cpu().numpy(), rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(got_stats.numpy(), ref_sums.stats.cpu().numpy(), rtol=1e-12)
+    if k in (1, 4):
+      _close_sums(fed.fetch_sums(), ref_sums.sums)
   assert fed.outstanding() == 0 and s1.step == 5 * 36
   assert int(s1.step_dev.item()) == s1.step
 
