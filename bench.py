@@ -218,21 +218,25 @@ def run_ours(args, rank, world, local_rank):
       launches[0] += 3   # walker kernel, reduce, mc kernel (parameter tables are cached)
     counter[0] += 1
     if world > 1 and counter[0] % EPOCH_BATCHES == 0:
-      # epoch end (training.py:619-620): the only exchange of the sharded run --
-      # accumulation is linear, so the [2P + 4] sums are all-reduced once per
-      # epoch, not once per batch
-      payload[:2 * P].copy_(sums.sums.reshape(-1))
-      payload[2 * P:].copy_(sums.stats.float())
-      dist.all_reduce(payload)
-      sums.reset()
+      epoch_end()
+
+  def epoch_end():
+    # epoch end (training.py:619-620): the only exchange of the sharded run --
+    # accumulation is linear, so the [2P + 4] sums are all-reduced once per
+    # epoch, not once per batch
+    payload[:2 * P].copy_(sums.sums.reshape(-1))
+    payload[2 * P:].copy_(sums.stats.float())
+    dist.all_reduce(payload)
+    sums.reset()
 
   for _ in range(max(args.warmup, 3)):
     step()
     flush.zero_()
   if world > 1:
-    for _ in range(3):               # one-time NCCL channel set-up happens here, not in the timed region
-      dist.all_reduce(payload)
-    sums.reset()
+    for _ in range(3):               # one-time NCCL set-up (first collective after graph replays: ~10 ms,
+      epoch_end()                    # measured) happens here, not in the timed region
+      step()
+      flush.zero_()
   counter[0] = 0
   torch.cuda.synchronize()
   if world > 1:
@@ -256,6 +260,11 @@ def run_ours(args, rank, world, local_rank):
   clocks = clock.stop() if clock else None
   n_launch = launches[0]
   t_step = np.array([m[0].elapsed_time(m[1]) for m in marks]) * 1e-3
+  if os.environ.get('CGSVMC_BENCH_DEBUG'):
+    order = np.argsort(t_step)[::-1][:8]
+    sys.stderr.write('rank %d: step time median %.1f us, max %.1f us; slowest steps %s\n' % (
+        rank, np.median(t_step) * 1e6, t_step.max() * 1e6,
+        [(int(i), round(float(t_step[i]) * 1e6, 1)) for i in order]))
   # per-phase device times (kernel shares, roofline kernel time): the same step
   # launched kernel by kernel with events between the phases, outside the timed region
   phase = [[ev() for _ in range(5)] for _ in range(20)]
