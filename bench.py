@@ -238,14 +238,16 @@ def run_ours(args, rank, world, local_rank):
       step()
       flush.zero_()
   counter[0] = 0
+  # NVML start-up (milliseconds, rank 0 only) before the barrier: a rank that
+  # enters the timed loop late makes the others wait in the first all-reduce
+  clock = ClockSampler(local_rank) if rank == 0 else None
+  launches[0] = 0
+  marks = [[ev(), ev()] for _ in range(args.steps)]
   torch.cuda.synchronize()
   if world > 1:
     dist.barrier()
 
   # ---- timed region: K steps, device-resident inputs -----------------------
-  clock = ClockSampler(local_rank) if rank == 0 else None
-  launches[0] = 0
-  marks = [[ev(), ev()] for _ in range(args.steps)]
   torch.cuda.synchronize()
   wall0 = time.perf_counter()
   for k in range(args.steps):
