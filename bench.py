@@ -298,8 +298,12 @@ def run_ours(args, rank, world, local_rank):
       fed.submit(host_cfg)
       if fed.outstanding() > 1:
         fed.result()                                              # host consumes the energy of step k - 1
-      if (k + 1) % EPOCH_BATCHES == 0:
-        fed.fetch_sums()                                          # epoch end: the [2, P] gradient sums
+      if (k + 1) % EPOCH_BATCHES == 0:                            # epoch end: the [2, P] gradient sums
+        if world > 1:                                             # (all-reduced over the walker shards first)
+          payload[:2 * P].copy_(sums.sums.reshape(-1))
+          payload[2 * P:].copy_(sums.stats.float())
+          dist.all_reduce(payload)
+        fed.fetch_sums()
         sums.reset()
     while fed.outstanding():
       fed.result()

@@ -34,6 +34,8 @@ struct NetDesc {
   const float* wt[kMaxLayers + 2];  // transposed weights (grad only)
   int64_t w_off[kMaxLayers + 2], b_off[kMaxLayers + 2];   // flat offsets (grad)
   const float* rbm_a; const float* rbm_a0;                // rbm onsite
+  int stage_weights;          // mlp forward: copy each layer's weights into shared memory first
+  int resident_weights;       // mlp forward: ALL layers fit: copied once per kernel (prepare())
 };
 
 __device__ __forceinline__ float activate(int act, float x) {
@@ -82,8 +84,53 @@ struct Mlp {
     const int dmax = d.D > d.N ? d.D : d.N;
     return (size_t)dmax * TS;
   }
+  // one layer's weight matrix [din][dout] staged in shared memory (forward of
+  // the non-gradient kernels): the 8 warps of the CTA would otherwise each
+  // stream it through L1 (ncu, C1: long-scoreboard stalls 6.3 per issue)
+  __host__ __device__ static size_t resident_floats(const NetDesc& d) {
+    // layers 0 .. L-1 (and the rbm head matrix): [N][D], then [D][D] each
+    const int n_mat = d.L + (d.kind == CGSVMC_ANSATZ_RBM ? 1 : 0);
+    if (n_mat == 0) return 0;
+    return ((size_t)d.N * d.D + (size_t)(n_mat - 1) * d.D * d.D + 3) / 4 * 4;
+  }
+  __host__ __device__ static size_t stage_floats(const NetDesc& d) {
+    if (d.resident_weights) return resident_floats(d);
+    if (!d.stage_weights || TW < 4) return 0;      // small tiles: the copy would outweigh the layer
+    const int dmax = d.D > d.N ? d.D : d.N;
+    return ((size_t)dmax * d.D + 3) / 4 * 4;
+  }
+  // offset of matrix l inside the resident copy
+  __host__ __device__ static size_t resident_offset(const NetDesc& d, int l) {
+    return l == 0 ? 0 : (size_t)d.N * d.D + (size_t)(l - 1) * d.D * d.D;
+  }
+  // once per kernel, all threads: every weight matrix into shared memory
+  __device__ static void prepare(const NetDesc& d, float* smem) {
+    if (!d.resident_weights) return;
+    float* wall = smem + 2 * act_floats(d);
+    const int n_mat = d.L + (d.kind == CGSVMC_ANSATZ_RBM ? 1 : 0);
+    for (int l = 0; l < n_mat; ++l) {
+      const int n = (l == 0 ? d.N : d.D) * d.D;
+      float* dst = wall + resident_offset(d, l);
+      for (int e = threadIdx.x; e < n; e += kThreads) dst[e] = __ldg(d.w[l] + e);
+    }
+    __syncthreads();
+  }
   __host__ static size_t forward_smem_bytes(const NetDesc& d) {
-    return (2 * act_floats(d) + T) * sizeof(float);
+    return (2 * act_floats(d) + T + stage_floats(d)) * sizeof(float);
+  }
+  // CTA-wide copy of W[din * dout] into `wbuf` (all threads call)
+  __device__ static const float* stage(const float* __restrict__ W, int din, int dout, float* wbuf) {
+    if (wbuf == nullptr) return W;
+    __syncthreads();                       // the previous layer may still read wbuf
+    const int n = din * dout;
+    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+      for (int e = threadIdx.x; e < n / 4; e += kThreads)
+        reinterpret_cast<float4*>(wbuf)[e] = __ldg(reinterpret_cast<const float4*>(W) + e);
+    } else {
+      for (int e = threadIdx.x; e < n; e += kThreads) wbuf[e] = __ldg(W + e);
+    }
+    __syncthreads();
+    return wbuf;
   }
 
   // spins of T configurations -> buf[i][t] = +-1
@@ -100,7 +147,9 @@ struct Mlp {
   // MODE 3: rbm head for the gradient, store tanh(pre) = d z / d theta;
   // MODE 4: backward-data with transposed weights, no bias, the result is
   //         multiplied by act'(.) evaluated from the stored output `aux`.
-  template <int MODE>
+  // STAGED: W points into shared memory (see stage()); otherwise the weights
+  // are read through the read-only global path.
+  template <int MODE, bool STAGED = false>
   __device__ static void layer(const NetDesc& d, const float* __restrict__ W,
                                const float* __restrict__ bias, int din, int dout, int act,
                                const float* in, float* out, float* zacc,
@@ -130,7 +179,7 @@ struct Mlp {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int j = jbase + 32 * k;
-          const float wv = j < dout ? __ldg(wrow + j) : 0.f;
+          const float wv = j < dout ? (STAGED ? wrow[j] : __ldg(wrow + j)) : 0.f;
 #pragma unroll
           for (int t = 0; t < TW; ++t) acc[t][k] = fmaf(hv[t], wv, acc[t][k]);
         }
@@ -191,16 +240,28 @@ struct Mlp {
     if (rbm) dot_head(d.rbm_a, d.rbm_a0, d.N, buf0, z, false);   // onsite term
     float* in = buf0;
     float* out = buf1;
+    float* wbuf = stage_floats(d) != 0 ? smem + 2 * act_floats(d) : nullptr;
+    const bool resident = d.resident_weights != 0;     // copied by prepare()
     int din = d.N;
     for (int l = 0; l < d.L; ++l) {
-      layer<0>(d, d.w[l], d.b[l], din, d.D, d.act, in, out, nullptr);
+      if (resident)
+        layer<0, true>(d, wbuf + resident_offset(d, l), d.b[l], din, d.D, d.act, in, out, nullptr);
+      else if (wbuf != nullptr)
+        layer<0, true>(d, stage(d.w[l], din, d.D, wbuf), d.b[l], din, d.D, d.act, in, out, nullptr);
+      else
+        layer<0>(d, d.w[l], d.b[l], din, d.D, d.act, in, out, nullptr);
       __syncthreads();
       float* tmp = in; in = out; out = tmp;
       din = d.D;
     }
     if (rbm) {
       __syncwarp();
-      layer<1>(d, d.w[d.L], d.b[d.L], din, d.D, 0, in, nullptr, z);
+      if (resident)
+        layer<1, true>(d, wbuf + resident_offset(d, d.L), d.b[d.L], din, d.D, 0, in, nullptr, z);
+      else if (wbuf != nullptr)
+        layer<1, true>(d, stage(d.w[d.L], din, d.D, wbuf), d.b[d.L], din, d.D, 0, in, nullptr, z);
+      else
+        layer<1>(d, d.w[d.L], d.b[d.L], din, d.D, 0, in, nullptr, z);
     } else {
       dot_head(d.w[d.L], d.b[d.L], din, in, z, false);
     }
@@ -360,12 +421,14 @@ struct MlpNet {
   __device__ static void forward(const NetDesc& d, const uint64_t* cfg, int, float* smem, float* z) {
     Mlp<TW>::forward(d, cfg, smem, z);
   }
+  __device__ static void prepare(const NetDesc& d, float* smem) { Mlp<TW>::prepare(d, smem); }
 };
 struct ConvNet {
   __host__ static size_t fwd_smem(const NetDesc& d, int T) { return Conv::forward_smem_bytes(d, T); }
   __device__ static void forward(const NetDesc& d, const uint64_t* cfg, int T, float* smem, float* z) {
     Conv::forward(d, cfg, T, smem, z);
   }
+  __device__ static void prepare(const NetDesc&, float*) {}
 };
 
 // Dynamic shared memory layout of the non-grad kernels:
@@ -396,6 +459,7 @@ __global__ void __launch_bounds__(kThreads)
 net_log_amp_kernel(NetDesc d, int T, size_t fwd_bytes, const uint64_t* __restrict__ packed,
                    int64_t B, float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
+  NET::prepare(d, smem);
   Carver carve(smem, fwd_bytes);
   uint64_t* cfg = carve.take<uint64_t>((size_t)T * d.NW);
   float* z = carve.take<float>(T);
@@ -434,6 +498,7 @@ net_mc_kernel(NetDesc d, int T, size_t fwd_bytes, uint64_t* __restrict__ packed,
               float* __restrict__ log_amp_out) {
   if (step0_dev != nullptr) step0 += *step0_dev;
   extern __shared__ __align__(16) float smem[];
+  NET::prepare(d, smem);
   Carver carve(smem, fwd_bytes);
   uint64_t* prop = carve.take<uint64_t>((size_t)T * d.NW);   // proposed configs [T][NW]
   uint64_t* cur = carve.take<uint64_t>((size_t)T * d.NW);    // current configs [T][NW]
@@ -510,6 +575,7 @@ net_replay_kernel(NetDesc d, int T, size_t fwd_bytes, uint64_t* __restrict__ pac
                   const float* __restrict__ u_sites, const float* __restrict__ u_acc,
                   int32_t* down_out, int32_t* up_out, float* log_ratio_out, uint8_t* accept_out) {
   extern __shared__ __align__(16) float smem[];
+  NET::prepare(d, smem);
   Carver carve(smem, fwd_bytes);
   uint64_t* prop = carve.take<uint64_t>((size_t)T * d.NW);
   uint64_t* cur = carve.take<uint64_t>((size_t)T * d.NW);
@@ -585,6 +651,7 @@ net_eloc_kernel(NetDesc d, int T, size_t fwd_bytes, const int2* __restrict__ bon
                 float* __restrict__ e_loc, float* __restrict__ log_amp_out,
                 float* __restrict__ diag_out, float* __restrict__ off_out) {
   extern __shared__ __align__(16) float smem[];
+  NET::prepare(d, smem);
   const int max_items = kElocWalkers * (n_bonds + 1);
   Carver carve(smem, fwd_bytes);
   uint64_t* cfg = carve.take<uint64_t>((size_t)T * d.NW);               // tile configs [T][NW]
@@ -968,6 +1035,15 @@ int build_desc(const cgsvmc_ansatz* a, NetDesc* d) {
   }
   if (s.kind == CGSVMC_ANSATZ_FULLY_CONNECTED || s.kind == CGSVMC_ANSATZ_RBM) {
     d->D = s.layer_size;
+    // forward kernels stage one layer's weights in shared memory when they fit 64 KB
+    d->stage_weights = (size_t)std::max(s.layer_size, s.n_sites) * s.layer_size * sizeof(float) <= 64 * 1024 &&
+                       (s.num_layers > 0 || s.kind == CGSVMC_ANSATZ_RBM);
+    {   // all matrices resident when they fit 96 KB (C1: 59 KB)
+      const int n_mat = s.num_layers + (s.kind == CGSVMC_ANSATZ_RBM ? 1 : 0);
+      const size_t all = n_mat == 0 ? 0 : ((size_t)s.n_sites * s.layer_size +
+                                           (size_t)(n_mat - 1) * s.layer_size * s.layer_size) * sizeof(float);
+      d->resident_weights = n_mat > 0 && all <= 96 * 1024;
+    }
     for (int l = 0; l <= s.num_layers; ++l) {
       d->w[l] = p + a->offsets[idx]; d->w_off[l] = a->offsets[idx]; ++idx;
       d->b[l] = p + a->offsets[idx]; d->b_off[l] = a->offsets[idx]; ++idx;
