@@ -15,9 +15,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('CGSVMC_LIBRARY') or os.path.join(_HERE, 'libcgsvmc.so')
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
-ANSATZ_KINDS = {'fully_connected': 1, 'rbm': 2, 'conv_1d': 3, 'conv_2d': 4}
+ANSATZ_KINDS = {'fully_connected': 1, 'rbm': 2, 'conv_1d': 3, 'conv_2d': 4,
+                'res_net_1d': 5, 'res_net_2d': 6}
 ACTIVATIONS = {'relu': 0, 'tanh': 1, 'sigmoid': 2, 'identity': 3, 'cos': 4,
-               'exp': 5, 'tan': 6}
+               'exp': 5, 'tan': 6, 'selu': 7}
 
 EXPORTS = [
     'cgsvmc_version', 'cgsvmc_last_error', 'cgsvmc_ansatz_create',

@@ -80,6 +80,19 @@ bool layout(const cgsvmc_ansatz_desc& d, std::vector<int64_t>* sizes) {
       }
       return true;
     }
+    case CGSVMC_ANSATZ_RESNET_1D:
+    case CGSVMC_ANSATZ_RESNET_2D: {
+      const int64_t taps = d.kind == CGSVMC_ANSATZ_RESNET_1D ? d.kernel_size
+                                                             : (int64_t)d.kernel_size * d.kernel_size;
+      const int64_t f = d.num_filters;
+      sizes->push_back(taps * f);
+      sizes->push_back(f);
+      for (int l = 0; l < 2 * d.num_layers; ++l) {
+        sizes->push_back(taps * f * f);
+        sizes->push_back(f);
+      }
+      return true;
+    }
     default:
       return false;
   }
@@ -116,10 +129,13 @@ int cgsvmc_ansatz_create(const cgsvmc_ansatz_desc* desc, cgsvmc_ansatz** out) {
   } else {
     if (d.num_layers < 1 || d.num_filters < 1 || d.kernel_size < 1)
       return invalid("ansatz_create: conv needs num_layers, num_filters, kernel_size >= 1");
-    if (d.kind == CGSVMC_ANSATZ_CONV_2D && (int64_t)d.size_x * d.size_y != d.n_sites)
+    if ((d.kind == CGSVMC_ANSATZ_CONV_2D || d.kind == CGSVMC_ANSATZ_RESNET_2D) &&
+        (int64_t)d.size_x * d.size_y != d.n_sites)
       return invalid("ansatz_create: size_x * size_y must equal n_sites");
+    if ((d.kind == CGSVMC_ANSATZ_RESNET_1D || d.kind == CGSVMC_ANSATZ_RESNET_2D) && d.num_layers > 7)
+      return invalid("ansatz_create: at most 7 residual blocks");
   }
-  if (d.nonlinearity < CGSVMC_ACT_RELU || d.nonlinearity > CGSVMC_ACT_TAN)
+  if (d.nonlinearity < CGSVMC_ACT_RELU || d.nonlinearity > CGSVMC_ACT_SELU)
     return invalid("ansatz_create: unknown nonlinearity");
   cgsvmc_ansatz* a = new (std::nothrow) cgsvmc_ansatz();
   if (a == nullptr) return invalid("ansatz_create: out of host memory");

@@ -34,6 +34,7 @@ struct NetDesc {
   const float* wt[kMaxLayers + 2];  // transposed weights (grad only)
   int64_t w_off[kMaxLayers + 2], b_off[kMaxLayers + 2];   // flat offsets (grad)
   const float* rbm_a; const float* rbm_a0;                // rbm onsite
+  int resnet;                 // conv family: layer 0 plain, then (selu conv, conv + skip) blocks
   int stage_weights;          // mlp forward: copy each layer's weights into shared memory first
   int resident_weights;       // mlp forward: ALL layers fit: copied once per kernel (prepare())
 };
@@ -46,6 +47,8 @@ __device__ __forceinline__ float activate(int act, float x) {
     case CGSVMC_ACT_IDENTITY: return x;
     case CGSVMC_ACT_COS: return cosf(x);
     case CGSVMC_ACT_EXP: return expf(x);
+    case CGSVMC_ACT_SELU:   // tf.nn.selu: scale * (x > 0 ? x : alpha * (exp(x) - 1))
+      return x > 0.f ? 1.0507009873554805f * x : 1.7580993408473766f * (expf(x) - 1.f);
     default: return tanf(x);
   }
 }
@@ -58,6 +61,7 @@ __device__ __forceinline__ float activate_grad(int act, float h) {
     case CGSVMC_ACT_TANH: return 1.f - h * h;
     case CGSVMC_ACT_SIGMOID: return h * (1.f - h);
     case CGSVMC_ACT_IDENTITY: return 1.f;
+    case CGSVMC_ACT_SELU: return h < 0.f ? h + 1.7580993408473766f : 1.0507009873554805f;
     case CGSVMC_ACT_EXP: return h;
     default: return 1.f + h * h;   // tan
   }
@@ -305,11 +309,16 @@ struct Conv {
   // forward pass): no store, z[t] += sum of outputs.  MODE 2: backward-data,
   // flipped taps (weights must be the [tap][cout][cin] transpose), post =
   // multiply with activate_grad(h_prev) read from `aux`.
+  // `res` (MODE 0 and 2): tensor of the output's shape added to the result --
+  // the skip connection of a residual block (may alias `out`: every element is
+  // read and written by the same thread).  MODE 2 with aux == nullptr skips
+  // the activation-gradient factor.
   template <int MODE>
   __device__ static void layer(const NetDesc& d, const float* __restrict__ W,
                                const float* __restrict__ bias, int cin, int cout, int act,
                                bool apply_act, int T, const float* in, float* out, float* z,
-                               const int* xi, const int* yi, const float* aux) {
+                               const int* xi, const int* yi, const float* aux,
+                               const float* res = nullptr) {
     const int npos = d.N;
     const int taps = d.kx * d.ky;
     for (int item = threadIdx.x; item < T * npos; item += kThreads) {
@@ -356,9 +365,12 @@ struct Conv {
               zsum += v;
             } else if (MODE == 2) {
               const size_t o = ((size_t)t * cout + c0 + c) * npos + pos;
-              out[o] = v * activate_grad(act, aux[o]);
+              if (aux != nullptr) v *= activate_grad(act, aux[o]);
+              out[o] = res != nullptr ? v + res[o] : v;
             } else {
-              out[((size_t)t * cout + c0 + c) * npos + pos] = apply_act ? activate(act, v) : v;
+              const size_t o = ((size_t)t * cout + c0 + c) * npos + pos;
+              if (apply_act) v = activate(act, v);
+              out[o] = res != nullptr ? v + res[o] : v;
             }
           }
         }
@@ -395,6 +407,31 @@ struct Conv {
     build_tables(d, xi, yi, false);
     load_spins(d, cfg, T, buf0);
     __syncthreads();
+    if (d.resnet) {
+      // x = conv0(sigma) in buf1; per block h = selu(conv1(x)) in buf0, then
+      // x += conv2(h) in place (wavefunctions.py:651-671, layers.py:203-228)
+      float* x = buf1;
+      float* h = buf0;
+      layer<0>(d, d.w[0], d.b[0], 1, d.C, d.act, false, T, buf0, x, z, xi, yi, nullptr);
+      __syncthreads();
+      for (int l = 1; l < d.L; l += 2) {
+        layer<0>(d, d.w[l], d.b[l], d.C, d.C, d.act, true, T, x, h, z, xi, yi, nullptr);
+        __syncthreads();
+        layer<0>(d, d.w[l + 1], d.b[l + 1], d.C, d.C, d.act, false, T, h, x, z, xi, yi, nullptr, x);
+        __syncthreads();
+      }
+      // per-position channel sums (into h, free now), then the fixed-order reduction
+      for (int item = threadIdx.x; item < T * d.N; item += kThreads) {
+        const int t = item / d.N, pos = item - t * d.N;
+        float sum = 0.f;
+        for (int c = 0; c < d.C; ++c) sum += x[((size_t)t * d.C + c) * d.N + pos];
+        h[item] = sum;
+      }
+      __syncthreads();
+      reduce_z(d, T, h, z);
+      __syncthreads();
+      return;
+    }
     float* in = buf0;
     float* out = buf1;
     int cin = 1;
@@ -953,6 +990,35 @@ conv_grad_kernel(NetDesc d, int T, const uint64_t* __restrict__ packed,
     __syncthreads();
     Conv::load_spins(d, cfg, T, H0);
     __syncthreads();
+    float* top = DL + (size_t)(L - 1) * szC;
+    if (d.resnet) {
+      // H(l) = input of conv l: H(1) = x_0 = conv0(sigma); block b (convs 2b+1,
+      // 2b+2): H(2b+2) = h_b = selu(conv(x_b)), H(2b+3) = x_{b+1} = x_b + conv(h_b)
+      // (the last x is not needed: z is its sum, so its delta is 1).
+      Conv::layer<0>(d, d.w[0], d.b[0], 1, C, d.act, false, T, H(0), H(1), nullptr, xi, yi, nullptr);
+      __syncthreads();
+      for (int l = 1; l < L; l += 2) {
+        Conv::layer<0>(d, d.w[l], d.b[l], C, C, d.act, true, T, H(l), H(l + 1), nullptr, xi, yi, nullptr);
+        __syncthreads();
+        if (l + 2 < L) {
+          Conv::layer<0>(d, d.w[l + 1], d.b[l + 1], C, C, d.act, false, T, H(l + 1), H(l + 2), nullptr,
+                         xi, yi, nullptr, H(l));
+          __syncthreads();
+        }
+      }
+      // DL[l] = delta at the output of conv l: DL[2b+2] = delta x_{b+1},
+      // DL[2b+1] = conv_{2b+2}^T(DL[2b+2]) * selu'(h_b), DL[2b] = DL[2b+2] + conv_{2b+1}^T(DL[2b+1])
+      for (size_t e = threadIdx.x; e < szC; e += kThreads) top[e] = 1.f;
+      __syncthreads();
+      for (int l = L - 1; l >= 2; l -= 2) {
+        Conv::layer<2>(d, d.wt[l], nullptr, C, C, d.act, false, T, DL + (size_t)l * szC,
+                       DL + (size_t)(l - 1) * szC, nullptr, xib, yib, H(l));
+        __syncthreads();
+        Conv::layer<2>(d, d.wt[l - 1], nullptr, C, C, d.act, false, T, DL + (size_t)(l - 1) * szC,
+                       DL + (size_t)(l - 2) * szC, nullptr, xib, yib, nullptr, DL + (size_t)l * szC);
+        __syncthreads();
+      }
+    } else {
     // forward up to the input of the last layer (its output is not needed)
     int cin = 1;
     for (int l = 0; l + 1 < L; ++l) {
@@ -961,13 +1027,13 @@ conv_grad_kernel(NetDesc d, int T, const uint64_t* __restrict__ packed,
       cin = C;
     }
     // backward: z = sum of the last layer's outputs => its delta is 1
-    float* top = DL + (size_t)(L - 1) * szC;
     for (size_t e = threadIdx.x; e < szC; e += kThreads) top[e] = 1.f;
     __syncthreads();
     for (int l = L - 1; l >= 1; --l) {
       Conv::layer<2>(d, d.wt[l], nullptr, C, C, d.act, false, T, DL + (size_t)l * szC,
                      DL + (size_t)(l - 1) * szC, nullptr, xib, yib, H(l));
       __syncthreads();
+    }
     }
     // accumulate
 #pragma unroll 1
@@ -1050,7 +1116,12 @@ int build_desc(const cgsvmc_ansatz* a, NetDesc* d) {
     }
   } else {
     d->C = s.num_filters;
-    if (s.kind == CGSVMC_ANSATZ_CONV_1D) {
+    if (s.kind == CGSVMC_ANSATZ_RESNET_1D || s.kind == CGSVMC_ANSATZ_RESNET_2D) {
+      d->resnet = 1;
+      d->L = 1 + 2 * s.num_layers;        // initial conv + two convs per block
+      d->act = CGSVMC_ACT_SELU;
+    }
+    if (s.kind == CGSVMC_ANSATZ_CONV_1D || s.kind == CGSVMC_ANSATZ_RESNET_1D) {
       d->X = s.n_sites; d->Y = 1; d->kx = s.kernel_size; d->ky = 1;
       d->pad_x = s.kernel_size % 2 ? (s.kernel_size - 1) / 2 : s.kernel_size / 2;   // layers.py:64-73
       d->pad_y = 0;
@@ -1058,7 +1129,7 @@ int build_desc(const cgsvmc_ansatz* a, NetDesc* d) {
       d->X = s.size_x; d->Y = s.size_y; d->kx = d->ky = s.kernel_size;
       d->pad_x = d->pad_y = s.kernel_size % 2 ? (s.kernel_size - 1) / 2 : s.kernel_size / 2 - 1;   // layers.py:132-141
     }
-    for (int l = 0; l < s.num_layers; ++l) {
+    for (int l = 0; l < d->L; ++l) {
       d->w[l] = p + a->offsets[2 * l]; d->w_off[l] = a->offsets[2 * l];
       d->b[l] = p + a->offsets[2 * l + 1]; d->b_off[l] = a->offsets[2 * l + 1];
     }
@@ -1066,7 +1137,10 @@ int build_desc(const cgsvmc_ansatz* a, NetDesc* d) {
   return CGSVMC_OK;
 }
 
-bool is_conv(const NetDesc& d) { return d.kind == CGSVMC_ANSATZ_CONV_1D || d.kind == CGSVMC_ANSATZ_CONV_2D; }
+bool is_conv(const NetDesc& d) {
+  return d.kind == CGSVMC_ANSATZ_CONV_1D || d.kind == CGSVMC_ANSATZ_CONV_2D ||
+         d.kind == CGSVMC_ANSATZ_RESNET_1D || d.kind == CGSVMC_ANSATZ_RESNET_2D;
+}
 
 template <typename F>
 int set_smem(F kernel, size_t bytes, const cgsvmc_ansatz* a) {

@@ -1,5 +1,6 @@
 """Mirror of the reference's wavefunctions.py for the in-scope ansaetze
-(fully_connected, rbm, conv_1d, conv_2d) on the CUDA library, including the
+(fully_connected, rbm, conv_1d, conv_2d, res_net_1d, res_net_2d) on the CUDA
+library, including the
 signed output activations (layers.py:13-21) and the sum / difference / product
 composites (wavefunctions.py:61-165, 1178-1194).
 
@@ -24,8 +25,7 @@ import torch
 from . import _native, layers
 from .session import Op
 
-_UNBUILT = ('res_net_1d', 'res_net_2d', 'mps', 'pbdg', 'fully_connected_nnb',
-            'ed_vector', 'gnn')
+_UNBUILT = ('mps', 'pbdg', 'fully_connected_nnb', 'ed_vector', 'gnn')
 
 
 def _sonnet_init(shapes, generator):
@@ -550,6 +550,82 @@ class Conv2DNetwork(_ExpAnsatz):
     return cls(**params)
 
 
+class ResNet1D(_ExpAnsatz):
+  """wavefunctions.py:617-711: initial periodic convolution, num_blocks
+  residual blocks x + conv(selu(conv(x))) (layers.py:231-296), sum."""
+  _kind = 'res_net_1d'
+
+  def __init__(self, num_blocks, num_filters, kernel_size, conv_stride=1, bottleneck=False,
+               output_activation='exp', name='res_net_1d'):
+    super().__init__(name=name)
+    _check_exp(output_activation)
+    if bottleneck:
+      raise NotImplementedError('BottleneckResBlock1d raises AttributeError in the reference itself '
+                                '(undefined self._output_channels, layers.py:348)')
+    if conv_stride != 1:
+      raise NotImplementedError('residual blocks are built for stride 1 (the skip connection '
+                                'requires it, layers.py:216-218)')
+    self._num_blocks, self._num_filters, self._kernel_size = num_blocks, num_filters, kernel_size
+    self._conv_stride, self._bottleneck, self._output_activation = conv_stride, bottleneck, output_activation
+    self._init_args = dict(num_blocks=num_blocks, num_filters=num_filters, kernel_size=kernel_size,
+                           conv_stride=conv_stride, bottleneck=bottleneck,
+                           output_activation=output_activation)
+
+  def _native_args(self, n):
+    return dict(kind=self._kind, n_sites=n, num_layers=self._num_blocks,
+                num_filters=self._num_filters, kernel_size=self._kernel_size, nonlinearity='selu')
+
+  def _spatial(self):
+    return (self._kernel_size,)
+
+  def _param_shapes(self, n):
+    sp, f = self._spatial(), self._num_filters
+    shapes = [sp + (1, f), (f,)]
+    for _ in range(self._num_blocks):
+      shapes += [sp + (f, f), (f,), sp + (f, f), (f,)]
+    return shapes
+
+  @classmethod
+  def from_hparams(cls, hparams, name=''):
+    params = dict(num_blocks=hparams.num_resnet_blocks, num_filters=hparams.num_conv_filters,
+                  kernel_size=hparams.kernel_size, conv_stride=hparams.conv_strides,
+                  output_activation=layers.NONLINEARITIES[hparams.output_activation])
+    if name:
+      params['name'] = name
+    wf = cls(**params)
+    wf._n_sites = hparams.num_sites
+    return wf
+
+
+class ResNet2D(ResNet1D):
+  """wavefunctions.py:713-809."""
+  _kind = 'res_net_2d'
+
+  def __init__(self, num_blocks, num_filters, kernel_size, conv_stride, size_x, size_y,
+               bottleneck=False, output_activation='exp', name='res_net_2d'):
+    super().__init__(num_blocks, num_filters, kernel_size, conv_stride, bottleneck,
+                     output_activation, name=name)
+    self._size_x, self._size_y = size_x, size_y
+    self._n_sites = size_x * size_y
+    self._init_args.update(size_x=size_x, size_y=size_y)
+
+  def _native_args(self, n):
+    return dict(super()._native_args(n), size_x=self._size_x, size_y=self._size_y)
+
+  def _spatial(self):
+    return (self._kernel_size, self._kernel_size)
+
+  @classmethod
+  def from_hparams(cls, hparams, name=''):
+    params = dict(num_blocks=hparams.num_resnet_blocks, num_filters=hparams.num_conv_filters,
+                  kernel_size=hparams.kernel_size, conv_stride=hparams.conv_strides,
+                  size_x=hparams.size_x, size_y=hparams.size_y,
+                  output_activation=layers.NONLINEARITIES[hparams.output_activation])
+    if name:
+      params['name'] = name
+    return cls(**params)
+
+
 def build_wavefunction(hparams):
   """wavefunctions.py:1157-1196."""
   wavefunction_type = hparams.wavefunction_type
@@ -582,4 +658,6 @@ WAVEFUNCTION_TYPES = {
     'rbm': RestrictedBoltzmannNetwork,
     'conv_1d': Conv1DNetwork,
     'conv_2d': Conv2DNetwork,
+    'res_net_1d': ResNet1D,
+    'res_net_2d': ResNet2D,
 }

@@ -57,6 +57,14 @@ extern "C" {
 #define CGSVMC_ANSATZ_RBM 2
 #define CGSVMC_ANSATZ_CONV_1D 3
 #define CGSVMC_ANSATZ_CONV_2D 4
+/* ResNet1D / ResNet2D (wavefunctions.py:617-809): an initial periodic
+ * convolution 1 -> F without nonlinearity, num_layers (= num_resnet_blocks)
+ * residual blocks x <- x + conv2(selu(conv1(x))) (layers.py:163-296), then the
+ * sum over sites and channels.  Flat layout: initial w, b; per block
+ * first_conv w, b, second_conv w, b (Sonnet creation order).  `nonlinearity`
+ * is ignored (selu is fixed in the blocks). */
+#define CGSVMC_ANSATZ_RESNET_1D 5
+#define CGSVMC_ANSATZ_RESNET_2D 6
 
 /* layers.NONLINEARITIES keys (layers.py:13-21) */
 #define CGSVMC_ACT_RELU 0
@@ -66,6 +74,7 @@ extern "C" {
 #define CGSVMC_ACT_COS 4
 #define CGSVMC_ACT_EXP 5
 #define CGSVMC_ACT_TAN 6
+#define CGSVMC_ACT_SELU 7   /* internal: the ResNet blocks */
 
 typedef struct cgsvmc_ansatz cgsvmc_ansatz;
 typedef struct cgsvmc_ham cgsvmc_ham;

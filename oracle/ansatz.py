@@ -12,6 +12,8 @@ Flat parameter layout (shared with the CUDA library, include/cgsvmc.h):
                     W[in,H], c[H]
   conv_1d         : per layer w[k, cin, cout], b[cout]
   conv_2d         : per layer w[k, k, cin, cout], b[cout]
+  res_net_1d / 2d : initial conv w, b (1 -> F), then per block first_conv w, b
+                    and second_conv w, b (F -> F)
 Matrices are row-major with the Sonnet shapes (snt.Linear w:[in,out];
 snt.Conv w:[spatial..., in, out]).
 """
@@ -30,14 +32,15 @@ NONLINEARITIES = {   # layers.py:13-21
     'tanh': torch.tanh,
     'sigmoid': torch.sigmoid,
     'identity': lambda x: x,
+    'selu': torch.selu,      # fixed inside the ResNet blocks (layers.py:225, 293)
 }
 
 
 @dataclasses.dataclass
 class AnsatzSpec:
-  kind: str                 # 'fully_connected' | 'rbm' | 'conv_1d' | 'conv_2d'
+  kind: str                 # 'fully_connected' | 'rbm' | 'conv_1d' | 'conv_2d' | 'res_net_1d' | 'res_net_2d'
   n_sites: int
-  num_layers: int = 3       # num_fc_layers / num_conv_layers
+  num_layers: int = 3       # num_fc_layers / num_conv_layers / num_resnet_blocks
   layer_size: int = 80      # fc_layer_size
   num_filters: int = 16
   kernel_size: int = 5
@@ -46,8 +49,8 @@ class AnsatzSpec:
   nonlinearity: str = 'relu'
 
   def __post_init__(self):
-    if self.kind == 'conv_2d' and self.size_x * self.size_y != self.n_sites:
-      raise ValueError('size_x * size_y must equal n_sites for conv_2d')
+    if self.kind in ('conv_2d', 'res_net_2d') and self.size_x * self.size_y != self.n_sites:
+      raise ValueError('size_x * size_y must equal n_sites for %s' % self.kind)
 
 
 def param_shapes(spec: AnsatzSpec) -> List[Tuple[str, Tuple[int, ...]]]:
@@ -74,6 +77,14 @@ def param_shapes(spec: AnsatzSpec) -> List[Tuple[str, Tuple[int, ...]]]:
           (k, k, c_in, spec.num_filters)
       out += [('w%d' % l, shape), ('b%d' % l, (spec.num_filters,))]
       c_in = spec.num_filters
+  elif spec.kind in ('res_net_1d', 'res_net_2d'):   # wavefunctions.py:651-671, 753-769
+    # initial periodic conv (1 -> F), then num_layers ResBlocks of two F -> F convs
+    k, f = spec.kernel_size, spec.num_filters
+    sp = (k,) if spec.kind == 'res_net_1d' else (k, k)
+    out += [('w_init', sp + (1, f)), ('b_init', (f,))]
+    for l in range(spec.num_layers):
+      out += [('w%d_1' % l, sp + (f, f)), ('b%d_1' % l, (f,)),
+              ('w%d_2' % l, sp + (f, f)), ('b%d_2' % l, (f,))]
   else:
     raise ValueError('Provided wavefunction_type is not registered.')
   return out
@@ -194,6 +205,19 @@ def log_amp(spec: AnsatzSpec, params: List[torch.Tensor],
       if l + 1 != spec.num_layers:
         h = act(h)
     return h.sum(dim=(1, 2, 3))
+  if spec.kind in ('res_net_1d', 'res_net_2d'):
+    # initial conv without nonlinearity, then x <- x + conv2(selu(conv1(x)))
+    # per block (layers.py:203-228, 271-296), then the sum over sites and channels
+    one_d = spec.kind == 'res_net_1d'
+    pad = _pad_periodic_1d if one_d else _pad_periodic_2d
+    h = x.unsqueeze(2) if one_d else x.reshape(-1, spec.size_x, spec.size_y, 1)
+    k = spec.kernel_size
+    h = _conv_valid(pad(h, k), params[0], params[1])
+    for l in range(spec.num_layers):
+      w1, b1, w2, b2 = params[2 + 4 * l:6 + 4 * l]
+      r = torch.selu(_conv_valid(pad(h, k), w1, b1))
+      h = h + _conv_valid(pad(r, k), w2, b2)
+    return h.sum(dim=(1, 2) if one_d else (1, 2, 3))
   raise ValueError('Provided wavefunction_type is not registered.')
 
 

@@ -82,6 +82,11 @@ def spec_from_hparams(hp):
   if kind in ('fully_connected', 'rbm'):
     return oansatz.AnsatzSpec(kind, hp.num_sites, num_layers=hp.num_fc_layers,
                               layer_size=hp.fc_layer_size)
+  if kind in ('res_net_1d', 'res_net_2d'):
+    return oansatz.AnsatzSpec(kind, hp.num_sites, num_layers=hp.num_resnet_blocks,
+                              num_filters=hp.num_conv_filters,
+                              kernel_size=hp.kernel_size, size_x=hp.size_x,
+                              size_y=hp.size_y, nonlinearity='selu')
   return oansatz.AnsatzSpec(kind, hp.num_sites, num_layers=hp.num_conv_layers,
                             num_filters=hp.num_conv_filters,
                             kernel_size=hp.kernel_size, size_x=hp.size_x,
@@ -250,7 +255,29 @@ def make_case(name, overrides, lattice, seed):
   return out
 
 
+# Added after the first set was frozen (the reference's random_configurations
+# is unseeded, so regenerating would change the committed files): generated by
+# `python tests/golden/make_golden.py resnet` only.
+RESNET_CASES = {
+    'resnet1d_chain12_k3': (dict(wavefunction_type='res_net_1d', num_sites=12, num_resnet_blocks=2,
+                                 num_conv_filters=4, kernel_size=3), 'chain'),
+    'resnet1d_chain12_k4': (dict(wavefunction_type='res_net_1d', num_sites=12, num_resnet_blocks=1,
+                                 num_conv_filters=3, kernel_size=4), 'chain'),
+    'resnet2d_4x4_k3': (dict(wavefunction_type='res_net_2d', num_sites=16, size_x=4, size_y=4,
+                             num_resnet_blocks=2, num_conv_filters=4, kernel_size=3), 'square'),
+    'resnet2d_4x6_k2': (dict(wavefunction_type='res_net_2d', num_sites=24, size_x=4, size_y=6,
+                             num_resnet_blocks=1, num_conv_filters=3, kernel_size=2), 'rect'),
+}
+
+
 def main():
+  if len(sys.argv) > 1 and sys.argv[1] == 'resnet':
+    for k, (name, (overrides, lattice)) in enumerate(sorted(RESNET_CASES.items())):
+      out = make_case(name, overrides, lattice, seed=700 + k)
+      path = os.path.join(HERE, name + '.npz')
+      np.savez_compressed(path, **out)
+      print('%-22s %7.1f KB  keys=%d' % (name, os.path.getsize(path) / 1024.0, len(out)))
+    return
   for k, (name, (overrides, lattice)) in enumerate(sorted(CASES.items())):
     out = make_case(name, overrides, lattice, seed=100 + k)
     path = os.path.join(HERE, name + '.npz')

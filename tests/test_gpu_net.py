@@ -14,7 +14,9 @@ F64 = torch.float64
 
 NET_GOLDEN = ['fc_chain20', 'fc_chain8_small', 'rbm_chain12_hidden', 'conv1d_chain12_k3',
               'conv1d_chain12_k4', 'conv2d_6x6_k3', 'conv2d_4x4_k2', 'conv2d_4x6_k3',
-              'conv2d_10x10']
+              'conv2d_10x10',
+              # ResNet1D / ResNet2D (wavefunctions.py:617-809)
+              'resnet1d_chain12_k3', 'resnet1d_chain12_k4', 'resnet2d_4x4_k3', 'resnet2d_4x6_k2']
 
 NET_SHAPES = [
     oansatz.AnsatzSpec('fully_connected', 20, num_layers=3, layer_size=80),          # C1
@@ -312,4 +314,43 @@ def test_batch_step_generic_ansatz(native):
   assert torch.equal(s1.packed, s2.packed)
   assert torch.equal(sums1.sums, sums2.sums) and torch.equal(sums1.stats, sums2.stats)
   assert torch.equal(s1.accept_count, s2.accept_count)
+
+
+def test_resnet_through_the_reference_api(native):
+  """res_net_2d from hparams: amplitudes and local energy against the oracle,
+  gradient against autograd, and the sampler keeps Sz."""
+  from cgs_vmc_b200 import graph_builders, operators, utils, wavefunctions
+  from cgs_vmc_b200.session import Session
+  hp = utils.create_hparams(wavefunction_type='res_net_2d', num_sites=16, size_x=4, size_y=4,
+                            num_resnet_blocks=2, num_conv_filters=4, kernel_size=3, batch_size=64)
+  wf = wavefunctions.build_wavefunction(hp).seed(5)
+  assert type(wf).__name__ == 'ResNet2D' and wf.fast_path
+  spec = oansatz.AnsatzSpec('res_net_2d', 16, num_layers=2, num_filters=4, kernel_size=3,
+                            size_x=4, size_y=4, nonlinearity='selu')
+  a = wf.native(16)
+  assert a.num_params == oansatz.num_params(spec)
+  with torch.no_grad():
+    a.params.add_(0.05 * torch.randn(a.num_params, generator=torch.Generator().manual_seed(1)).cuda())
+  params = oansatz.unflatten(spec, a.params.detach().cpu().to(F64))
+  cfg = bits.random_sz0_configs(16, 64, np.random.default_rng(2))
+  cfg_t = torch.from_numpy(cfg).float().cuda()
+  z = wf.log_amplitude(cfg_t).cpu().numpy()
+  zo = (oansatz.log_amp(spec, params, torch.from_numpy(cfg).to(F64)) + 10.0).numpy()
+  np.testing.assert_allclose(z, zo, rtol=2e-5, atol=2e-4)
+  ij, jx, jz = lattices.j1j2_couplings(4, 0.5)
+  ham = operators.HeisenbergHamiltonian([tuple(b) for b in ij], jx, jz)
+  e = ham.local_value(wf, cfg_t).cpu().numpy()
+  eo = hamiltonian.local_energy(torch.from_numpy(cfg).to(F64), ij, jx, jz,
+                                lambda c: oansatz.log_amp(spec, params, c)).numpy()
+  np.testing.assert_allclose(e, eo, rtol=2e-4, atol=2e-3)
+  w = torch.randn(2, 64, generator=torch.Generator().manual_seed(3)).cuda()
+  got = a.weighted_grad_sum(graph_builders.as_packed(cfg_t, 16), w).cpu().numpy()
+  ref = estimators.weighted_grad_sum(spec, params, torch.from_numpy(cfg).to(F64), w.cpu().to(F64)).numpy()
+  np.testing.assert_allclose(got, ref, rtol=0, atol=2e-4 * np.abs(ref).max())
+  shared = {}
+  configs = graph_builders.get_configs(shared, 64, 16)
+  mc_step, acc = graph_builders.get_monte_carlo_sampling(shared, configs, wf)
+  s = Session()
+  s.run(mc_step, n_steps=32)
+  assert np.all(configs.value().cpu().numpy().sum(axis=1) == 0) and s.run(acc) > 0
 

@@ -56,7 +56,8 @@ def test_session_runs_ops_and_lists():
 
 
 def test_registries_and_error_types():
-  assert set(wavefunctions.WAVEFUNCTION_TYPES) == {'fully_connected', 'rbm', 'conv_1d', 'conv_2d'}
+  assert set(wavefunctions.WAVEFUNCTION_TYPES) == {'fully_connected', 'rbm', 'conv_1d', 'conv_2d',
+                                                   'res_net_1d', 'res_net_2d'}
   assert set(training.GROUND_STATE_OPTIMIZERS) == {'EnergyGradient', 'LogOverlapITSWO', 'ITSWO'}
   assert set(training.SUPERVISED_OPTIMIZERS) == {'SWO', 'LogOverlapSWO', 'DualSamplingSWO', 'BasisIterSWO'}
   with pytest.raises(ValueError, match='not registered'):          # wavefunctions.py:1196
