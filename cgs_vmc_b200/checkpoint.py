@@ -2,8 +2,8 @@
 (tf.train.Saver(wavefunction.get_trainable_variables(), max_to_keep=5),
 run_training.py:134-146).  Like the reference only the trainable variables are
 saved (not Adam slots, num_epochs, walkers); the
-exp_norm_shift is stored additionally because amplitudes here depend on it
-only through an irrelevant constant factor."""
+exp_norm_shift of every leaf is stored additionally (the reference loses it
+on restore, which changes a sum / difference of wavefunctions)."""
 import os
 
 import torch
@@ -19,7 +19,10 @@ class Saver:
     del session
     path = save_path + '.pt'
     variables = [v.detach().cpu().clone() for v in self._wf.get_trainable_variables()]
-    torch.save({'variables': variables, 'exp_norm_shift': self._wf._exp_norm_shift}, path)
+    # one shift per leaf: in a sum / difference the relative scale of the parts matters
+    shifts = [leaf._exp_norm_shift for leaf in self._wf.leaves()]
+    torch.save({'variables': variables, 'exp_norm_shift': self._wf._exp_norm_shift,
+                'leaf_exp_norm_shifts': shifts}, path)
     self._kept.append(path)
     while self._max_to_keep and len(self._kept) > self._max_to_keep:
       old = self._kept.pop(0)
@@ -41,6 +44,12 @@ class Saver:
       if tuple(dst.shape) != tuple(src.shape):
         raise ValueError('checkpoint variable shape %s != %s' % (tuple(src.shape), tuple(dst.shape)))
       dst.copy_(src.to(dst.device))
+    shifts = data.get('leaf_exp_norm_shifts')
+    leaves = self._wf.leaves()
+    if shifts is not None and len(shifts) == len(leaves):
+      for leaf, shift in zip(leaves, shifts):
+        if shift is not None:
+          leaf._exp_norm_shift = float(shift)
 
 
 def latest_checkpoint(checkpoint_dir):

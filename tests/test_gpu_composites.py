@@ -160,3 +160,24 @@ def test_composite_energy_training_lowers_energy():
   assert np.all(np.isfinite(energies))
   assert np.mean(energies[-5:]) < np.mean(energies[:5]) - 0.3, (energies[:5], energies[-5:])
   assert np.mean(energies[-5:]) > e0 - 0.2
+
+
+def test_checkpoint_roundtrip_of_a_composite(tmp_path):
+  """checkpoint.Saver over the leaves of a composite: variables and the
+  per-leaf exp_norm_shift survive, so psi is reproduced exactly."""
+  from cgs_vmc_b200 import checkpoint
+  wf, hp, kind, oleaves, g = _build('cmp_sum_rbm_fc_tanh')
+  cfg = torch.from_numpy(g['configs']).cuda()
+  psi = wf(cfg).clone()
+  saver = checkpoint.Saver(wf)
+  path = saver.save(None, str(tmp_path / 'model_prior_0_epochs'))
+  wf2, _, _, _, _ = _build('cmp_sum_rbm_fc_tanh')
+  for leaf in wf2.leaves():
+    with torch.no_grad():
+      leaf.native().params.mul_(0.5)
+    if leaf.fast_path:
+      leaf._exp_norm_shift = -10.0
+  assert not torch.allclose(wf2(cfg), psi)
+  checkpoint.Saver(wf2).restore(None, checkpoint.latest_checkpoint(str(tmp_path)))
+  assert path.endswith('.pt') and torch.equal(wf2(cfg), psi)
+
