@@ -186,9 +186,10 @@ class HostFedBatchStep(_CapturedStep):
   """The batch step for a caller that keeps the reference's float32 [B, N]
   configuration tensor in HOST memory (graph_builders.py:92-125 viewed from
   outside the session): every submit() uploads one pinned host batch on a copy
-  stream (double-buffered, so the upload of batch k overlaps the compute of
-  batch k - 1), then replays one captured graph per buffer slot --
-  cgsvmc_pack_configs, the batch step, and the device->host copy of the step's
+  stream and bit-packs it there (cgsvmc_pack_configs; double-buffered, so
+  upload and packing of batch k overlap the compute of batch k - 1), then
+  replays one captured graph per buffer slot -- the batch step on the slot's
+  walker buffer and the device->host copy of the step's
   result, the energy statistics (sum E, sum E^2, n: the metric the reference
   reads back, training.py:619-620), into pinned host memory.  result() blocks
   until the oldest outstanding batch has landed.  The [2, P] gradient sums are
@@ -212,14 +213,24 @@ class HostFedBatchStep(_CapturedStep):
     self._collected = 0
     for c in self.dev_cfg:
       c.copy_(state.configs())
+    # one walker buffer per slot: the upload AND the packing of batch k run on the
+    # copy stream while batch k - 1 computes; the graphs step the slot's buffer
+    # (after a submit `state.packed` is rebound to the buffer just stepped)
+    import types
+    self.slot_packed = [state.packed.clone() for _ in range(2)]
+    self.slot_state = [types.SimpleNamespace(
+        packed=self.slot_packed[i], seed=state.seed, walker_id0=state.walker_id0,
+        step_dev=state.step_dev, accept_count=state.accept_count, batch_size=B, n_sites=N)
+        for i in range(2)]
     self._prepare(state, ansatz, ham, sums, n_steps, (0, 1))
+    for p in self.slot_packed:               # the warm-up stepped slot 0
+      p.copy_(state.packed)
     main = torch.cuda.current_stream()
     for ev in self.consumed:
       ev.record(main)
 
   def _body(self, slot):
-    _native.pack_configs(self.dev_cfg[slot], out=self.state.packed)
-    self.sums.batch_step(self.ham, self.state, self.n_steps, on_device_counter=True)
+    self.sums.batch_step(self.ham, self.slot_state[slot], self.n_steps, on_device_counter=True)
     self.host_stats[slot].copy_(self.sums.stats, non_blocking=True)
 
   def submit(self, host_configs):
@@ -229,10 +240,12 @@ class HostFedBatchStep(_CapturedStep):
     with torch.cuda.stream(self.copy_stream):
       self.copy_stream.wait_event(self.consumed[slot])
       self.dev_cfg[slot].copy_(host_configs, non_blocking=True)
+      _native.pack_configs(self.dev_cfg[slot], out=self.slot_packed[slot])
       self.uploaded[slot].record(self.copy_stream)
     main.wait_event(self.uploaded[slot])
     self._replay(slot)
-    self.consumed[slot].record(main)      # the packed copy is taken: the slot may be refilled
+    self.state.packed = self.slot_packed[slot]
+    self.consumed[slot].record(main)      # the slot's buffers may be refilled after this step
     self.landed[slot].record(main)
     self._submitted += 1
 
