@@ -139,6 +139,13 @@ def run(name, reps, walkers=None, sweep_fraction=1.0):
 
 
 def main():
+  # keep stdout for the JSON lines only (NCCL prints its version banner there)
+  global print
+  sys.stdout.flush()
+  out = os.fdopen(os.dup(1), 'w')
+  os.dup2(2, 1)
+  _print = print
+  print = lambda *a, **k: _print(*a, **dict(k, file=out, flush=True))
   ap = argparse.ArgumentParser()
   ap.add_argument('--configs', default='c1,c3,c4,c5rbm,c5conv')
   ap.add_argument('--reps', type=int, default=5)
