@@ -161,6 +161,7 @@ int cgsvmc_ansatz_destroy(cgsvmc_ansatz* a) {
   if (a->scratch != nullptr) cudaFree(a->scratch);
   if (a->tables != nullptr) cudaFree(a->tables);
   if (a->acc_weights != nullptr) cudaFree(a->acc_weights);
+  if (a->pair_table != nullptr) cudaFree(a->pair_table);
   delete a;
   return CGSVMC_OK;
 }
@@ -200,6 +201,8 @@ int cgsvmc_ham_create(const int32_t* ij_host, const float* jx_host, const float*
     if (ij_host[2 * k] == ij_host[2 * k + 1]) return invalid("ham_create: bond connects a site to itself");
   cgsvmc_ham* h = new (std::nothrow) cgsvmc_ham();
   if (h == nullptr) return invalid("ham_create: out of host memory");
+  static uint64_t next_uid = 0;
+  h->uid = ++next_uid;
   h->n_bonds = n_bonds;
   h->n_sites = n_sites;
   const size_t nb = (size_t)std::max(n_bonds, 1);

@@ -31,9 +31,14 @@ struct cgsvmc_ansatz {
   const uint64_t* step_counter_dev = nullptr;   // set during cgsvmc_mc_steps_graph: device-side step offset
   float* acc_weights = nullptr;    // owned: [2, B] weight rows of cgsvmc_accumulate (tile networks)
   size_t acc_weights_bytes = 0;
+  float* pair_table = nullptr;     // owned: bond-pair table of the rbm2 walker kernel ([2 n_bonds][HP])
+  size_t pair_table_bytes = 0;
+  uint64_t pair_ham_uid = 0;       // the Hamiltonian it was built for
+  bool pair_valid = false;         // matches the current tables
 };
 
 struct cgsvmc_ham {
+  uint64_t uid = 0;      // unique per created handle (cache key)
   int32_t n_bonds = 0;
   int32_t n_sites = 0;
   int2* ij = nullptr;    // device [n_bonds]

@@ -113,6 +113,21 @@ reduce_kernel(const float* __restrict__ partials, int n_cta, int64_t stride, int
   if (blockIdx.x == 0 && threadIdx.x == 32 && counter != nullptr) *counter += advance;
 }
 
+// Bond-pair table for the local energy: row 2 k + o holds F[d][j] * G[u][j] with
+// d the raised and u the lowered site of bond k in orientation o (o = 0: the
+// bond's first site is raised).  The same single-rounding product the two-row
+// ratio loop forms on the fly.
+__global__ void __launch_bounds__(128)
+pair_prep_kernel(Image im, const float* __restrict__ img, const int2* __restrict__ bonds, int n_bonds,
+                 float* __restrict__ pair) {
+  const int r = blockIdx.x, k = r >> 1, o = r & 1;
+  if (k >= n_bonds) return;
+  const int2 b = bonds[k];
+  const int d = o ? b.y : b.x, u = o ? b.x : b.y;
+  for (int j = threadIdx.x; j < im.HP; j += 128)
+    pair[(size_t)r * im.HP + j] = img[im.off_f + (size_t)d * im.HP + j] * img[im.off_g + (size_t)u * im.HP + j];
+}
+
 Image make_image(int N, int H, int HP) {
   Image im;
   im.N = N; im.H = H; im.HP = HP; im.NP = round_up(N, 4);
@@ -130,9 +145,10 @@ Image make_image(int N, int H, int HP) {
 }
 
 size_t walker_smem_bytes(const Image& im, int slots, bool ws, bool do_eloc, int n_bonds, bool do_grad,
-                         bool mc = false) {
+                         bool mc = false, bool pt = false) {
   const int NP4 = round_up(im.N + 1, 4);
-  size_t b = ws ? (size_t)im.total * 4 : 0;
+  size_t b = ws ? (size_t)(im.total - (pt ? im.off_f : 0)) * 4 : 0;
+  if (pt) b += (size_t)2 * n_bonds * im.HP * 4;
   b += 16;
   if (do_eloc) b += (size_t)n_bonds * 16 + (size_t)slots * round_up(n_bonds, 8) * 4;
   if (do_grad) b += (size_t)slots * im.HP * 4 + (size_t)slots * 2 * NP4 * 4;
@@ -190,7 +206,29 @@ int build_image(cgsvmc_ansatz* a, const Plan& pl, cudaStream_t st) {
   prep_kernel<<<blocks, 128, 0, st>>>(pl.im, p + a->offsets[0], p + a->offsets[1], p + a->offsets[2],
                                       p + a->offsets[3], a->tables);
   a->tables_valid = true;
+  a->pair_valid = false;
   return cuda_fail(cudaGetLastError(), "rbm2 prep launch");
+}
+
+// (Re)builds the bond-pair table when the tables or the Hamiltonian changed.
+int build_pair_table(cgsvmc_ansatz* a, const cgsvmc_ham* h, const Plan& pl, cudaStream_t st) {
+  const size_t bytes = (size_t)2 * h->n_bonds * pl.im.HP * 4;
+  if (a->pair_table_bytes < bytes) {
+    if (a->pair_table != nullptr) {
+      if (int rc = cuda_fail(cudaDeviceSynchronize(), "pair table sync")) return rc;
+      cudaFree(a->pair_table);
+      a->pair_table = nullptr;
+      a->pair_table_bytes = 0;
+    }
+    if (int rc = cuda_fail(cudaMalloc(&a->pair_table, bytes), "pair table alloc")) return rc;
+    a->pair_table_bytes = bytes;
+    a->pair_valid = false;
+  }
+  if (a->pair_valid && a->pair_ham_uid == h->uid) return CGSVMC_OK;
+  pair_prep_kernel<<<2 * h->n_bonds, 128, 0, st>>>(pl.im, a->tables, h->ij, h->n_bonds, a->pair_table);
+  a->pair_valid = true;
+  a->pair_ham_uid = h->uid;
+  return cuda_fail(cudaGetLastError(), "rbm2 pair prep launch");
 }
 
 }  // namespace
@@ -203,7 +241,7 @@ bool rbm2_supported(const cgsvmc_ansatz* a, const cgsvmc_ham* h) {
   if (!base_plan(a, 1, &pl)) return false;
   const int slots = pl.slots;
   const int nb = h != nullptr ? h->n_bonds : 0;
-  if (nb >= 65535) return false;
+  if (nb >= 32768) return false;      // list entries keep 15 bits of bond index
   // the largest launch (accumulate) must fit with the image left in global memory
   return walker_smem_bytes(pl.im, slots, false, h != nullptr, nb, true, true) <= (size_t)a->max_smem_optin;
 }
@@ -236,15 +274,23 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
   const int slots = pl.slots;
   const int nb = do_eloc ? h->n_bonds : 0;
   pl.ws = walker_smem_bytes(pl.im, slots, true, do_eloc, nb, do_grad, mc) <= (size_t)a->max_smem_optin;
-  pl.walker_smem = walker_smem_bytes(pl.im, slots, pl.ws, do_eloc, nb, do_grad, mc);
+  // bond-pair table: 8 lanes per walker, at least one bond, pair index below 2^15,
+  // and everything (image from F on + pair table + staging) in shared memory
+  static const bool pt_off = getenv("CGSVMC_RBM2_NO_PAIR_TABLE") != nullptr;
+  pl.pt = !pt_off && do_eloc && pl.ws && pl.lpw == 8 && nb >= 1 && nb < 16384 &&
+          walker_smem_bytes(pl.im, slots, true, do_eloc, nb, do_grad, mc, true) <= (size_t)a->max_smem_optin;
+  pl.walker_smem = walker_smem_bytes(pl.im, slots, pl.ws, do_eloc, nb, do_grad, mc, pl.pt);
   if (pl.walker_smem > (size_t)a->max_smem_optin) {
     set_error("rbm2: problem does not fit in shared memory");
     return CGSVMC_ERR_UNSUPPORTED;
   }
   if (int rc = build_image(a, pl, st)) return rc;
+  if (pl.pt)
+    if (int rc = build_pair_table(a, h, pl, st)) return rc;
   const int64_t P = a->n_params;
   WalkerArgs A;
   memset(&A, 0, sizeof(A));
+  A.pair_table = pl.pt ? a->pair_table : nullptr;
   A.packed = packed; A.B = B; A.wpc = pl.wpc; A.n_batches = pl.n_batches;
   A.do_eloc = do_eloc ? 1 : 0;
   if (do_eloc) { A.bonds_ij = h->ij; A.bonds_jx = h->jx; A.bonds_jz = h->jz; A.n_bonds = h->n_bonds; }

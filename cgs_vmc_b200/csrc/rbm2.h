@@ -19,6 +19,7 @@ struct Plan {
   int nw, lpw, kjv;     // words per walker, lanes per walker, HP / 32
   int slots;             // walkers per CTA batch the variant can hold
   bool ws;               // image in shared memory
+  bool pt;               // walker kernel: bond-pair table in shared memory (E_loc reads one row per ratio)
   int wpc;               // walkers per CTA batch
   int64_t n_batches;
   int grid;

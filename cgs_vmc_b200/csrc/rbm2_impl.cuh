@@ -126,7 +126,10 @@ __device__ __forceinline__ float group_sum(float v) {
 
 // TMA bulk copy global -> shared of the parameter image; every thread returns
 // after the bytes have landed.  `bar` is an 8-byte shared mbarrier.
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+// (a second region -- the bond-pair table -- may ride on the same barrier)
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                          void* dst2 = nullptr, const void* src2 = nullptr,
+                                          uint32_t bytes2 = 0) {
   const uint32_t bar_a = smem_u32(bar);
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
@@ -134,17 +137,22 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes + bytes2)
                  : "memory");
-    uint32_t done = 0;
-    while (done < bytes) {
-      const uint32_t chunk = min(bytes - done, 32768u);
-      asm volatile(
-          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-              smem_u32(reinterpret_cast<char*>(dst) + done)),
-          "l"(reinterpret_cast<const char*>(src) + done), "r"(chunk), "r"(bar_a)
-          : "memory");
-      done += chunk;
+    for (int region = 0; region < 2; ++region) {
+      char* d = reinterpret_cast<char*>(region == 0 ? dst : dst2);
+      const char* g = reinterpret_cast<const char*>(region == 0 ? src : src2);
+      const uint32_t total = region == 0 ? bytes : bytes2;
+      uint32_t done = 0;
+      while (done < total) {
+        const uint32_t chunk = min(total - done, 32768u);
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(d + done)),
+            "l"(g + done), "r"(chunk), "r"(bar_a)
+            : "memory");
+        done += chunk;
+      }
     }
   }
   uint32_t ok = 0;
@@ -202,7 +210,8 @@ __device__ __forceinline__ int spin_bit(const uint64_t (&s)[NW], int site) {
 // theta_j = base_j + sum_{i up} 2 W[i][j];  p = 1 / (1 + e^{-2 theta}),
 // m = 1 / (1 + e^{2 theta}).  Optionally returns this lane's share of
 // sum_j log cosh theta_j + a . sigma (group_sum + a0 gives z).
-template <int NW, int LPW, int KJV, bool WS>
+// W2S: the 2W rows are in shared memory (default: wherever the image is).
+template <int NW, int LPW, int KJV, bool WS, bool W2S = WS>
 __device__ __forceinline__ float init_state(const Tables& t, const Image& im, const uint64_t (&s)[NW],
                                             int sub, float (&p)[32 / LPW * KJV],
                                             float (&m)[32 / LPW * KJV], bool want_z) {
@@ -228,7 +237,7 @@ __device__ __forceinline__ float init_state(const Tables& t, const Image& im, co
 #pragma unroll
         for (int q = 0; q < KJV; ++q) {
           float v[VW];
-          ldv<VW, WS>(row + 32 * q, v);
+          ldv<VW, W2S>(row + 32 * q, v);
 #pragma unroll
           for (int c = 0; c < VW; c += 2)
             add2(th[VW * q + c], th[VW * q + c + 1], th[VW * q + c], th[VW * q + c + 1], v[c], v[c + 1]);
@@ -338,21 +347,70 @@ __device__ __forceinline__ void transpose_reduce(float (&part)[LPW], int sub) {
   }
 }
 
+// This lane's share of sum_j log2(p_j T_j + m_j) with T = one row of the
+// bond-pair table (T_j = F[d][j] G[u][j], formed by pair_prep_kernel with the
+// same multiply as exchange_log2_partial: identical values, half the
+// shared-memory traffic and no FMUL2 per pair of hidden units).
+template <int LPW, int KJV>
+__device__ __forceinline__ float pair_log2_partial(const float* __restrict__ row, int sub,
+                                                   const float (&p)[32 / LPW * KJV],
+                                                   const float (&m)[32 / LPW * KJV]) {
+  constexpr int VW = 32 / LPW, KJ = VW * KJV;
+  float n[KJ];
+#pragma unroll
+  for (int q = 0; q < KJV; ++q) {
+    float tv[VW];
+    ldv<VW, true>(row + VW * sub + 32 * q, tv);
+#pragma unroll
+    for (int c = 0; c < VW; c += 2) {
+      const int k = VW * q + c;
+      fma2(n[k], n[k + 1], p[k], p[k + 1], tv[c], tv[c + 1], m[k], m[k + 1]);
+    }
+  }
+  float lsum = 0.f;
+#pragma unroll
+  for (int k = 0; k < KJ; k += 4) {
+    float pr;
+    if (k + 3 < KJ) {
+      float q0, q1;
+      mul2(q0, q1, n[k], n[k + 1], n[k + 2], n[k + 3]);
+      pr = q0 * q1;
+    } else {
+      pr = n[k] * n[k + 1];
+    }
+    lsum += lg2_approx(pr);
+  }
+  return lsum;
+}
+
 // One round of the local-energy off-diagonal sum: R (= LPW or LPW / 2) listed
 // bonds of this walker starting at it0.  list entry = site to raise | site to
 // lower << 8 | bond index << 16; bond_s[k].z = j_x bits.  Returns this lane's
 // share of sum_k 0.5 j_x psi(flip_k) / psi (operators.py:168-169).
+// pair_s != nullptr: rows of the bond-pair table (row 2 k + o, o = bit 31 of
+// the entry: which end of bond k is raised) instead of two site rows.
 template <int R, int LPW, int KJV, bool WS>
 __device__ __forceinline__ float ratio_round(const Tables& t, const uint32_t* list, const int4* bond_s,
                                              int it0, int cnt, int sub,
                                              const float (&p)[32 / LPW * KJV],
-                                             const float (&m)[32 / LPW * KJV]) {
+                                             const float (&m)[32 / LPW * KJV],
+                                             const float* pair_s = nullptr) {
+  constexpr int HP = 32 * KJV;
   float part[R], tdummy[32 / LPW * KJV];
+  if (pair_s != nullptr) {
 #pragma unroll
-  for (int i = 0; i < R; ++i) {
-    const uint32_t ent = it0 + i < cnt ? list[it0 + i] : 0u;
-    part[i] = exchange_log2_partial<LPW, KJV, WS, false>(t, (int)(ent & 0xffu), (int)((ent >> 8) & 0xffu),
-                                                         sub, p, m, tdummy);
+    for (int i = 0; i < R; ++i) {
+      const uint32_t ent = it0 + i < cnt ? list[it0 + i] : 0u;
+      const int row = (int)(((ent >> 16) & 0x7fffu) * 2u + (ent >> 31));
+      part[i] = pair_log2_partial<LPW, KJV>(pair_s + (size_t)row * HP, sub, p, m);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const uint32_t ent = it0 + i < cnt ? list[it0 + i] : 0u;
+      part[i] = exchange_log2_partial<LPW, KJV, WS, false>(t, (int)(ent & 0xffu), (int)((ent >> 8) & 0xffu),
+                                                           sub, p, m, tdummy);
+    }
   }
   // partial round (R < LPW): fold the sub-groups of R lanes first
 #pragma unroll
@@ -383,7 +441,7 @@ __device__ __forceinline__ float ratio_round(const Tables& t, const uint32_t* li
     // (explicit roundings: no FMA contraction, so the fused, split and
     // gradient-less instantiations give bit-identical local energies)
     const float l2 = __fadd_rn(total, __fsub_rn(ld1<WS>(t.a2 + dn), ld1<WS>(t.a2 + up)));
-    term = __fmul_rn(0.5f * __int_as_float(bond_s[ent >> 16].z), ex2_approx(l2));
+    term = __fmul_rn(0.5f * __int_as_float(bond_s[(ent >> 16) & 0x7fffu].z), ex2_approx(l2));
   }
   return term;
 }
@@ -677,6 +735,9 @@ struct WalkerArgs {
   uint64_t seed, walker0, step0;
   const uint64_t* step0_dev;
   unsigned long long* accept_count;
+  // bond-pair table (PT kernels): [2 n_bonds][HP], row 2 k + o = F[d] * G[u]
+  // for bond k with d = (o ? j_k : i_k) raised and the other end lowered
+  const float* pair_table;
 };
 
 // MC: after the estimators of a walker are done (and its gradient inputs are
@@ -684,16 +745,23 @@ struct WalkerArgs {
 // steps from the state (p, m) it already holds, and writes the configuration
 // back; the CTA-wide gradient tiles follow.  Saves a launch, a second table
 // load and a second state build per batch iteration.
-template <int NW, int LPW, int KJV, bool WS, bool MC>
+// PT (needs WS): the local energy reads ONE row of the bond-pair table per
+// amplitude ratio instead of two site rows (the binding resource of this
+// kernel is shared-memory bandwidth); to make room the 2W rows of the state
+// build stay in global memory (23 KB at C2, L1-resident) and the
+// shared-memory image starts at the F table.
+template <int NW, int LPW, int KJV, bool WS, bool MC, bool PT = false>
 __global__ void __launch_bounds__((Geometry<LPW, KJV>::THREADS), 1)
 walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
   using Geo = Geometry<LPW, KJV>;
   constexpr int WPW = Geo::WPW, KJ = Geo::KJ, VW = Geo::VW, HP = Geo::HP;
   constexpr int SLOTS = Geo::SLOTS, THREADS = Geo::THREADS;
+  static_assert(!PT || WS, "the pair-table kernel keeps its tables in shared memory");
   extern __shared__ __align__(16) float smem[];
   // ---- shared-memory carve-up (mirrors walker_smem_bytes) ----
-  float* img_s = smem;
-  char* cur = reinterpret_cast<char*>(smem + (WS ? im.total : 0));
+  const int img_skip = PT ? im.off_f : 0;          // floats of the image left in global memory
+  float* img_s = smem - img_skip;                  // so that img_s + off_x addresses table x
+  char* cur = reinterpret_cast<char*>(smem + (WS ? im.total - img_skip : 0));
   uint64_t* bar = reinterpret_cast<uint64_t*>(cur); cur += 16;
   int4* bond_s = reinterpret_cast<int4*>(cur); cur += (size_t)(A.do_eloc ? A.n_bonds : 0) * 16;
   const int list_ld = (A.n_bonds + 7) / 8 * 8;
@@ -704,6 +772,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
   float* e_s = reinterpret_cast<float*>(cur); cur += (size_t)SLOTS * 4;
   // select table: inside the image when it is in shared memory, else 2048 bytes here (MC only)
   uint8_t* lut = WS ? reinterpret_cast<uint8_t*>(img_s + im.off_lut) : reinterpret_cast<uint8_t*>(cur);
+  float* pair_s = PT ? reinterpret_cast<float*>(cur) : nullptr;      // [2 n_bonds][HP]
 
   RBM2_MARK(1, 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -719,7 +788,9 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
 #pragma unroll
     for (int w = 0; w < NW; ++w) s_first[w] = w < im.words ? A.packed[bb * im.words + w] : 0ull;
   }
-  if (WS) bulk_load(img_s, img_g, (uint32_t)im.total * 4u, bar);
+  if (PT) bulk_load(smem, img_g + img_skip, (uint32_t)(im.total - img_skip) * 4u, bar,
+                    pair_s, A.pair_table, (uint32_t)(2 * A.n_bonds * HP) * 4u);
+  else if (WS) bulk_load(img_s, img_g, (uint32_t)im.total * 4u, bar);
   else if (MC) build_lut(lut);
   if (A.do_eloc) {
     for (int k = threadIdx.x; k < A.n_bonds; k += THREADS) {
@@ -729,7 +800,8 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
   }
   __syncthreads();
   RBM2_MARK(1, 1);
-  const Tables t = tables_at(WS ? img_s : img_g, im);
+  Tables t = tables_at(WS ? img_s : img_g, im);
+  if (PT) t.w2 = img_g + im.off_w2;
   SitePicker<NW, LPW> picker;
   if (MC) picker.setup(im.N, sub);
   unsigned int n_acc = 0;
@@ -763,7 +835,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
         s[w] = batch_no == 0 ? s_first[w] : (w < im.words ? A.packed[bb * im.words + w] : 0ull);
       float p[KJ], m[KJ];
       const bool want_z = A.log_amp != nullptr;
-      float z = init_state<NW, LPW, KJV, WS>(t, im, s, sub, p, m, want_z);
+      float z = init_state<NW, LPW, KJV, WS, WS && !PT>(t, im, s, sub, p, m, want_z);
       if (want_z) {
         z = group_sum<LPW>(z) + ld1<WS>(t.a0);
         if (valid && sub == 0) A.log_amp[b] = z;
@@ -786,7 +858,8 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
             anti = bi != spin_bit<NW>(s, bd.y);
             diag = __fmaf_rn(anti ? -0.25f : 0.25f, __int_as_float(bd.w), diag);   // operators.py:165,169
             const int up = bi ? bd.x : bd.y, dn = bi ? bd.y : bd.x;
-            ent = (uint32_t)dn | ((uint32_t)up << 8) | ((uint32_t)k << 16);
+            // bit 31: the raised site is the bond's second end (pair-table row 2 k + 1)
+            ent = (uint32_t)dn | ((uint32_t)up << 8) | ((uint32_t)k << 16) | (bi ? 0x80000000u : 0u);
           }
           const uint32_t vote = __ballot_sync(CGSVMC_FULL_MASK, anti);
           const uint32_t gbits = (vote >> (grp * LPW)) & ((1u << LPW) - 1u);
@@ -812,9 +885,9 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
         float off_lane = 0.f;
         int it0 = 0;
         for (; n_max - it0 > RND / 2; it0 += RND)
-          off_lane = __fadd_rn(off_lane, ratio_round<RND, LPW, KJV, WS>(t, list, bond_s, it0, cnt, sub, p, m));
+          off_lane = __fadd_rn(off_lane, ratio_round<RND, LPW, KJV, WS>(t, list, bond_s, it0, cnt, sub, p, m, pair_s));
         if (it0 < n_max)
-          off_lane = __fadd_rn(off_lane, ratio_round<RND / 2, LPW, KJV, WS>(t, list, bond_s, it0, cnt, sub, p, m));
+          off_lane = __fadd_rn(off_lane, ratio_round<RND / 2, LPW, KJV, WS>(t, list, bond_s, it0, cnt, sub, p, m, pair_s));
         const float off = group_sum<LPW>(off_lane);
         e_val = __fadd_rn(diag, off);
         RBM2_MARK(1, 3);
@@ -1006,14 +1079,16 @@ template <int NW, int LPW, int KJV>
 int launch_walker_variant(const Plan& pl, const float* img, const WalkerArgs& A, cudaStream_t st) {
   constexpr int THREADS = Geometry<LPW, KJV>::THREADS;
   const bool mc = A.packed_rw != nullptr;
-#define RBM2_LAUNCH_WALKER(WSV, MCV)                                              \
+#define RBM2_LAUNCH_WALKER(WSV, MCV, PTV)                                         \
   do {                                                                            \
-    auto kern = walker_kernel<NW, LPW, KJV, WSV, MCV>;                            \
+    auto kern = walker_kernel<NW, LPW, KJV, WSV, MCV, PTV>;                       \
     if (int rc = opt_in_smem(kern, pl.walker_smem)) return rc;                    \
     kern<<<pl.grid, THREADS, pl.walker_smem, st>>>(pl.im, img, A);                \
   } while (0)
-  if (pl.ws) { if (mc) RBM2_LAUNCH_WALKER(true, true); else RBM2_LAUNCH_WALKER(true, false); }
-  else { if (mc) RBM2_LAUNCH_WALKER(false, true); else RBM2_LAUNCH_WALKER(false, false); }
+  if (pl.pt) {                       // planned only for LPW == 8 with the image in shared memory
+    if (LPW == 8) { if (mc) RBM2_LAUNCH_WALKER(true, true, (LPW == 8)); else RBM2_LAUNCH_WALKER(true, false, (LPW == 8)); }
+  } else if (pl.ws) { if (mc) RBM2_LAUNCH_WALKER(true, true, false); else RBM2_LAUNCH_WALKER(true, false, false); }
+  else { if (mc) RBM2_LAUNCH_WALKER(false, true, false); else RBM2_LAUNCH_WALKER(false, false, false); }
 #undef RBM2_LAUNCH_WALKER
   return cuda_fail(cudaGetLastError(), "rbm2 walker launch");
 }
