@@ -293,9 +293,10 @@ def run_ours(args, rank, world, local_rank):
   host_cfg.copy_(state.configs().cpu())
   fed = engine.HostFedBatchStep(state, ansatz, ham, sums, SWEEP_STEPS)
 
-  def e2e_run(n):
+  def e2e_run(n, host_input=None):
+    host_input = host_cfg if host_input is None else host_input
     for k in range(n):
-      fed.submit(host_cfg)
+      fed.submit(host_input)
       if fed.outstanding() > 1:
         fed.result()                                              # host consumes the energy of step k - 1
       if (k + 1) % EPOCH_BATCHES == 0:                            # epoch end: the [2, P] gradient sums
@@ -321,6 +322,22 @@ def run_ours(args, rank, world, local_rank):
   if world > 1:
     dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
   e2e_s = float(e2e_total.item())
+  # the same with the host holding the walkers in the library's bit-packed layout
+  # (8 B per walker instead of 144 B): shows how much of e2e is the PCIe upload
+  host_packed = state.packed.cpu().pin_memory()
+  e2e_run(4, host_packed)
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  p0, p1 = ev(), ev()
+  p0.record()
+  e2e_run(args.steps, host_packed)
+  p1.record()
+  torch.cuda.synchronize()
+  e2e_packed_total = torch.tensor([p0.elapsed_time(p1) * 1e-3], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(e2e_packed_total, op=dist.ReduceOp.MAX)
+  e2e_packed_s = float(e2e_packed_total.item())
 
   if rank != 0:
     if world > 1:
@@ -411,7 +428,13 @@ def run_ours(args, rank, world, local_rank):
               'h2d_bytes_per_step': fed.h2d_bytes,
               'd2h_bytes_per_step': fed.d2h_bytes_stats + fed.d2h_bytes_sums / EPOCH_BATCHES,
               'd2h': 'energy statistics every step; the [2, P] gradient sums once per epoch of %d steps '
-                     '(training.py:562-568 reads them once per epoch)' % EPOCH_BATCHES},
+                     '(training.py:562-568 reads them once per epoch)' % EPOCH_BATCHES,
+              'input': 'float32 [B, N] +-1 configurations (the reference layout) from pinned host memory',
+              'packed_host_input': {
+                  'value': walkers_total * SWEEP_STEPS * args.steps / e2e_packed_s,
+                  'ms_per_step': e2e_packed_s / args.steps * 1e3,
+                  'h2d_bytes_per_step': int(host_packed.numel() * 8),
+                  'what': 'same loop with the host holding the walkers bit-packed (uint64 [B, ceil(N/64)])'}},
       'gpu_launches': n_launch,
       'clocks': clocks,
       'wall_s_timed_region': wall,

@@ -151,7 +151,9 @@ size_t walker_smem_bytes(const Image& im, int slots, bool ws, bool do_eloc, int 
   if (pt) b += (size_t)2 * n_bonds * im.HP * 4;
   b += 16;
   if (do_eloc) b += (size_t)n_bonds * 16 + (size_t)slots * round_up(n_bonds, 8) * 4;
-  if (do_grad) b += (size_t)slots * im.HP * 4 + (size_t)slots * 2 * NP4 * 4;
+  // T_s (tanh staging; with the pair table at least N rows: the parked 2W table) and ws_s
+  b += (size_t)std::max(do_grad ? slots * im.HP : 0, pt ? im.N * im.HP : 0) * 4;
+  if (do_grad) b += (size_t)slots * 2 * NP4 * 4;
   b += (size_t)slots * 4;
   if (mc && !ws) b += 2048;
   return b;

@@ -129,7 +129,8 @@ __device__ __forceinline__ float group_sum(float v) {
 // (a second region -- the bond-pair table -- may ride on the same barrier)
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
                                           void* dst2 = nullptr, const void* src2 = nullptr,
-                                          uint32_t bytes2 = 0) {
+                                          uint32_t bytes2 = 0, void* dst3 = nullptr,
+                                          const void* src3 = nullptr, uint32_t bytes3 = 0) {
   const uint32_t bar_a = smem_u32(bar);
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
@@ -137,12 +138,13 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes + bytes2)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a),
+                 "r"(bytes + bytes2 + bytes3)
                  : "memory");
-    for (int region = 0; region < 2; ++region) {
-      char* d = reinterpret_cast<char*>(region == 0 ? dst : dst2);
-      const char* g = reinterpret_cast<const char*>(region == 0 ? src : src2);
-      const uint32_t total = region == 0 ? bytes : bytes2;
+    for (int region = 0; region < 3; ++region) {
+      char* d = reinterpret_cast<char*>(region == 0 ? dst : region == 1 ? dst2 : dst3);
+      const char* g = reinterpret_cast<const char*>(region == 0 ? src : region == 1 ? src2 : src3);
+      const uint32_t total = region == 0 ? bytes : region == 1 ? bytes2 : bytes3;
       uint32_t done = 0;
       while (done < total) {
         const uint32_t chunk = min(total - done, 32768u);
@@ -747,9 +749,11 @@ struct WalkerArgs {
 // load and a second state build per batch iteration.
 // PT (needs WS): the local energy reads ONE row of the bond-pair table per
 // amplitude ratio instead of two site rows (the binding resource of this
-// kernel is shared-memory bandwidth); to make room the 2W rows of the state
-// build stay in global memory (23 KB at C2, L1-resident) and the
-// shared-memory image starts at the F table.
+// kernel is shared-memory bandwidth); to make room the shared-memory image
+// starts at the F table and the 2W rows of the state build are parked in the
+// buffer that later stages tanh(theta) for the gradient tiles (a CTA barrier
+// separates the two uses; later batches of the same CTA read 2W from global
+// memory).
 template <int NW, int LPW, int KJV, bool WS, bool MC, bool PT = false>
 __global__ void __launch_bounds__((Geometry<LPW, KJV>::THREADS), 1)
 walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
@@ -767,7 +771,9 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
   const int list_ld = (A.n_bonds + 7) / 8 * 8;
   uint32_t* list_s = reinterpret_cast<uint32_t*>(cur); cur += (size_t)(A.do_eloc ? SLOTS * list_ld : 0) * 4;
   const int NP4 = (im.N + 1 + 3) / 4 * 4;
-  float* T_s = reinterpret_cast<float*>(cur); cur += (size_t)(A.do_grad ? SLOTS * HP : 0) * 4;
+  // (PT: at least N rows, the first batch's 2W table lives here during the state build)
+  float* T_s = reinterpret_cast<float*>(cur);
+  cur += (size_t)max(A.do_grad ? SLOTS * HP : 0, PT ? im.N * HP : 0) * 4;
   float* ws_s = reinterpret_cast<float*>(cur); cur += (size_t)(A.do_grad ? SLOTS * 2 * NP4 : 0) * 4;
   float* e_s = reinterpret_cast<float*>(cur); cur += (size_t)SLOTS * 4;
   // select table: inside the image when it is in shared memory, else 2048 bytes here (MC only)
@@ -789,7 +795,8 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
     for (int w = 0; w < NW; ++w) s_first[w] = w < im.words ? A.packed[bb * im.words + w] : 0ull;
   }
   if (PT) bulk_load(smem, img_g + img_skip, (uint32_t)(im.total - img_skip) * 4u, bar,
-                    pair_s, A.pair_table, (uint32_t)(2 * A.n_bonds * HP) * 4u);
+                    pair_s, A.pair_table, (uint32_t)(2 * A.n_bonds * HP) * 4u,
+                    T_s, img_g + im.off_w2, (uint32_t)(im.N * HP) * 4u);
   else if (WS) bulk_load(img_s, img_g, (uint32_t)im.total * 4u, bar);
   else if (MC) build_lut(lut);
   if (A.do_eloc) {
@@ -801,7 +808,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
   __syncthreads();
   RBM2_MARK(1, 1);
   Tables t = tables_at(WS ? img_s : img_g, im);
-  if (PT) t.w2 = img_g + im.off_w2;
+  if (PT) t.w2 = T_s;
   SitePicker<NW, LPW> picker;
   if (MC) picker.setup(im.N, sub);
   unsigned int n_acc = 0;
@@ -825,22 +832,31 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
     const int64_t b0 = batch * A.wpc;
     const int n_valid = (int)min((int64_t)A.wpc, A.B - b0);
     const bool warp_on = warp * WPW < n_valid;
+    const bool valid = slot < n_valid;
+    const int64_t b = b0 + slot;
+    const int64_t bb = valid ? b : b0 + n_valid - 1;
+    uint64_t s[NW];
+    float p[KJ], m[KJ];
     if (warp_on) {
-      const bool valid = slot < n_valid;
-      const int64_t b = b0 + slot;
-      const int64_t bb = valid ? b : b0 + n_valid - 1;
-      uint64_t s[NW];
 #pragma unroll
       for (int w = 0; w < NW; ++w)
         s[w] = batch_no == 0 ? s_first[w] : (w < im.words ? A.packed[bb * im.words + w] : 0ull);
-      float p[KJ], m[KJ];
       const bool want_z = A.log_amp != nullptr;
-      float z = init_state<NW, LPW, KJV, WS, WS && !PT>(t, im, s, sub, p, m, want_z);
+      float z = init_state<NW, LPW, KJV, WS>(t, im, s, sub, p, m, want_z);
       if (want_z) {
         z = group_sum<LPW>(z) + ld1<WS>(t.a0);
         if (valid && sub == 0) A.log_amp[b] = z;
       }
       RBM2_MARK(1, 2);
+    }
+    // PT: every warp is done with the parked 2W rows before T_s is written for
+    // the gradient; from here on (the sampler's rare state rebuild, later
+    // batches) the 2W rows come from global memory
+    if (PT && A.do_grad && batch_no == 0) {
+      __syncthreads();
+      t.w2 = img_g + im.off_w2;
+    }
+    if (warp_on) {
       float e_val = 0.f;
       if (A.do_eloc) {
         // ---- enumerate antiparallel bonds (operators.py:154-167) ----

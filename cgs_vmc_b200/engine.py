@@ -204,7 +204,6 @@ class HostFedBatchStep(_CapturedStep):
     self.host_stats = [torch.empty(4, dtype=torch.float64).pin_memory() for _ in range(2)]
     self.host_sums = torch.empty(2, P, dtype=torch.float32).pin_memory()
     self.uploaded = [torch.cuda.Event() for _ in range(2)]
-    self.consumed = [torch.cuda.Event() for _ in range(2)]
     self.landed = [torch.cuda.Event() for _ in range(2)]
     self.h2d_bytes = B * N * 4
     self.d2h_bytes_stats = 32
@@ -226,7 +225,7 @@ class HostFedBatchStep(_CapturedStep):
     for p in self.slot_packed:               # the warm-up stepped slot 0
       p.copy_(state.packed)
     main = torch.cuda.current_stream()
-    for ev in self.consumed:
+    for ev in self.landed:
       ev.record(main)
 
   def _body(self, slot):
@@ -234,18 +233,27 @@ class HostFedBatchStep(_CapturedStep):
     self.host_stats[slot].copy_(self.sums.stats, non_blocking=True)
 
   def submit(self, host_configs):
-    """host_configs: pinned float32 [B, N] of +-1.  Asynchronous."""
+    """host_configs: pinned host tensor, either the reference's float32 [B, N]
+    of +-1 (uploaded and bit-packed on the copy stream) or the library's own
+    walker layout, int64 [B, ceil(N / 64)] bit-packed (uploaded as is: 8 bytes
+    per walker up to 64 sites instead of 4 N).  Asynchronous."""
     slot = self._submitted & 1
     main = torch.cuda.current_stream()
     with torch.cuda.stream(self.copy_stream):
-      self.copy_stream.wait_event(self.consumed[slot])
-      self.dev_cfg[slot].copy_(host_configs, non_blocking=True)
-      _native.pack_configs(self.dev_cfg[slot], out=self.slot_packed[slot])
+      self.copy_stream.wait_event(self.landed[slot])
+      if host_configs.dtype == torch.int64:
+        if tuple(host_configs.shape) != tuple(self.slot_packed[slot].shape):
+          raise ValueError('Size of existing variable does not match.')
+        self.slot_packed[slot].copy_(host_configs, non_blocking=True)
+      else:
+        self.dev_cfg[slot].copy_(host_configs, non_blocking=True)
+        _native.pack_configs(self.dev_cfg[slot], out=self.slot_packed[slot])
       self.uploaded[slot].record(self.copy_stream)
     main.wait_event(self.uploaded[slot])
     self._replay(slot)
     self.state.packed = self.slot_packed[slot]
-    self.consumed[slot].record(main)      # the slot's buffers may be refilled after this step
+    # one event: the step's statistics have landed on the host AND the slot's
+    # buffers may be refilled
     self.landed[slot].record(main)
     self._submitted += 1
 
