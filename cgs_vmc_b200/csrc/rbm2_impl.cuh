@@ -779,6 +779,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
   // select table: inside the image when it is in shared memory, else 2048 bytes here (MC only)
   uint8_t* lut = WS ? reinterpret_cast<uint8_t*>(img_s + im.off_lut) : reinterpret_cast<uint8_t*>(cur);
   float* pair_s = PT ? reinterpret_cast<float*>(cur) : nullptr;      // [2 n_bonds][HP]
+  int* tile_next_s = reinterpret_cast<int*>(bar) + 2;                // behind the 8-byte mbarrier
 
   RBM2_MARK(1, 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -818,7 +819,6 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
   constexpr int CT = HP / 4;
   const int RT = NP4 / 4;
   const int n_tiles = RT * CT;
-  const int n_pass = (n_tiles + THREADS - 1) / THREADS;
   // The a-gradient (entries rev (+ THREADS) of [2][NP4]) and the energy
   // statistics are taken from the END of the CTA: with fewer tiles than
   // threads those warps have no tile work.
@@ -941,21 +941,52 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
         if (sub == 0) e_s[slot] = e_val;
       }
       RBM2_MARK(1, 4);
-      if (MC) {
-        n_acc += mc_sweep<NW, LPW, KJV, WS>(t, im, picker, lut, s, p, m, sub, valid, A.n_steps, A.seed,
-                                            A.walker0 + (uint64_t)bb, mc_step0);
-        if (valid && sub == 0) {
+    }
+    // The gradient tiles need every walker's staged rows but not the sweep:
+    // after this barrier the warps that own walkers run their Metropolis steps
+    // while the warps without walkers (wpc < SLOTS) already work through the
+    // tiles, 32 at a time from a shared counter; the sweeping warps join when
+    // they are done.  (FMA-pipe tile work under the sampler's issue gaps.)
+    if (A.do_grad) {
+      if (threadIdx.x == 0) *tile_next_s = 0;
+      __syncthreads();
+    }
+    if (MC && warp_on) {
+      n_acc += mc_sweep<NW, LPW, KJV, WS>(t, im, picker, lut, s, p, m, sub, valid, A.n_steps, A.seed,
+                                          A.walker0 + (uint64_t)bb, mc_step0);
+      if (valid && sub == 0) {
 #pragma unroll
-          for (int w = 0; w < NW; ++w) if (w < im.words) A.packed_rw[b * im.words + w] = s[w];
-        }
+        for (int w = 0; w < NW; ++w) if (w < im.words) A.packed_rw[b * im.words + w] = s[w];
       }
       RBM2_MARK(1, 5);
     }
     if (A.do_grad) {
-      __syncthreads();
       RBM2_MARK(1, 6);
-      for (int pass = 0; pass < n_pass; ++pass) {
-        const int tile = threadIdx.x + pass * THREADS;
+      // side sums first (the warps at the END of the CTA get here early)
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int e = rev + h2 * THREADS;
+        if (e < 2 * NP4) {
+#pragma unroll 4
+          for (int sb = 0; sb < n_valid; ++sb) acc_a[h2] += ws_s[(size_t)sb * 2 * NP4 + e];
+        }
+      }
+      if (warp == THREADS / 32 - 1 && A.stat_partials != nullptr) {
+        double e1 = 0.0, e2 = 0.0;
+        for (int sb = lane; sb < n_valid; sb += 32) {
+          const double e = (double)e_s[sb];
+          e1 += e;
+          e2 += e * e;
+        }
+        sum_e += warp_sum(e1);
+        sum_e2 += warp_sum(e2);
+      }
+      for (;;) {
+        int tile_base = 0;
+        if (lane == 0) tile_base = atomicAdd(tile_next_s, 32);
+        tile_base = __shfl_sync(CGSVMC_FULL_MASK, tile_base, 0);
+        if (tile_base >= n_tiles) break;
+        const int tile = tile_base + lane;
         if (tile < n_tiles) {
           const int rt = tile / CT, ct = tile - rt * CT;
           // the accumulators live only here: a CTA's partial sums are kept in
@@ -1014,24 +1045,6 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
               }
             }
         }
-      }
-#pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        const int e = rev + h2 * THREADS;
-        if (e < 2 * NP4) {
-#pragma unroll 4
-          for (int sb = 0; sb < n_valid; ++sb) acc_a[h2] += ws_s[(size_t)sb * 2 * NP4 + e];
-        }
-      }
-      if (warp == THREADS / 32 - 1 && A.stat_partials != nullptr) {
-        double e1 = 0.0, e2 = 0.0;
-        for (int sb = lane; sb < n_valid; sb += 32) {
-          const double e = (double)e_s[sb];
-          e1 += e;
-          e2 += e * e;
-        }
-        sum_e += warp_sum(e1);
-        sum_e2 += warp_sum(e2);
       }
       RBM2_MARK(1, 7);
       __syncthreads();
