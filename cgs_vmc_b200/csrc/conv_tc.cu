@@ -341,7 +341,6 @@ struct Engine {
   // warp-uniform), then every warp runs the epilogue.
   template <int CC>
   __device__ void tensor_layer(int layer, int n_cfg) {
-    const int taps = d.kx * d.ky;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool first = layer == 0;
     const uint32_t buf = (!first && d.n_wbuf == 2) ? (use_count & 1u) : 0u;

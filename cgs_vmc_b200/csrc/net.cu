@@ -280,7 +280,6 @@ struct Mlp {
 // positions handled by a warp read consecutive addresses).  One thread owns
 // one (configuration, position) and all output channels in chunks of 16.
 struct Conv {
-  __host__ __device__ static int cmax(const NetDesc& d) { return d.C; }
   __host__ __device__ static size_t act_floats(const NetDesc& d, int T) {
     return (size_t)T * d.C * d.N;
   }
@@ -452,7 +451,6 @@ struct Conv {
 // ---------------------------------------------------------------------------
 template <int TW>
 struct MlpNet {
-  static constexpr bool kFixedT = true;
   __host__ __device__ static int tile(const NetDesc&, int) { return Mlp<TW>::T; }
   __host__ static size_t fwd_smem(const NetDesc& d, int) { return Mlp<TW>::forward_smem_bytes(d); }
   __device__ static void forward(const NetDesc& d, const uint64_t* cfg, int, float* smem, float* z) {
@@ -470,10 +468,6 @@ struct ConvNet {
 
 // Dynamic shared memory layout of the non-grad kernels:
 //   [ forward scratch (fwd_smem) | cfg words T*NW u64 | z tile T f32 | kernel extras ]
-__device__ __forceinline__ uint64_t* cfg_area(float* smem, size_t fwd_bytes) {
-  return reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(smem) + fwd_bytes);
-}
-
 // Bump allocator over the dynamic shared memory behind the forward scratch;
 // every block is 16-byte aligned (host sizes include the slack).
 struct Carver {

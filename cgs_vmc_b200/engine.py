@@ -4,6 +4,8 @@ This is the host-side glue under the reference-shaped API (graph_builders,
 operators, training): it owns the torch buffers and calls the C-ABI.  Nothing
 here computes on the CPU.
 """
+import types
+
 import torch
 
 from . import _native
@@ -215,7 +217,6 @@ class HostFedBatchStep(_CapturedStep):
     # one walker buffer per slot: the upload AND the packing of batch k run on the
     # copy stream while batch k - 1 computes; the graphs step the slot's buffer
     # (after a submit `state.packed` is rebound to the buffer just stepped)
-    import types
     self.slot_packed = [state.packed.clone() for _ in range(2)]
     self.slot_state = [types.SimpleNamespace(
         packed=self.slot_packed[i], seed=state.seed, walker_id0=state.walker_id0,

@@ -547,7 +547,7 @@ def _close_sums(got, ref):
   np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=0, atol=2e-6 * np.abs(ref).max() + 1e-6)
 
 
-@pytest.mark.parametrize('n_side,hidden,batch,j1j2', [(6, 144, 777, False), (4, 24, 130, True),
+@pytest.mark.parametrize('n_side,hidden,batch,j1j2', [(6, 144, 777, False), (6, 144, 8192, False), (4, 24, 130, True),
                                                       (16, 256, 300, False), (10, 64, 257, True)])
 def test_batch_step_equals_accumulate_then_sweep(native, n_side, hidden, batch, j1j2):
   """cgsvmc_batch_step (estimators + sweep fused in one kernel for the pure
