@@ -161,7 +161,8 @@ int cgsvmc_ansatz_destroy(cgsvmc_ansatz* a) {
   if (a->scratch != nullptr) cudaFree(a->scratch);
   if (a->tables != nullptr) cudaFree(a->tables);
   if (a->acc_weights != nullptr) cudaFree(a->acc_weights);
-  if (a->pair_table != nullptr) cudaFree(a->pair_table);
+  for (auto& pt : a->pair_tables)
+    if (pt.buf != nullptr) cudaFree(pt.buf);
   delete a;
   return CGSVMC_OK;
 }

@@ -31,10 +31,18 @@ struct cgsvmc_ansatz {
   const uint64_t* step_counter_dev = nullptr;   // set during cgsvmc_mc_steps_graph: device-side step offset
   float* acc_weights = nullptr;    // owned: [2, B] weight rows of cgsvmc_accumulate (tile networks)
   size_t acc_weights_bytes = 0;
-  float* pair_table = nullptr;     // owned: bond-pair table of the rbm2 walker kernel ([2 n_bonds][HP])
-  size_t pair_table_bytes = 0;
-  uint64_t pair_ham_uid = 0;       // the Hamiltonian it was built for
-  bool pair_valid = false;         // matches the current tables
+  // owned: bond-pair tables of the rbm2 walker kernel ([2 n_bonds][HP]), one per
+  // Hamiltonian this ansatz has been used with.  Entries are never moved or
+  // evicted (captured CUDA graphs keep pointing at them); past kMaxPairTables
+  // Hamiltonians the two-row path is used.
+  struct PairTable {
+    uint64_t ham_uid = 0;
+    float* buf = nullptr;
+    size_t bytes = 0;
+    bool valid = false;            // matches the current tables
+  };
+  static constexpr int kMaxPairTables = 16;
+  std::vector<PairTable> pair_tables;
 };
 
 struct cgsvmc_ham {

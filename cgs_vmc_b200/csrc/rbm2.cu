@@ -208,28 +208,30 @@ int build_image(cgsvmc_ansatz* a, const Plan& pl, cudaStream_t st) {
   prep_kernel<<<blocks, 128, 0, st>>>(pl.im, p + a->offsets[0], p + a->offsets[1], p + a->offsets[2],
                                       p + a->offsets[3], a->tables);
   a->tables_valid = true;
-  a->pair_valid = false;
+  for (auto& pt : a->pair_tables) pt.valid = false;
   return cuda_fail(cudaGetLastError(), "rbm2 prep launch");
 }
 
-// (Re)builds the bond-pair table when the tables or the Hamiltonian changed.
-int build_pair_table(cgsvmc_ansatz* a, const cgsvmc_ham* h, const Plan& pl, cudaStream_t st) {
-  const size_t bytes = (size_t)2 * h->n_bonds * pl.im.HP * 4;
-  if (a->pair_table_bytes < bytes) {
-    if (a->pair_table != nullptr) {
-      if (int rc = cuda_fail(cudaDeviceSynchronize(), "pair table sync")) return rc;
-      cudaFree(a->pair_table);
-      a->pair_table = nullptr;
-      a->pair_table_bytes = 0;
-    }
-    if (int rc = cuda_fail(cudaMalloc(&a->pair_table, bytes), "pair table alloc")) return rc;
-    a->pair_table_bytes = bytes;
-    a->pair_valid = false;
-  }
-  if (a->pair_valid && a->pair_ham_uid == h->uid) return CGSVMC_OK;
-  pair_prep_kernel<<<2 * h->n_bonds, 128, 0, st>>>(pl.im, a->tables, h->ij, h->n_bonds, a->pair_table);
-  a->pair_valid = true;
-  a->pair_ham_uid = h->uid;
+// The pair-table slot of (ansatz, Hamiltonian); nullptr when the ansatz has
+// already been used with kMaxPairTables other Hamiltonians.
+cgsvmc_ansatz::PairTable* pair_slot(cgsvmc_ansatz* a, const cgsvmc_ham* h, size_t bytes) {
+  for (auto& pt : a->pair_tables)
+    if (pt.ham_uid == h->uid) return pt.bytes >= bytes ? &pt : nullptr;
+  if ((int)a->pair_tables.size() >= cgsvmc_ansatz::kMaxPairTables) return nullptr;
+  cgsvmc_ansatz::PairTable pt;
+  pt.ham_uid = h->uid;
+  if (cudaMalloc(&pt.buf, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  pt.bytes = bytes;
+  a->pair_tables.push_back(pt);
+  return &a->pair_tables.back();
+}
+
+// (Re)builds the bond-pair table of this Hamiltonian when the tables changed.
+int build_pair_table(cgsvmc_ansatz* a, const cgsvmc_ham* h, const Plan& pl,
+                     cgsvmc_ansatz::PairTable* slot, cudaStream_t st) {
+  if (slot->valid) return CGSVMC_OK;
+  pair_prep_kernel<<<2 * h->n_bonds, 128, 0, st>>>(pl.im, a->tables, h->ij, h->n_bonds, slot->buf);
+  slot->valid = true;
   return cuda_fail(cudaGetLastError(), "rbm2 pair prep launch");
 }
 
@@ -281,6 +283,8 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
   static const bool pt_off = getenv("CGSVMC_RBM2_NO_PAIR_TABLE") != nullptr;
   pl.pt = !pt_off && do_eloc && pl.ws && pl.lpw == 8 && nb >= 1 && nb < 16384 &&
           walker_smem_bytes(pl.im, slots, true, do_eloc, nb, do_grad, mc, true) <= (size_t)a->max_smem_optin;
+  cgsvmc_ansatz::PairTable* slot = pl.pt ? pair_slot(a, h, (size_t)2 * nb * pl.im.HP * 4) : nullptr;
+  if (slot == nullptr) pl.pt = false;
   pl.walker_smem = walker_smem_bytes(pl.im, slots, pl.ws, do_eloc, nb, do_grad, mc, pl.pt);
   if (pl.walker_smem > (size_t)a->max_smem_optin) {
     set_error("rbm2: problem does not fit in shared memory");
@@ -288,11 +292,11 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
   }
   if (int rc = build_image(a, pl, st)) return rc;
   if (pl.pt)
-    if (int rc = build_pair_table(a, h, pl, st)) return rc;
+    if (int rc = build_pair_table(a, h, pl, slot, st)) return rc;
   const int64_t P = a->n_params;
   WalkerArgs A;
   memset(&A, 0, sizeof(A));
-  A.pair_table = pl.pt ? a->pair_table : nullptr;
+  A.pair_table = pl.pt ? slot->buf : nullptr;
   A.packed = packed; A.B = B; A.wpc = pl.wpc; A.n_batches = pl.n_batches;
   A.do_eloc = do_eloc ? 1 : 0;
   if (do_eloc) { A.bonds_ij = h->ij; A.bonds_jx = h->jx; A.bonds_jz = h->jz; A.n_bonds = h->n_bonds; }

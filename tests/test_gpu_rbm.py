@@ -578,6 +578,41 @@ def test_batch_step_equals_accumulate_then_sweep(native, n_side, hidden, batch, 
   assert torch.equal(sums1.log_amp, sums2.log_amp)
 
 
+def test_pair_tables_of_two_hamiltonians_do_not_evict_each_other(native):
+  """The walker kernel keeps one bond-pair table per (ansatz, Hamiltonian);
+  a captured graph for one Hamiltonian must stay correct when the same
+  ansatz is evaluated with another one in between (and after a parameter
+  update seen first by the other Hamiltonian)."""
+  from cgs_vmc_b200 import engine
+  from gpu_util import packed_cuda
+  spec = _c2_spec()
+  a, params, cfg = _setup(spec, seed=3, batch=300)
+  ij, jx, jz = lattices.heisenberg_couplings(lattices.square_nn_bonds(6))
+  ham_x = native.Hamiltonian(ij, jx, jz, 36)
+  ij2, jx2, jz2 = lattices.j1j2_couplings(6, 0.5)
+  ham_y = native.Hamiltonian(ij2[72:110], jx2[72:110], jz2[72:110], 36)     # some diagonal bonds
+  s1 = engine.WalkerState(300, 36, seed=5, packed=packed_cuda(cfg))
+  s2 = engine.WalkerState(300, 36, seed=5, packed=packed_cuda(cfg))
+  sums1, sums2 = engine.EnergyGradientSums(a, 300), engine.EnergyGradientSums(a, 300)
+  g = engine.GraphedBatchStep(s1, a, ham_x, sums1, 36)
+  for rep in range(4):
+    if rep == 2:
+      a.params.mul_(0.9)
+    e_y, _ = a.local_energy(ham_y, s2.packed)                 # other Hamiltonian in between
+    g.replay()
+    e2 = sums2.accumulate(ham_x, s2.packed).clone()
+    s2.mc_steps(a, 36)
+    assert torch.equal(s1.packed, s2.packed)
+    assert torch.equal(sums1.weights[1], e2)
+    assert torch.isfinite(e_y).all()
+  fn = lambda c: oansatz.log_amp(spec, [p * 0.9 for p in params], c)
+  cfg_now = torch.from_numpy(bits.unpack(s2.packed.cpu().numpy().view(np.uint64), 36)).to(F64)
+  e_y, _ = a.local_energy(ham_y, s2.packed)
+  eo = hamiltonian.local_energy(cfg_now, ij2[72:110], jx2[72:110], jz2[72:110], fn).numpy()
+  np.testing.assert_allclose(e_y.cpu().numpy(), eo, rtol=2e-4, atol=2e-4)
+  assert torch.equal(sums1.sums, sums2.sums)
+
+
 def test_host_fed_batch_step(native):
   """engine.HostFedBatchStep (pinned host configurations in, energy statistics
   out every batch, gradient sums on request; one graph per buffer slot) gives
