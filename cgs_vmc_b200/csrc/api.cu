@@ -21,9 +21,8 @@ int cuda_fail(cudaError_t err, const char* what) {
 int ensure_scratch(cgsvmc_ansatz* a, size_t bytes) {
   if (bytes <= a->scratch_bytes) return CGSVMC_OK;
   if (a->scratch != nullptr) {
-    // earlier launches may still read the old buffer
-    if (int rc = cuda_fail(cudaDeviceSynchronize(), "scratch sync")) return rc;
-    cudaFree(a->scratch);
+    // earlier launches -- and captured graphs -- may still use the old buffer
+    a->retired.push_back(a->scratch);
     a->scratch = nullptr;
     a->scratch_bytes = 0;
   }
@@ -159,6 +158,7 @@ int cgsvmc_ansatz_create(const cgsvmc_ansatz_desc* desc, cgsvmc_ansatz** out) {
 int cgsvmc_ansatz_destroy(cgsvmc_ansatz* a) {
   if (a == nullptr) return CGSVMC_OK;
   if (a->scratch != nullptr) cudaFree(a->scratch);
+  for (void* p : a->retired) cudaFree(p);
   if (a->tables != nullptr) cudaFree(a->tables);
   if (a->acc_weights != nullptr) cudaFree(a->acc_weights);
   for (auto& pt : a->pair_tables)
@@ -385,8 +385,7 @@ int cgsvmc_accumulate(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_
   const size_t need = (size_t)2 * B * sizeof(float);
   if (am->acc_weights_bytes < need) {
     if (am->acc_weights != nullptr) {
-      if (int rc = cuda_fail(cudaDeviceSynchronize(), "accumulate sync")) return rc;
-      cudaFree(am->acc_weights);
+      am->retired.push_back(am->acc_weights);
       am->acc_weights = nullptr;
       am->acc_weights_bytes = 0;
     }

@@ -24,6 +24,9 @@ struct cgsvmc_ansatz {
   int max_smem_optin = 0;          // bytes
   float* scratch = nullptr;        // owned device scratch (gradient partials ...)
   size_t scratch_bytes = 0;
+  // buffers outgrown by a later, larger request: kept until the handle is
+  // destroyed because captured CUDA graphs may still point at them
+  std::vector<void*> retired;
   float* tables = nullptr;         // owned: derived parameter image of the rbm2 kernels
   size_t tables_bytes = 0;
   bool tables_valid = false;       // tables match the bound parameters

@@ -553,11 +553,14 @@ __device__ __forceinline__ unsigned int mc_sweep(const Tables& t, const Image& i
                                                  uint64_t step0) {
   constexpr int KJ = 32 / LPW * KJV;
   float tq[KJ];
-  // an accepted move scales p_j by at most 2^(8 log2(e) max|W|); keep the
-  // growth between renormalisations below 2^30
-  // (2^30 per element: the ratio loop multiplies four terms before its lg2)
+  // an accepted move scales p_j by at most 2^(8 log2(e) max|W|) = 2^wbits; the
+  // window keeps the worst-case growth between renormalisations below 2^96
+  // (p_j itself cannot overflow).  The four-term products of the ratio loop
+  // could still leave the float32 range in that worst case -- every hidden
+  // unit pushed the same way by every move -- which the non-finite check below
+  // catches and repairs; typical growth is a bounded random walk far below it.
   const float wbits = 11.541560327111707f * ld1<WS>(t.a0 + 1);
-  const int renorm_window = max(1, min(32, (int)((30.f - wbits) / (wbits + 1e-6f))));
+  const int renorm_window = max(1, min(32, (int)((96.f - wbits) / (wbits + 1e-6f))));
   unsigned int n_acc = 0;
   int n_up = 0;
 #pragma unroll
