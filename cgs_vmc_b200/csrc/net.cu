@@ -819,6 +819,12 @@ mlp_grad_kernel(NetDesc d, const uint64_t* __restrict__ packed, const float* __r
   const int offW = offOnes + TS;               // K weight rows
   const int offEnd = offW + K * TS;
   uint64_t* cfg = reinterpret_cast<uint64_t*>(smem + (offEnd + 3) / 4 * 4);
+  // one layer's weight matrix staged in shared memory (see Mlp::stage): the
+  // layers of the forward AND backward pass would otherwise be streamed
+  // through L1 by every warp (ncu: long-scoreboard 7.6 per issue, issue-active 15 %)
+  float* wbuf = d.stage_weights
+      ? reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(cfg + (size_t)T * d.NW) + 15) / 16 * 16)
+      : nullptr;
   auto Hrow = [&](int l, int i) { return l == 0 ? offH0 + i * TS : offHl + ((l - 1) * D + i) * TS; };
 
   // decode this thread's entries into (A row, B row) shared-memory offsets
@@ -884,19 +890,31 @@ mlp_grad_kernel(NetDesc d, const uint64_t* __restrict__ packed, const float* __r
     // forward, keeping every layer's output
     int din = N;
     for (int l = 0; l < L; ++l) {
-      M::template layer<0>(d, d.w[l], d.b[l], din, D, d.act, smem + Hrow(l, 0), smem + Hrow(l + 1, 0), nullptr);
+      if (wbuf != nullptr)
+        M::template layer<0, true>(d, M::stage(d.w[l], din, D, wbuf), d.b[l], din, D, d.act,
+                                   smem + Hrow(l, 0), smem + Hrow(l + 1, 0), nullptr);
+      else
+        M::template layer<0>(d, d.w[l], d.b[l], din, D, d.act, smem + Hrow(l, 0), smem + Hrow(l + 1, 0), nullptr);
       __syncthreads();
       din = D;
     }
     if (rbm) {
-      M::template layer<3>(d, d.w[L], d.b[L], din, D, 0, smem + Hrow(L, 0), smem + offDH, nullptr);
+      if (wbuf != nullptr)
+        M::template layer<3, true>(d, M::stage(d.w[L], din, D, wbuf), d.b[L], din, D, 0, smem + Hrow(L, 0),
+                                   smem + offDH, nullptr);
+      else
+        M::template layer<3>(d, d.w[L], d.b[L], din, D, 0, smem + Hrow(L, 0), smem + offDH, nullptr);
       __syncthreads();
     }
     // backward: delta of the top hidden layer, then down to hidden layer 0
     if (L >= 1) {
       float* top = smem + offDL + (L - 1) * D * TS;
       if (rbm) {
-        M::template layer<4>(d, d.wt[L], nullptr, D, D, d.act, smem + offDH, top, nullptr, smem + Hrow(L, 0));
+        if (wbuf != nullptr)
+          M::template layer<4, true>(d, M::stage(d.wt[L], D, D, wbuf), nullptr, D, D, d.act, smem + offDH, top,
+                                     nullptr, smem + Hrow(L, 0));
+        else
+          M::template layer<4>(d, d.wt[L], nullptr, D, D, d.act, smem + offDH, top, nullptr, smem + Hrow(L, 0));
       } else {
         for (int e = threadIdx.x; e < D * T; e += kThreads) {
           const int i = e / T, t = e - i * T;
@@ -905,8 +923,13 @@ mlp_grad_kernel(NetDesc d, const uint64_t* __restrict__ packed, const float* __r
       }
       __syncthreads();
       for (int l = L - 1; l >= 1; --l) {
-        M::template layer<4>(d, d.wt[l], nullptr, D, D, d.act, smem + offDL + l * D * TS,
-                             smem + offDL + (l - 1) * D * TS, nullptr, smem + Hrow(l, 0));
+        if (wbuf != nullptr)
+          M::template layer<4, true>(d, M::stage(d.wt[l], D, D, wbuf), nullptr, D, D, d.act,
+                                     smem + offDL + l * D * TS, smem + offDL + (l - 1) * D * TS, nullptr,
+                                     smem + Hrow(l, 0));
+        else
+          M::template layer<4>(d, d.wt[l], nullptr, D, D, d.act, smem + offDL + l * D * TS,
+                               smem + offDL + (l - 1) * D * TS, nullptr, smem + Hrow(l, 0));
         __syncthreads();
       }
     }
@@ -1276,10 +1299,12 @@ int net_grad(cgsvmc_ansatz* a, const uint64_t* packed, const float* weights, int
     smem = (size_t)T * per_cfg + 2 * (size_t)T * 4 + fixed + (size_t)T * d.NW * 8 + 32;
   } else {
     const bool rbm = d.kind == CGSVMC_ANSATZ_RBM;
+    const size_t stage_bytes = (size_t)std::max(d.D, d.N) * d.D * 4 + 16;
     auto need = [&](int ts, int t) {
       return ((size_t)d.N + 2 * (size_t)d.L * d.D + (rbm ? d.D : 0) + 1 + 2) * ts * 4 + 16 +
-             (size_t)t * d.NW * 8;
+             (size_t)t * d.NW * 8 + (d.stage_weights ? stage_bytes : 0);
     };
+    if (d.stage_weights && (int64_t)need(36, 32) > a->max_smem_optin - 1024) d.stage_weights = 0;
     if ((int64_t)need(36, 32) > a->max_smem_optin - 1024) tw4 = false;
     T = tw4 ? 32 : 8;
     smem = need(tw4 ? 36 : 12, T);
