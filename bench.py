@@ -322,6 +322,18 @@ def run_ours(args, rank, world, local_rank):
   if world > 1:
     dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
   e2e_s = float(e2e_total.item())
+  # pinned host -> device rate of this box for the 1.18 MB configuration tensor
+  # (explains how far e2e sits above the device-resident step)
+  dst_probe = torch.empty_like(host_cfg, device=dev)
+  c0, c1 = ev(), ev()
+  dst_probe.copy_(host_cfg, non_blocking=True)
+  torch.cuda.synchronize()
+  c0.record()
+  for _ in range(20):
+    dst_probe.copy_(host_cfg, non_blocking=True)
+  c1.record()
+  torch.cuda.synchronize()
+  h2d_gbps = 20 * host_cfg.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
   # the same with the host holding the walkers in the library's bit-packed layout
   # (8 B per walker instead of 144 B): shows how much of e2e is the PCIe upload
   host_packed = state.packed.cpu().pin_memory()
@@ -430,6 +442,7 @@ def run_ours(args, rank, world, local_rank):
               'd2h': 'energy statistics every step; the [2, P] gradient sums once per epoch of %d steps '
                      '(training.py:562-568 reads them once per epoch)' % EPOCH_BATCHES,
               'input': 'float32 [B, N] +-1 configurations (the reference layout) from pinned host memory',
+              'h2d_gbps_this_box': h2d_gbps,
               'packed_host_input': {
                   'value': walkers_total * SWEEP_STEPS * args.steps / e2e_packed_s,
                   'ms_per_step': e2e_packed_s / args.steps * 1e3,
