@@ -28,13 +28,20 @@
  * Amplitudes: all entry points work with z(sigma) = log psi(sigma) + shift,
  * i.e. the tensor the reference hands to add_exp_normalization + tf.exp
  * (wavefunctions.py:206-232); psi = exp(z - exp_norm_shift) is formed by the
- * host wrapper.  The in-scope ansaetze (output_activation = exp) are positive.
+ * host wrapper.  With output_activation = exp the amplitude is positive and
+ * the fused sampler / local-energy / estimator entry points apply; signed
+ * output activations and sum / difference / product composites evaluate
+ * cgsvmc_log_amp of their parts and use the amplitude-agnostic entry points
+ * (cgsvmc_propose_exchange, cgsvmc_accept_exchange,
+ * cgsvmc_local_energy_from_amps) near the end of this header.
  *
  * Flat parameter layout (float32, row-major, Sonnet shapes):
  *   fully_connected : W_1[in,out], b_1[out], ..., W_L, b_L, W_out[in,1], b_out[1]
  *   rbm             : a[N], a0[1], (W_l, b_l) hidden layers ..., W[in,H], c[H]
  *   conv_1d         : per layer w[k, cin, cout], b[cout]
  *   conv_2d         : per layer w[k, k, cin, cout], b[cout]
+ *   res_net_1d / 2d : initial conv w[k(, k), 1, F], b[F]; per block first_conv
+ *                     w[k(, k), F, F], b[F], second_conv w[k(, k), F, F], b[F]
  */
 #ifndef CGSVMC_H_
 #define CGSVMC_H_
