@@ -308,11 +308,13 @@ struct Conv {
   // forward pass): no store, z[t] += sum of outputs.  MODE 2: backward-data,
   // flipped taps (weights must be the [tap][cout][cin] transpose), post =
   // multiply with activate_grad(h_prev) read from `aux`.
-  // `res` (MODE 0 and 2): tensor of the output's shape added to the result --
-  // the skip connection of a residual block (may alias `out`: every element is
-  // read and written by the same thread).  MODE 2 with aux == nullptr skips
-  // the activation-gradient factor.
-  template <int MODE>
+  // RES (MODE 0 and 2): `res`, a tensor of the output's shape, is added to the
+  // result -- the skip connection of a residual block (may alias `out`: every
+  // element is read and written by the same thread).  ACTGRAD = false: MODE 2
+  // without the activation-gradient factor.
+  // RES / ACTGRAD are compile-time so that the plain conv ansaetze keep their
+  // original inner loops.
+  template <int MODE, bool RES = false, bool ACTGRAD = true>
   __device__ static void layer(const NetDesc& d, const float* __restrict__ W,
                                const float* __restrict__ bias, int cin, int cout, int act,
                                bool apply_act, int T, const float* in, float* out, float* z,
@@ -364,12 +366,12 @@ struct Conv {
               zsum += v;
             } else if (MODE == 2) {
               const size_t o = ((size_t)t * cout + c0 + c) * npos + pos;
-              if (aux != nullptr) v *= activate_grad(act, aux[o]);
-              out[o] = res != nullptr ? v + res[o] : v;
+              if (ACTGRAD) v *= activate_grad(act, aux[o]);
+              out[o] = RES ? v + res[o] : v;
             } else {
               const size_t o = ((size_t)t * cout + c0 + c) * npos + pos;
               if (apply_act) v = activate(act, v);
-              out[o] = res != nullptr ? v + res[o] : v;
+              out[o] = RES ? v + res[o] : v;
             }
           }
         }
@@ -416,7 +418,7 @@ struct Conv {
       for (int l = 1; l < d.L; l += 2) {
         layer<0>(d, d.w[l], d.b[l], d.C, d.C, d.act, true, T, x, h, z, xi, yi, nullptr);
         __syncthreads();
-        layer<0>(d, d.w[l + 1], d.b[l + 1], d.C, d.C, d.act, false, T, h, x, z, xi, yi, nullptr, x);
+        layer<0, true>(d, d.w[l + 1], d.b[l + 1], d.C, d.C, d.act, false, T, h, x, z, xi, yi, nullptr, x);
         __syncthreads();
       }
       // per-position channel sums (into h, free now), then the fixed-order reduction
@@ -457,6 +459,7 @@ struct MlpNet {
     Mlp<TW>::forward(d, cfg, smem, z);
   }
   __device__ static void prepare(const NetDesc& d, float* smem) { Mlp<TW>::prepare(d, smem); }
+  static constexpr int kMinCtas = 0;  // residency left to ptxas
 };
 struct ConvNet {
   __host__ static size_t fwd_smem(const NetDesc& d, int T) { return Conv::forward_smem_bytes(d, T); }
@@ -464,6 +467,7 @@ struct ConvNet {
     Conv::forward(d, cfg, T, smem, z);
   }
   __device__ static void prepare(const NetDesc&, float*) {}
+  static constexpr int kMinCtas = 2;  // conv_tile() budgets 96 KB of shared memory per CTA
 };
 
 // Dynamic shared memory layout of the non-grad kernels:
@@ -486,7 +490,7 @@ __host__ inline size_t carve_bytes(size_t n, size_t elem) { return (n * elem + 1
 // K1: log-amplitudes of consecutive walkers
 // ---------------------------------------------------------------------------
 template <class NET>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, NET::kMinCtas)
 net_log_amp_kernel(NetDesc d, int T, size_t fwd_bytes, const uint64_t* __restrict__ packed,
                    int64_t B, float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
@@ -522,7 +526,7 @@ __device__ __forceinline__ int kth_set_bit_serial(const uint64_t* words, int nw,
 }
 
 template <class NET>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, NET::kMinCtas)
 net_mc_kernel(NetDesc d, int T, size_t fwd_bytes, uint64_t* __restrict__ packed, int64_t B,
               int n_steps, uint64_t seed, uint64_t walker0, uint64_t step0,
               const uint64_t* __restrict__ step0_dev, unsigned long long* accept_count,
@@ -601,7 +605,7 @@ net_mc_kernel(NetDesc d, int T, size_t fwd_bytes, uint64_t* __restrict__ packed,
 
 // Replay step: uniforms supplied by the caller (graph_builders.py:59-79).
 template <class NET>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, NET::kMinCtas)
 net_replay_kernel(NetDesc d, int T, size_t fwd_bytes, uint64_t* __restrict__ packed, int64_t B,
                   const float* __restrict__ u_sites, const float* __restrict__ u_acc,
                   int32_t* down_out, int32_t* up_out, float* log_ratio_out, uint8_t* accept_out) {
@@ -675,7 +679,7 @@ net_replay_kernel(NetDesc d, int T, size_t fwd_bytes, uint64_t* __restrict__ pac
 constexpr int kElocWalkers = 8;
 
 template <class NET>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, NET::kMinCtas)
 net_eloc_kernel(NetDesc d, int T, size_t fwd_bytes, const int2* __restrict__ bonds_ij,
                 const float* __restrict__ bonds_jx, const float* __restrict__ bonds_jz,
                 int n_bonds, const uint64_t* __restrict__ packed, int64_t B,
@@ -966,7 +970,7 @@ mlp_grad_kernel(NetDesc d, const uint64_t* __restrict__ packed, const float* __r
 }
 
 template <int K>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 1)  // one CTA per SM (shared memory): no register cap, no spills
 conv_grad_kernel(NetDesc d, int T, const uint64_t* __restrict__ packed,
                  const float* __restrict__ weights, int64_t B, int64_t walkers_per_cta, int64_t P,
                  float* __restrict__ partials) {
@@ -1018,8 +1022,8 @@ conv_grad_kernel(NetDesc d, int T, const uint64_t* __restrict__ packed,
         Conv::layer<0>(d, d.w[l], d.b[l], C, C, d.act, true, T, H(l), H(l + 1), nullptr, xi, yi, nullptr);
         __syncthreads();
         if (l + 2 < L) {
-          Conv::layer<0>(d, d.w[l + 1], d.b[l + 1], C, C, d.act, false, T, H(l + 1), H(l + 2), nullptr,
-                         xi, yi, nullptr, H(l));
+          Conv::layer<0, true>(d, d.w[l + 1], d.b[l + 1], C, C, d.act, false, T, H(l + 1), H(l + 2), nullptr,
+                               xi, yi, nullptr, H(l));
           __syncthreads();
         }
       }
@@ -1031,8 +1035,8 @@ conv_grad_kernel(NetDesc d, int T, const uint64_t* __restrict__ packed,
         Conv::layer<2>(d, d.wt[l], nullptr, C, C, d.act, false, T, DL + (size_t)l * szC,
                        DL + (size_t)(l - 1) * szC, nullptr, xib, yib, H(l));
         __syncthreads();
-        Conv::layer<2>(d, d.wt[l - 1], nullptr, C, C, d.act, false, T, DL + (size_t)(l - 1) * szC,
-                       DL + (size_t)(l - 2) * szC, nullptr, xib, yib, nullptr, DL + (size_t)l * szC);
+        Conv::layer<2, true, false>(d, d.wt[l - 1], nullptr, C, C, d.act, false, T, DL + (size_t)(l - 1) * szC,
+                                    DL + (size_t)(l - 2) * szC, nullptr, xib, yib, nullptr, DL + (size_t)l * szC);
         __syncthreads();
       }
     } else {
