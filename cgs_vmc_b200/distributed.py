@@ -4,7 +4,8 @@ Walkers are independent Markov chains: rank r owns the contiguous block of
 global walker ids [r * B/G, (r + 1) * B/G); parameters are replicated; the only
 exchange is one all-reduce(sum) of the packed float32 buffer
   [ sum_b O_b (P) | sum_b E_b O_b (P) | sum E, sum E^2, n, 0 ]
-per optimisation step (or a P-vector + scalar for the supervised loss).
+per optimisation step (or a P-vector + scalar for the supervised loss), carried
+in float64 so the energy statistics stay exact.
 Works with any initialised torch.distributed backend (nccl on the GPUs, gloo
 in the CPU tests of the host logic).
 """
@@ -35,24 +36,44 @@ def shard(batch_size):
 
 
 def pack_sums(sums, stats):
-  """[K, P] float32 sums + [4] float64 statistics -> one float32 buffer."""
-  return torch.cat([sums.reshape(-1), stats.to(torch.float32)])
+  """[K, P] float32 sums + [4] float64 statistics -> one FLOAT64 buffer
+  [K * P + 4].  The statistics (sum E, sum E^2, n) stay exact in double
+  (a float32 payload loses the walker count above 2^24 and the variance long
+  before); the payload is latency-bound either way (86 KB at C2)."""
+  return torch.cat([sums.reshape(-1).to(torch.float64), stats.to(torch.float64)])
 
 
 def unpack_sums(payload, sums, stats):
   n = sums.numel()
   sums.copy_(payload[:n].view_as(sums))
-  stats.copy_(payload[n:n + stats.numel()].to(stats.dtype))
+  stats.copy_(payload[n:n + stats.numel()])
 
 
-def allreduce_sums(sums, stats):
-  """In-place all-reduce(sum) of the estimator accumulators; a no-op on one
-  rank."""
+def allreduce_sums(sums, stats, out_sums=None, out_stats=None):
+  """All-reduce(sum) of the estimator accumulators over the walker shards
+  (training.py:550-564 sees the whole batch).  The totals go to `out_sums` /
+  `out_stats` when given -- the local accumulators then stay local, so further
+  batches can be accumulated and reduced again without double counting -- and
+  in place otherwise.  Returns (sums, stats) holding the totals; a no-op on
+  one rank."""
+  out_sums = sums if out_sums is None else out_sums
+  out_stats = stats if out_stats is None else out_stats
   if world_size() == 1:
-    return
+    if out_sums is not sums:
+      out_sums.copy_(sums)
+      out_stats.copy_(stats)
+    return out_sums, out_stats
   payload = pack_sums(sums, stats)
   dist.all_reduce(payload, op=dist.ReduceOp.SUM)
-  unpack_sums(payload, sums, stats)
+  unpack_sums(payload, out_sums, out_stats)
+  return out_sums, out_stats
+
+
+def broadcast_(tensor, src=0):
+  """Rank `src`'s values on every rank (parameter replicas start identical)."""
+  if world_size() > 1:
+    dist.broadcast(tensor, src=src)
+  return tensor
 
 
 def allreduce_(tensor, op='sum'):

@@ -12,6 +12,7 @@ single step for drop-in callers.
 import collections
 import copy
 import math
+import types
 
 import torch
 
@@ -89,6 +90,15 @@ def create_sgd_optimizer(hparams):
   return OPTIMIZERS[hparams.optimizer](hparams)
 
 
+def _update_norm_op(wavefunction, configs):
+  """wavefunction.update_norm(wavefunction(configs)) of training.py:584, 377,
+  726 with the batch maximum taken in the log domain."""
+  if not wavefunction.fast_path:
+    return wavefunction.update_norm(lambda: wavefunction(configs))
+  return wavefunction.update_norm(lambda: wavefunction(configs),
+                                  log_amplitudes=lambda: wavefunction.log_amplitude(configs))
+
+
 def _epoch_increment():
   def run():
     graph_builders.get_or_create_num_epochs().add_(1)
@@ -108,6 +118,8 @@ class _Model:
     self.fast = bool(wavefunction.fast_path)
     self.leaves = wavefunction.leaves()
     self.leaf_params = [leaf.native().params for leaf in self.leaves]
+    for params in self.leaf_params:      # replicas start from rank 0's parameters
+      distributed.broadcast_(params)
     self.num_params = sum(int(p.numel()) for p in self.leaf_params)
     self.device = self.leaf_params[0].device
     self.optimizers = ([create_sgd_optimizer(hparams) for _ in self.leaves]
@@ -194,23 +206,38 @@ class EnergyGradientOptimizer(WavefunctionOptimizer):
     ham = hamiltonian.native(n_sites)
     sums = (engine.EnergyGradientSums(ansatz, local_batch) if model.fast
             else _GenericEnergyGradientSums(model, hamiltonian, configs))
+    # The walker-sharded totals live in their own buffers: the local
+    # accumulators stay local, so metrics / apply_gradients may be run in the
+    # middle of an epoch and accumulation continued (training.py:550-564 are
+    # running means over every accumulate call since the last reset).
     state = {'reduced': False}
+    if distributed.world_size() > 1:
+      total = types.SimpleNamespace(sums=torch.zeros_like(sums.sums),
+                                    stats=torch.zeros_like(sums.stats))
+    else:
+      total = sums
 
     def accumulate():                      # training.py:539-558, one batch
       sums.accumulate(ham, configs.packed)
+      state['reduced'] = False
 
     def reduce_once():
-      if not state['reduced']:
-        distributed.allreduce_sums(sums.sums, sums.stats)
-        state['reduced'] = True
+      if total is not sums and not state['reduced']:
+        distributed.allreduce_sums(sums.sums, sums.stats, total.sums, total.stats)
+      state['reduced'] = True
+
+    def global_gradient():                 # training.py:562-564 on the all-reduced sums
+      nb = float(sums.n_batches)
+      mean_e = (total.stats[0] / total.stats[2]).float()
+      return total.sums[1] / nb - mean_e * total.sums[0] / nb
 
     def apply_gradients():                 # training.py:562-567
       reduce_once()
-      model.apply_gradients(sums.gradient())
+      model.apply_gradients(global_gradient())
 
     def metrics():                         # mean_energy, training.py:555, 582
       reduce_once()
-      return float(sums.mean_energy().item())
+      return float((total.stats[0] / total.stats[2]).item())
 
     def reset():                           # training.py:568
       sums.reset()
@@ -236,7 +263,7 @@ class EnergyGradientOptimizer(WavefunctionOptimizer):
         mc_step=mc_step, acc_rate=acc_rate,
         metrics=Op(metrics, 'mean_energy'),
         epoch_increment=_epoch_increment(),
-        update_wf_norm=wavefunction.update_norm(lambda: wavefunction(configs)))
+        update_wf_norm=_update_norm_op(wavefunction, configs))
 
   def run_optimization_epoch(self, train_ops, session, hparams, epoch_number=0):
     """training.py:589-623."""
@@ -395,7 +422,7 @@ class LogOverlapSWO:
         apply_gradients=Op(apply_gradients, 'apply_gradients'),
         reset_gradients=Op(sums.reset, 'reset_gradients'),
         mc_step=mc_step, acc_rate=acc_rate, metrics=None,
-        update_wf_norm=wavefunction.update_norm(lambda: wavefunction(configs)),
+        update_wf_norm=_update_norm_op(wavefunction, configs),
         epoch_increment=_epoch_increment())
 
   def run_optimization_epoch(self, train_ops, session, hparams, epoch_number):
@@ -522,7 +549,7 @@ class LogOverlapImaginaryTimeSWO(WavefunctionOptimizer):
         update_supervisor=wavefunctions.module_transfer_ops(wavefunction, wf_omega),
         update_normalization=None,
         epoch_increment=_epoch_increment(),
-        update_wf_norm=wavefunction.update_norm(lambda: wavefunction(configs)))
+        update_wf_norm=_update_norm_op(wavefunction, configs))
 
   def run_optimization_epoch(self, train_ops, session, hparams, epoch_number=0):
     """training.py:729-778."""

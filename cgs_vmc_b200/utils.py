@@ -30,6 +30,15 @@ class HParams:
       value = int(value)
     elif isinstance(old, float):
       value = float(value)
+    elif isinstance(old, (list, tuple)):
+      # tf HParams keeps the list type of the default: a scalar override of a
+      # list-valued hyper-parameter is an error there, as is a wrong length for
+      # the fixed-size pairs (composite_wavefunction_types, ...)
+      if not isinstance(value, (list, tuple)):
+        raise ValueError('Must pass a list for multi-valued parameter: %s' % name)
+      if isinstance(old, tuple) and len(value) != len(old):
+        raise ValueError('Hyperparameter %s takes %d values, got %d' % (name, len(old), len(value)))
+      value = type(old)(value)
     setattr(self, name, value)
 
   def override_from_dict(self, values):
@@ -52,12 +61,22 @@ class HParams:
     for item in items:
       name, _, raw = item.partition('=')
       name, raw = name.strip(), raw.strip()
-      try:
-        value = ast.literal_eval(raw)
-      except (ValueError, SyntaxError):
-        value = raw
-      self.set_hparam(name, value)
+      self.set_hparam(name, self._parse_value(raw))
     return self
+
+  @staticmethod
+  def _parse_value(raw):
+    """A number, a bare string, or a bracketed list of either
+    (tf.contrib.training.HParams.parse takes `x=[rbm,fully_connected]` with
+    unquoted strings)."""
+    try:
+      return ast.literal_eval(raw)
+    except (ValueError, SyntaxError):
+      pass
+    if len(raw) >= 2 and raw[0] in '[(' and raw[-1] in '])':
+      inner = raw[1:-1].strip()
+      return [HParams._parse_value(item.strip()) for item in inner.split(',')] if inner else []
+    return raw
 
   def values(self):
     return {k: getattr(self, k) for k in self._names}

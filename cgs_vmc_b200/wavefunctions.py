@@ -27,6 +27,21 @@ from .session import Op
 
 _UNBUILT = ('mps', 'pbdg', 'fully_connected_nnb', 'ed_vector', 'gnn')
 
+# The reference initialises every module from TensorFlow's unseeded random
+# stream: two wavefunctions never start with the same parameters.  Here an
+# unseeded wavefunction draws its initial parameters from a stream keyed by
+# (torch.initial_seed(), number of wavefunctions initialised so far in this
+# process): distinct per instance, identical on every rank of a sharded run
+# (all ranks build the same wavefunctions in the same order; the optimizers
+# additionally broadcast rank 0's parameters, training._Model).
+_INIT_COUNTER = [0]
+
+
+def _next_init_seed():
+  _INIT_COUNTER[0] += 1
+  mixed = (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + _INIT_COUNTER[0] * 0xD1B54A32D192ED03)
+  return mixed & 0x7FFFFFFFFFFFFFFF
+
 
 def _sonnet_init(shapes, generator):
   """Sonnet v1 defaults: weights truncated normal (+-2 sigma), sigma =
@@ -82,8 +97,7 @@ class Wavefunction:
       self._n_sites = int(n_sites)
       self._native = _native.Ansatz(**self._native_args(self._n_sites))
       gen = torch.Generator()
-      if self._seed is not None:
-        gen.manual_seed(int(self._seed))
+      gen.manual_seed(int(self._seed) if self._seed is not None else _next_init_seed())
       shapes = self._param_shapes(self._n_sites)
       init = _sonnet_init(shapes, gen)
       self._native.set_params(torch.cat([t.reshape(-1) for t in init]))
@@ -167,28 +181,44 @@ class Wavefunction:
     return new
 
   # ---- normalisation (wavefunctions.py:206-288) ---------------------------
-  def normalize_batch(self, batch_of_amplitudes, max_value=1e10):
+  def _global_log_max(self, batch_of_amplitudes, log_amplitudes):
+    """log of the largest amplitude over the WHOLE batch: tf.reduce_max of
+    wavefunctions.py:255 / 283 runs over every walker, so under walker
+    sharding the local maximum is all-reduced (MAX) -- every rank then applies
+    the same shift.  With `log_amplitudes` (a tensor or callable giving
+    log psi = z - shift) the maximum is taken in the log domain, where
+    exp overflow cannot turn the shift into inf."""
+    from . import distributed
+    if log_amplitudes is not None:
+      logs = log_amplitudes() if callable(log_amplitudes) else log_amplitudes
+      log_max = torch.as_tensor(logs).max().reshape(1).double()
+    else:
+      amps = batch_of_amplitudes() if callable(batch_of_amplitudes) else batch_of_amplitudes
+      log_max = torch.log(torch.as_tensor(amps).max()).reshape(1).double()
+    distributed.allreduce_(log_max, op='max')
+    return float(log_max.item())
+
+  def normalize_batch(self, batch_of_amplitudes, max_value=1e10, log_amplitudes=None):
+    """Op mapping the batch onto (0, max_value] (wavefunctions.py:234-257)."""
     if self._exp_norm_shift is None and self._native is None:
       return None
 
     def run():
-      log_max = float(torch.log(torch.as_tensor(batch_of_amplitudes()
-                                if callable(batch_of_amplitudes)
-                                else batch_of_amplitudes).max()))
+      log_max = self._global_log_max(batch_of_amplitudes, log_amplitudes)
       self._exp_norm_shift += log_max - math.log(max_value)
       return self._exp_norm_shift
     return Op(run, 'normalize_batch')
 
-  def update_norm(self, batch_of_amplitudes, max_value=1e10):
+  def update_norm(self, batch_of_amplitudes, max_value=1e10, log_amplitudes=None):
     """Op that raises exp_norm_shift iff max psi > max_value
     (wavefunctions.py:261-288).  `batch_of_amplitudes` may be a tensor or a
-    callable returning the current amplitudes (graph semantics)."""
+    callable returning the current amplitudes (graph semantics);
+    `log_amplitudes` optionally gives log psi of the same batch."""
     if not self.fast_path:          # no exp_norm_shift without the exp output
       return None
 
     def run():
-      amps = batch_of_amplitudes() if callable(batch_of_amplitudes) else batch_of_amplitudes
-      log_max = float(torch.log(torch.as_tensor(amps).max()))
+      log_max = self._global_log_max(batch_of_amplitudes, log_amplitudes)
       max_log = math.log(max_value)
       if log_max > max_log:
         self._exp_norm_shift += log_max - max_log
@@ -222,6 +252,11 @@ def module_transfer_ops(source_module, target_module):
       raise ValueError('`target_module` does not have the same structure as source.')
     for a, b in zip(src, dst):
       b.native().params.copy_(a.native().params)
+      # The reference copies the trainable variables only and leaves the copy's
+      # exp_norm_shift at its initial -10.  psi_target / psi then carries the
+      # constant factor e^(shift - shift_copy), which cancels in the log-overlap
+      # gradient; copying the shift as well keeps that ratio O(1) in float32.
+      b._exp_norm_shift = a._exp_norm_shift
   return Op(run, 'module_transfer')
 
 
@@ -326,7 +361,7 @@ class _Composite(Wavefunction):
     logabs, sign = self.amplitudes(graph_builders.as_packed(inputs, n))
     return sign * torch.exp(logabs)
 
-  def update_norm(self, batch_of_amplitudes, max_value=1e10):
+  def update_norm(self, batch_of_amplitudes, max_value=1e10, log_amplitudes=None):
     return None          # no exp_norm_shift of its own (wavefunctions.py:261-270)
 
   def __deepcopy__(self, memo):

@@ -69,3 +69,43 @@ def lookup_amplitude(basis, vector):
                     for k in keys])
     return torch.from_numpy(out)
   return psi_fn
+
+
+def configs_of(basis, n_sites):
+  """float64 [dim, N] of +-1 for the bit patterns of `basis` (bit i = site i up)."""
+  bits = (np.asarray(basis)[:, None] >> np.arange(n_sites)[None, :]) & 1
+  return 2.0 * bits.astype(np.float64) - 1.0
+
+
+def exact_expectation(n_sites, bonds_ij, jx, jz, psi_fn):
+  """<psi|H|psi> / <psi|psi> over the Sz = 0 sector: what the mean local value
+  of evaluation.py:98-102 converges to when the walkers sample |psi|^2.
+  psi_fn maps float64 configurations [dim, N] to amplitudes [dim]."""
+  basis, h = hamiltonian_matrix(n_sites, bonds_ij, jx, jz)
+  psi = np.asarray(psi_fn(configs_of(basis, n_sites)), dtype=np.float64)
+  return float(psi @ (h @ psi) / (psi @ psi))
+
+
+def exact_acceptance_rate(n_sites, psi_fn):
+  """Stationary acceptance probability of the exchange sampler of
+  graph_builders.py:54-89: a uniformly random up site and a uniformly random
+  down site are exchanged and the move is accepted with min(1, (psi'/psi)^2):
+    A = sum_s pi(s) / (n_up n_dn) sum_{u, d} min(1, pi(s^{ud}) / pi(s))."""
+  basis = sz0_basis(n_sites)
+  index = {int(s): k for k, s in enumerate(basis)}
+  psi = np.asarray(psi_fn(configs_of(basis, n_sites)), dtype=np.float64)
+  pi = psi * psi / np.sum(psi * psi)
+  n_up = n_sites - n_sites // 2
+  n_dn = n_sites // 2
+  total = 0.0
+  for k, s in enumerate(basis):
+    s = int(s)
+    ups = [i for i in range(n_sites) if (s >> i) & 1]
+    dns = [i for i in range(n_sites) if not (s >> i) & 1]
+    acc = 0.0
+    for u in ups:
+      for d in dns:
+        t = s ^ ((1 << u) | (1 << d))
+        acc += min(1.0, pi[index[t]] / pi[k]) if pi[k] > 0 else 0.0
+    total += pi[k] * acc / (n_up * n_dn)
+  return float(total)

@@ -223,8 +223,10 @@ def make_case(name, overrides, lattice, seed):
         [g.detach().reshape(-1) for g in ops.apply_gradients]).numpy()
     out['eg_mean_energy'] = np.float32(ops.metrics.detach())
 
-  # (5) SWO loss + gradient, training.py:141-189
-  if name != 'conv2d_10x10':
+  # (5) SWO loss + gradient, training.py:141-189.  Not for N >= 64: the
+  # reference's own np.sqrt(2**n_sites) (training.py:170) raises TypeError once
+  # 2**N no longer fits a 64-bit integer, so SWO cannot run there at all.
+  if name != 'conv2d_10x10' and n < 64:
     target = wavefunctions.build_wavefunction(hp)
     target(dummy)
     tparams = oansatz.init_params(spec, seed=seed + 1000, bias_scale=0.1)
@@ -270,7 +272,26 @@ RESNET_CASES = {
 }
 
 
+# Round 2: the C3 network (10x10, 5 layers x 16 filters x 5x5) with the energy
+# gradient and the SWO gradient recorded from the reference (the frozen
+# conv2d_10x10 case skips both).  Uniform NN couplings, because the reference's
+# HeisenbergHamiltonian -- which EnergyGradientOptimizer needs -- has a single
+# (j_x, j_z) (operators.py:215-225).  `python tests/golden/make_golden.py c3grad`.
+C3GRAD_CASES = {
+    'conv2d_10x10_grad': (dict(wavefunction_type='conv_2d', num_sites=100, size_x=10, size_y=10,
+                               num_conv_layers=5, num_conv_filters=16, kernel_size=5), 'square'),
+}
+BATCH['conv2d_10x10_grad'] = 2
+
+
 def main():
+  if len(sys.argv) > 1 and sys.argv[1] == 'c3grad':
+    for k, (name, (overrides, lattice)) in enumerate(sorted(C3GRAD_CASES.items())):
+      out = make_case(name, overrides, lattice, seed=900 + k)
+      path = os.path.join(HERE, name + '.npz')
+      np.savez_compressed(path, **out)
+      print('%-22s %7.1f KB  keys=%d' % (name, os.path.getsize(path) / 1024.0, len(out)))
+    return
   if len(sys.argv) > 1 and sys.argv[1] == 'resnet':
     for k, (name, (overrides, lattice)) in enumerate(sorted(RESNET_CASES.items())):
       out = make_case(name, overrides, lattice, seed=700 + k)

@@ -172,17 +172,80 @@ def test_supervised_training_reduces_loss():
 
 
 def test_monte_carlo_operator_evaluator():
+  """MonteCarloOperatorEvaluator (evaluation.py:95-152) on the 12-site chain:
+  the mean of the sampled values agrees with the exact <psi|H|psi>/<psi|psi>
+  of the same parameters within Monte-Carlo error bars, and the acceptance
+  rate the reference computes and discards (evaluation.py:145-151) agrees with
+  the exact stationary acceptance probability of the exchange sampler."""
   from cgs_vmc_b200 import evaluation, operators, utils, wavefunctions
   from cgs_vmc_b200.session import Session
-  hp = utils.create_hparams(wavefunction_type='fully_connected', num_sites=8, num_fc_layers=1,
-                            fc_layer_size=8, batch_size=256, num_equilibration_sweeps=3,
-                            num_evaluation_samples=5)
+  n = 12
+  hp = utils.create_hparams(wavefunction_type='fully_connected', num_sites=n, num_fc_layers=1,
+                            fc_layer_size=8, batch_size=4096, num_equilibration_sweeps=20,
+                            num_monte_carlo_sweeps=2, num_evaluation_samples=40)
   wf = wavefunctions.build_wavefunction(hp).seed(4)
-  ham = operators.HeisenbergHamiltonian(lattices.chain_bonds(8), -1.0, 1.0)
+  bonds = lattices.chain_bonds(n)
+  ham = operators.HeisenbergHamiltonian(bonds, -1.0, 1.0)
   ev = evaluation.MonteCarloOperatorEvaluator()
   ops = ev.build_eval_ops(wavefunction=wf, operator=ham, hparams=hp, shared_resources={})
-  values = ev.run_evaluation(ops, Session(), hp, epoch_num=0)
-  assert len(values) == 5 and all(-4.0 < v < 2.1 for v in values)
+  session = Session()
+  values = ev.run_evaluation(ops, session, hp, epoch_num=0)
+  assert len(values) == hp.num_evaluation_samples
+  spec, params = _oracle_view(wf, 'fully_connected', hp)
+  psi_fn = lambda c: oansatz.psi(spec, params, torch.from_numpy(np.asarray(c)).to(F64), shift=-10.0).numpy()
+  exact = ed.exact_expectation(n, bonds, [-1.0] * n, [1.0] * n, psi_fn)
+  # each value is the mean over 4096 walkers; successive samples are 2 sweeps
+  # apart, so their spread gives the error bar of the grand mean (x2 for the
+  # residual autocorrelation)
+  values = np.asarray(values)
+  err = 2.0 * values.std(ddof=1) / np.sqrt(len(values))
+  assert abs(values.mean() - exact) < 4.0 * err + 1e-4, (values.mean(), exact, err)
+  assert err < 0.01 * abs(exact)
+  # acceptance: one more sweep group, counted by the op the evaluator exposes
+  steps = 5 * n
+  session.run(ops.mc_step, n_steps=steps)
+  rate = session.run(ops.acceptance_rate) / (steps * hp.batch_size)
+  exact_rate = ed.exact_acceptance_rate(n, psi_fn)
+  assert abs(rate - exact_rate) < 0.01, (rate, exact_rate)
+
+
+def test_update_norm_on_device_amplitudes():
+  """wavefunctions.py:261-288 through the API: the shift moves by log(max psi)
+  - log(max_value) iff the batch maximum exceeds max_value, and psi of the
+  same configurations drops accordingly."""
+  from cgs_vmc_b200 import graph_builders, utils, wavefunctions
+  hp = utils.create_hparams(wavefunction_type='rbm', num_sites=16, num_fc_layers=0, fc_layer_size=12)
+  wf = wavefunctions.build_wavefunction(hp).seed(5)
+  configs = graph_builders.get_configs({}, 128, 16)
+  psi0 = wf(configs).clone()
+  assert wf._exp_norm_shift == -10.0
+  top = float(psi0.max())
+  assert wf.update_norm(lambda: wf(configs), max_value=2.0 * top)() == -10.0        # below: unchanged
+  got = wf.update_norm(lambda: wf(configs), max_value=0.25 * top)()
+  assert abs(got - (-10.0 + np.log(4.0))) < 1e-4
+  torch.testing.assert_close(wf(configs), psi0 / 4.0, rtol=1e-4, atol=0.0)
+  # log-domain form used by the optimizers: same rule, no exp overflow
+  got2 = wf.update_norm(None, max_value=1.0, log_amplitudes=lambda: wf.log_amplitude(configs))()
+  assert abs(got2 - (got + np.log(top / 4.0))) < 1e-4
+  assert abs(float(wf(configs).max()) - 1.0) < 1e-4
+  # normalize_batch (wavefunctions.py:234-257) always rescales
+  got3 = wf.normalize_batch(lambda: wf(configs), max_value=8.0)()
+  assert abs(got3 - (got2 - np.log(8.0))) < 1e-4
+
+
+def test_unseeded_wavefunctions_differ():
+  """Two unseeded modules start from different parameters (the reference draws
+  from TF's unseeded stream): `diff` of two same-type leaves is not psi = 0."""
+  from cgs_vmc_b200 import utils, wavefunctions
+  hp = utils.create_hparams(wavefunction_type='diff', num_sites=12, num_fc_layers=1, fc_layer_size=6,
+                            composite_wavefunction_types=('fully_connected', 'fully_connected'),
+                            composite_output_activations=('exp', 'exp'))
+  wf = wavefunctions.build_wavefunction(hp)
+  cfg = torch.from_numpy(bits.random_sz0_configs(12, 32, np.random.default_rng(2))).cuda()
+  psi = wf(cfg)
+  assert torch.isfinite(psi).all() and (psi != 0).all()
+  a, b = wf.leaves()
+  assert not torch.equal(a.native().params, b.native().params)
 
 
 def test_drivers_end_to_end(tmp_path):

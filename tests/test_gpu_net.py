@@ -15,6 +15,7 @@ F64 = torch.float64
 NET_GOLDEN = ['fc_chain20', 'fc_chain8_small', 'rbm_chain12_hidden', 'conv1d_chain12_k3',
               'conv1d_chain12_k4', 'conv2d_6x6_k3', 'conv2d_4x4_k2', 'conv2d_4x6_k3',
               'conv2d_10x10',
+              'conv2d_10x10_grad',     # the C3 network with the reference's energy gradient (batch 2)
               # ResNet1D / ResNet2D (wavefunctions.py:617-809)
               'resnet1d_chain12_k3', 'resnet1d_chain12_k4', 'resnet2d_4x4_k3', 'resnet2d_4x6_k2']
 
@@ -282,6 +283,8 @@ def test_energy_gradient_and_swo_golden(native, name):
     grad = (s[1] - mean_e * s[0]).cpu().numpy()
     ref = g['eg_gradient']
     assert np.linalg.norm(grad - ref) <= 5e-4 * np.linalg.norm(ref) + 1e-4
+  if 'swo_gradient' not in g:        # N >= 64: the reference's own SWO raises (np.sqrt(2**N), training.py:170)
+    return
   target = make_native(spec, g['swo_target_params_flat'])
   packed = packed_cuda(g['swo_configs'])
   psi = torch.exp(a.log_amp(packed).double() - float(g['shift']))

@@ -124,7 +124,7 @@ def test_pack_unpack_sums():
   sums = torch.arange(10, dtype=torch.float32).reshape(2, 5)
   stats = torch.tensor([1.5, 2.5, 7.0, 0.0], dtype=torch.float64)
   payload = distributed.pack_sums(sums, stats)
-  assert payload.dtype == torch.float32 and payload.numel() == 14
+  assert payload.dtype == torch.float64 and payload.numel() == 14
   s2, t2 = torch.zeros_like(sums), torch.zeros_like(stats)
   distributed.unpack_sums(payload, s2, t2)
   assert torch.equal(s2, sums) and torch.equal(t2, stats)
@@ -152,6 +152,37 @@ def _worker(rank, world, port, out_dir):
                                rtol=1e-6, atol=1e-6)
     m = distributed.allreduce_(torch.tensor([float(rank)]), op='max')
     assert m.item() == world - 1
+    # totals into separate buffers: the local accumulators stay local, so a
+    # second reduce after further accumulation does not double count
+    # (metrics in the middle of an epoch, then accumulate again)
+    local_sums = per_walker[mine].sum(0)
+    local_stats = torch.tensor([e[mine].sum(), (e[mine] ** 2).sum(), float(local), 0.0], dtype=torch.float64)
+    keep = (local_sums.clone(), local_stats.clone())
+    tot_s, tot_t = torch.zeros_like(local_sums), torch.zeros_like(local_stats)
+    for _ in range(2):
+      distributed.allreduce_sums(local_sums, local_stats, tot_s, tot_t)
+      assert torch.equal(local_sums, keep[0]) and torch.equal(local_stats, keep[1])
+      torch.testing.assert_close(tot_s, per_walker.sum(0), rtol=1e-5, atol=1e-5)
+      assert tot_t[2].item() == 64.0
+    # walker counts beyond 2^24 and sum E^2 stay exact (float64 payload)
+    big = torch.tensor([1.0, 3.0, float(2 ** 24 + 1 + rank), 0.0], dtype=torch.float64)
+    _, big_tot = distributed.allreduce_sums(torch.zeros(1, 3), big, torch.zeros(1, 3), torch.zeros(4, dtype=torch.float64))
+    assert big_tot[2].item() == float(2 * (2 ** 24 + 1) + 1)
+    # update_norm (wavefunctions.py:261-288): tf.reduce_max runs over the WHOLE
+    # batch, so the shards' maxima are all-reduced and every rank applies the
+    # same shift; only rank 1 holds the amplitude above max_value here
+    wf = wavefunctions.RestrictedBoltzmannNetwork(0, 4)
+    wf._exp_norm_shift = -10.0
+    amps = torch.tensor([1.0, 2.0]) if rank == 0 else torch.tensor([3.0, 1e12])
+    shift = wf.update_norm(amps)()
+    assert abs(shift - (-10.0 + np.log(1e12) - np.log(1e10))) < 1e-5
+    shift2 = wf.update_norm(None, log_amplitudes=torch.log(amps.double()))()    # log-domain form
+    assert abs(shift2 - (shift + np.log(1e12) - np.log(1e10))) < 1e-5
+    assert wf.update_norm(torch.tensor([5.0, 7.0]))() == shift2              # below max_value: unchanged
+    # parameter replicas start from rank 0's values
+    prm = torch.full((3,), float(rank + 1))
+    distributed.broadcast_(prm)
+    assert torch.equal(prm, torch.ones(3))
     open(os.path.join(out_dir, 'ok%d' % rank), 'w').close()
   finally:
     dist.destroy_process_group()
@@ -163,3 +194,42 @@ def test_sharded_allreduce_gloo_world2(tmp_path):
   port = 29500 + os.getpid() % 2000
   mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
   assert sorted(os.listdir(tmp_path)) == ['ok0', 'ok1']
+
+
+def test_update_norm_reference_rule():
+  """wavefunctions.py:261-288 / 234-257 on one rank: shift += log(max psi) -
+  log(max_value) iff max psi > max_value; normalize_batch always."""
+  wf = wavefunctions.FullyConnectedNetwork(1, 4)
+  wf._exp_norm_shift = -10.0
+  assert wf.update_norm(torch.tensor([1.0, 9.9e9]))() == -10.0
+  got = wf.update_norm(torch.tensor([1.0, 4e10]))()
+  assert abs(got - (-10.0 + np.log(4e10 / 1e10))) < 1e-5
+  got2 = wf.normalize_batch(torch.tensor([0.5, 2.0]), max_value=4.0)()
+  assert abs(got2 - (got + np.log(2.0 / 4.0))) < 1e-6
+  # callable inputs are evaluated when the op runs (graph semantics)
+  box = {'v': torch.tensor([1.0])}
+  op = wf.update_norm(lambda: box['v'], max_value=10.0)
+  assert op() == got2
+  box['v'] = torch.tensor([1000.0])
+  assert abs(op() - (got2 + np.log(100.0))) < 1e-5
+  # signed outputs carry no exp_norm_shift: no op (wavefunctions.py:280-281)
+  assert wavefunctions.FullyConnectedNetwork(1, 4, output_activation='tanh').update_norm(torch.ones(2)) is None
+
+
+def test_unseeded_wavefunctions_get_distinct_init_streams():
+  a, b = wavefunctions._next_init_seed(), wavefunctions._next_init_seed()
+  assert a != b and 0 <= a < 2 ** 63 and 0 <= b < 2 ** 63
+
+
+def test_hparams_parse_unquoted_lists():
+  """tf.contrib.training.HParams.parse accepts name=[a,b] with bare strings."""
+  h = utils.create_hparams()
+  h.parse('composite_wavefunction_types=[rbm,fully_connected],composite_output_activations=[exp,tanh],'
+          'batch_size=8,learning_rates=[0.1,0.2],nonlinearity=relu')
+  assert h.composite_wavefunction_types == ('rbm', 'fully_connected')
+  assert h.composite_output_activations == ('exp', 'tanh')
+  assert h.batch_size == 8 and h.learning_rates == [0.1, 0.2] and h.nonlinearity == 'relu'
+  with pytest.raises(ValueError):
+    h.parse('composite_wavefunction_types=[rbm]')
+  with pytest.raises(ValueError):
+    h.parse('learning_rates=0.1')

@@ -92,3 +92,20 @@ def test_sampled_energy_matches_ed_chain8():
         cfg, torch.from_numpy(rng.random((64, n))), torch.from_numpy(rng.random(64)), log_fn)
   e = hamiltonian.local_energy(cfg, ij, jx, jz, log_fn)
   np.testing.assert_allclose(e.numpy(), e0, atol=1e-9)
+
+
+def test_exact_expectation_and_acceptance_known_answers():
+  """oracle/ed.py helpers behind the evaluator parity test: the exact
+  expectation of the ground vector is E0, and a constant amplitude is accepted
+  with probability one."""
+  import numpy as np
+  from oracle import ed, lattices
+  n = 8
+  bonds = lattices.chain_bonds(n)
+  ij, jx, jz = lattices.heisenberg_couplings(bonds)
+  e0, basis, vec = ed.ground_state(n, ij, jx, jz)
+  psi_fn = ed.lookup_amplitude(basis, vec)
+  assert abs(ed.exact_expectation(n, ij, jx, jz, lambda c: psi_fn(c).numpy()) - e0) < 1e-10
+  assert abs(ed.exact_acceptance_rate(n, lambda c: np.ones(len(c))) - 1.0) < 1e-12
+  rate = ed.exact_acceptance_rate(n, lambda c: psi_fn(c).numpy())
+  assert 0.0 < rate < 1.0
