@@ -30,6 +30,7 @@ EXPORTS = [
     'cgsvmc_flip_enum', 'cgsvmc_local_energy', 'cgsvmc_weighted_grad_sum',
     'cgsvmc_energy_stats', 'cgsvmc_accumulate', 'cgsvmc_batch_step',
     'cgsvmc_propose_exchange', 'cgsvmc_accept_exchange', 'cgsvmc_local_energy_from_amps',
+    'cgsvmc_swo_weights', 'cgsvmc_adam_step',
 ]
 
 
@@ -84,6 +85,9 @@ def load():
   lib.cgsvmc_propose_exchange.argtypes = [vp, i64, i32, u64, u64, u64, vp, vp, vp]
   lib.cgsvmc_accept_exchange.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]
   lib.cgsvmc_local_energy_from_amps.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+  f32 = ctypes.c_float
+  lib.cgsvmc_swo_weights.argtypes = [vp, vp, vp, vp, i64, f32, f32, vp, vp, vp]
+  lib.cgsvmc_adam_step.argtypes = [vp, vp, vp, i64, vp, vp, vp, f32, f32, vp, f32, f32, f32, u64, vp, vp]
   for name in EXPORTS:
     fn = getattr(lib, name)
     if name not in ('cgsvmc_last_error', 'cgsvmc_ansatz_num_params'):
@@ -443,3 +447,50 @@ def local_energy_from_amps(ham, packed, logabs, sign, flipped_logabs, flipped_si
                                              _ptr(diag), _ptr(off), _stream()))
   return (e, diag, off) if want_parts else e
 
+
+
+def swo_weights(log_amp, log_amp_target, log_norm, total, sign=None, sign_target=None, out=None,
+                loss_acc=None):
+  """Loss and gradient weights of SupervisedWavefunctionOptimizer
+  (training.py:166-175) in one kernel: returns weights [1, B] = 2 (1 - r) / total
+  with r = psi_target sqrt(2^N) / psi; loss_acc (float64 [2]) += (sum (1 - r)^2, B)."""
+  b = log_amp.numel()
+  for name, t in (('log_amp', log_amp), ('log_amp_target', log_amp_target)):
+    _want(t, torch.float32, (b,), name)
+  for name, t in (('sign', sign), ('sign_target', sign_target)):
+    if t is not None:
+      _want(t, torch.float32, (b,), name)
+  if out is None:
+    out = torch.empty(1, b, dtype=torch.float32, device=log_amp.device)
+  _want(out, torch.float32, (1, b), 'out')
+  if loss_acc is not None:
+    _want(loss_acc, torch.float64, (2,), 'loss_acc')
+  check(load().cgsvmc_swo_weights(_ptr(log_amp), _ptr(sign), _ptr(log_amp_target), _ptr(sign_target), b,
+                                  float(log_norm), 1.0 / float(total), _ptr(out), _ptr(loss_acc),
+                                  _stream()))
+  return out
+
+
+def adam_step(params, m, v, grad=None, sums=None, stats=None, num_batches=1.0, lr=0.0, lr_dev=None,
+              beta1=0.9, beta2=0.99, eps=1e-8, t=1, t_dev=None):
+  """One tf.train.AdamOptimizer update of the flat parameter buffer in one
+  kernel; the gradient is `grad` or the energy gradient of training.py:562-564
+  formed from (sums [2, P], stats [4])."""
+  n = params.numel()
+  for name, x in (('params', params), ('m', m), ('v', v)):
+    _want(x, torch.float32, (n,), name)
+  if grad is not None:
+    _want(grad, torch.float32, (n,), 'grad')
+  if sums is not None:
+    _want(sums, torch.float32, (2, n), 'sums')
+    _want(stats, torch.float64, (4,), 'stats')
+  if lr_dev is not None:
+    _want(lr_dev, torch.float32, (1,), 'lr_dev')
+  if t_dev is not None:
+    _want(t_dev, torch.int64, (1,), 't_dev')
+  check(load().cgsvmc_adam_step(_ptr(params), _ptr(m), _ptr(v), n, _ptr(grad), _ptr(sums), _ptr(stats),
+                                1.0 / float(num_batches), float(lr), _ptr(lr_dev), float(beta1),
+                                float(beta2), float(eps), int(t), _ptr(t_dev), _stream()))
+  # the kernel wrote through the raw pointer: tell torch, so that the ansatz
+  # handles notice the parameter change (Ansatz._sync_params)
+  torch.autograd.graph.increment_version(params)

@@ -4,7 +4,20 @@
 #include <cstring>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "internal.h"
+
+// NVTX ranges around the entry points (header-only nvtx3: a no-op function
+// pointer check unless a profiler is attached), named after the kernel groups
+// of SURVEY.md 2.2: K0 utility, K1 amplitudes, K2 sampler, K3 local energy,
+// K4 weighted gradient sums, K5 statistics / loss.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 namespace cgsvmc {
 
@@ -233,12 +246,14 @@ int cgsvmc_ham_destroy(cgsvmc_ham* h) {
 }
 
 int cgsvmc_pack_configs(const float* configs, int64_t B, int32_t N, uint64_t* packed, void* stream) {
+  NvtxRange range("cgsvmc:K0 pack_configs");
   if (B < 0 || N < 1 || N > CGSVMC_MAX_SITES) return invalid("pack_configs: bad shape");
   if (B > 0 && (configs == nullptr || packed == nullptr)) return invalid("pack_configs: NULL buffer");
   return launch_pack(configs, B, N, packed, (cudaStream_t)stream);
 }
 
 int cgsvmc_unpack_configs(const uint64_t* packed, int64_t B, int32_t N, float* configs, void* stream) {
+  NvtxRange range("cgsvmc:K0 unpack_configs");
   if (B < 0 || N < 1 || N > CGSVMC_MAX_SITES) return invalid("unpack_configs: bad shape");
   if (B > 0 && (configs == nullptr || packed == nullptr)) return invalid("unpack_configs: NULL buffer");
   return launch_unpack(packed, B, N, configs, (cudaStream_t)stream);
@@ -246,6 +261,7 @@ int cgsvmc_unpack_configs(const uint64_t* packed, int64_t B, int32_t N, float* c
 
 int cgsvmc_random_configs(uint64_t* packed, int64_t B, int32_t N, uint64_t seed, uint64_t walker_id0,
                           void* stream) {
+  NvtxRange range("cgsvmc:K0 random_configs");
   if (B < 0 || N < 2 || N > CGSVMC_MAX_SITES) return invalid("random_configs: bad shape");
   if (B > 0 && packed == nullptr) return invalid("random_configs: NULL buffer");
   return launch_random_configs(packed, B, N, seed, walker_id0, (cudaStream_t)stream);
@@ -253,6 +269,7 @@ int cgsvmc_random_configs(uint64_t* packed, int64_t B, int32_t N, uint64_t seed,
 
 int cgsvmc_log_amp(const cgsvmc_ansatz* a, const uint64_t* packed, int64_t B, float* log_amp,
                    void* stream) {
+  NvtxRange range("cgsvmc:K1 log_amp");
   if (int rc = check_ready(a)) return rc;
   if (B < 0) return invalid("log_amp: n_walkers < 0");
   if (B == 0) return CGSVMC_OK;
@@ -266,6 +283,7 @@ int cgsvmc_log_amp(const cgsvmc_ansatz* a, const uint64_t* packed, int64_t B, fl
 int cgsvmc_mc_steps(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int32_t n_steps,
                     uint64_t seed, uint64_t walker_id0, uint64_t step0,
                     unsigned long long* accept_count, float* log_amp_out, void* stream) {
+  NvtxRange range("cgsvmc:K2 mc_steps");
   if (int rc = check_ready(a)) return rc;
   if (B < 0 || n_steps < 0) return invalid("mc_steps: negative size");
   if (B == 0) return CGSVMC_OK;
@@ -286,6 +304,7 @@ int cgsvmc_mc_steps(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int32_t
 int cgsvmc_mc_steps_graph(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int32_t n_steps,
                           uint64_t seed, uint64_t walker_id0, uint64_t* step_counter,
                           unsigned long long* accept_count, float* log_amp_out, void* stream) {
+  NvtxRange range("cgsvmc:K2 mc_steps_graph");
   if (a == nullptr) return invalid("ansatz handle is NULL");
   if (step_counter == nullptr) return invalid("mc_steps_graph: NULL step counter");
   if (rbm_fast_supported(a) && !rbm2_supported(a, nullptr)) {
@@ -303,6 +322,7 @@ int cgsvmc_mc_steps_graph(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, i
 int cgsvmc_mc_step_replay(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, const float* u_sites,
                           const float* u_acc, int32_t* down_site, int32_t* up_site,
                           float* log_ratio, uint8_t* accept_mask, void* stream) {
+  NvtxRange range("cgsvmc:K2 mc_step_replay");
   if (int rc = check_ready(a)) return rc;
   if (B < 0) return invalid("mc_step_replay: n_walkers < 0");
   if (B == 0) return CGSVMC_OK;
@@ -317,6 +337,7 @@ int cgsvmc_mc_step_replay(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, c
 
 int cgsvmc_flip_enum(const cgsvmc_ham* h, const uint64_t* packed, int64_t B, uint64_t* flipped,
                      uint32_t* active_mask, void* stream) {
+  NvtxRange range("cgsvmc:K3 flip_enum");
   if (h == nullptr) return invalid("flip_enum: NULL hamiltonian");
   if (B < 0) return invalid("flip_enum: n_walkers < 0");
   if (B > 0 && packed == nullptr) return invalid("flip_enum: NULL configs");
@@ -326,6 +347,7 @@ int cgsvmc_flip_enum(const cgsvmc_ham* h, const uint64_t* packed, int64_t B, uin
 int cgsvmc_local_energy(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed,
                         int64_t B, float* e_loc, float* log_amp_out, float* diag_out,
                         float* offdiag_ratio_out, void* stream) {
+  NvtxRange range("cgsvmc:K3 local_energy");
   if (int rc = check_ready(a)) return rc;
   if (h == nullptr) return invalid("local_energy: NULL hamiltonian");
   if (h->n_sites != a->desc.n_sites) return invalid("local_energy: hamiltonian and ansatz n_sites differ");
@@ -347,6 +369,7 @@ int cgsvmc_local_energy(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint6
 
 int cgsvmc_weighted_grad_sum(const cgsvmc_ansatz* a, const uint64_t* packed, const float* weights,
                              int64_t B, int32_t K, float* out, void* stream) {
+  NvtxRange range("cgsvmc:K4 weighted_grad_sum");
   if (int rc = check_ready(a)) return rc;
   if (B < 0) return invalid("weighted_grad_sum: n_walkers < 0");
   if (K < 1 || K > 4) return invalid("weighted_grad_sum: n_weights must be in 1..4");
@@ -370,6 +393,7 @@ int cgsvmc_weighted_grad_sum(const cgsvmc_ansatz* a, const uint64_t* packed, con
 
 int cgsvmc_accumulate(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, int64_t B,
                       float* e_loc_out, float* log_amp_out, float* sums, double* stats, void* stream) {
+  NvtxRange range("cgsvmc:K3+K4+K5 accumulate");
   if (int rc = check_ready(a)) return rc;
   if (h == nullptr) return invalid("accumulate: NULL hamiltonian");
   if (h->n_sites != a->desc.n_sites) return invalid("accumulate: hamiltonian and ansatz n_sites differ");
@@ -406,6 +430,7 @@ int cgsvmc_batch_step(const cgsvmc_ansatz* a, const cgsvmc_ham* h, uint64_t* pac
                       float* e_loc_out, float* log_amp_out, float* sums, double* stats,
                       int32_t n_steps, uint64_t seed, uint64_t walker_id0, uint64_t step0,
                       uint64_t* step_counter, unsigned long long* accept_count, void* stream) {
+  NvtxRange range("cgsvmc:K2+K3+K4+K5 batch_step");
   if (int rc = check_ready(a)) return rc;
   if (h == nullptr) return invalid("batch_step: NULL hamiltonian");
   if (h->n_sites != a->desc.n_sites) return invalid("batch_step: hamiltonian and ansatz n_sites differ");
@@ -433,6 +458,7 @@ int cgsvmc_batch_step(const cgsvmc_ansatz* a, const cgsvmc_ham* h, uint64_t* pac
 int cgsvmc_propose_exchange(const uint64_t* packed, int64_t B, int32_t N, uint64_t seed,
                             uint64_t walker_id0, uint64_t step, uint64_t* proposed, float* u_acc,
                             void* stream) {
+  NvtxRange range("cgsvmc:K2 propose_exchange");
   if (B < 0 || N < 2 || N > CGSVMC_MAX_SITES) return invalid("propose_exchange: bad shape");
   if (B > 0 && (packed == nullptr || proposed == nullptr || u_acc == nullptr))
     return invalid("propose_exchange: NULL buffer");
@@ -442,6 +468,7 @@ int cgsvmc_propose_exchange(const uint64_t* packed, int64_t B, int32_t N, uint64
 int cgsvmc_accept_exchange(uint64_t* packed, const uint64_t* proposed, int64_t B, int32_t N,
                            float* logabs, float* sign, const float* logabs_new, const float* sign_new,
                            const float* u_acc, unsigned long long* accept_count, void* stream) {
+  NvtxRange range("cgsvmc:K2 accept_exchange");
   if (B < 0 || N < 2 || N > CGSVMC_MAX_SITES) return invalid("accept_exchange: bad shape");
   if (B > 0 && (packed == nullptr || proposed == nullptr || logabs == nullptr || logabs_new == nullptr ||
                 u_acc == nullptr))
@@ -455,6 +482,7 @@ int cgsvmc_local_energy_from_amps(const cgsvmc_ham* h, const uint64_t* packed, i
                                   const float* logabs, const float* sign, const float* flipped_logabs,
                                   const float* flipped_sign, float* e_loc, float* diag_out,
                                   float* offdiag_ratio_out, void* stream) {
+  NvtxRange range("cgsvmc:K3 local_energy_from_amps");
   if (h == nullptr) return invalid("local_energy_from_amps: NULL hamiltonian");
   if (B < 0) return invalid("local_energy_from_amps: n_walkers < 0");
   if (B > 0 && (packed == nullptr || logabs == nullptr || (h->n_bonds > 0 && flipped_logabs == nullptr)))
@@ -463,7 +491,36 @@ int cgsvmc_local_energy_from_amps(const cgsvmc_ham* h, const uint64_t* packed, i
                                offdiag_ratio_out, (cudaStream_t)stream);
 }
 
+int cgsvmc_swo_weights(const float* log_amp, const float* sign, const float* log_amp_target,
+                       const float* sign_target, int64_t B, float log_norm, float inv_total,
+                       float* weights_out, double* loss_acc, void* stream) {
+  NvtxRange range("cgsvmc:K5 swo_weights");
+  if (B < 0) return invalid("swo_weights: n_walkers < 0");
+  if (B > 0 && (log_amp == nullptr || log_amp_target == nullptr || weights_out == nullptr))
+    return invalid("swo_weights: NULL buffer");
+  return launch_swo_weights(log_amp, sign, log_amp_target, sign_target, B, log_norm, inv_total, weights_out,
+                            loss_acc, (cudaStream_t)stream);
+}
+
+int cgsvmc_adam_step(float* params, float* m, float* v, int64_t n, const float* grad, const float* sums,
+                     const double* stats, float inv_num_batches, float lr, const float* lr_dev,
+                     float beta1, float beta2, float eps, uint64_t t, uint64_t* t_dev, void* stream) {
+  NvtxRange range("cgsvmc:adam_step");
+  if (n < 0) return invalid("adam_step: n < 0");
+  if (n == 0) return CGSVMC_OK;
+  if (params == nullptr || m == nullptr || v == nullptr) return invalid("adam_step: NULL buffer");
+  if ((grad == nullptr) == (sums == nullptr)) return invalid("adam_step: give either grad or sums");
+  if (sums != nullptr && stats == nullptr) return invalid("adam_step: sums need stats");
+  if (t_dev == nullptr && t < 1) return invalid("adam_step: t starts at 1");
+  if (int rc = launch_adam(params, m, v, n, grad, sums, stats, inv_num_batches, lr, lr_dev, beta1, beta2, eps,
+                           t, t_dev, (cudaStream_t)stream))
+    return rc;
+  if (t_dev != nullptr) return launch_advance_counter(t_dev, 1, (cudaStream_t)stream);
+  return CGSVMC_OK;
+}
+
 int cgsvmc_energy_stats(const float* e_loc, int64_t B, double* stats, void* stream) {
+  NvtxRange range("cgsvmc:K5 energy_stats");
   if (B < 0) return invalid("energy_stats: n_walkers < 0");
   if (B > 0 && (e_loc == nullptr || stats == nullptr)) return invalid("energy_stats: NULL buffer");
   return launch_energy_stats(e_loc, B, stats, (cudaStream_t)stream);

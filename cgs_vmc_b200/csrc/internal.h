@@ -87,6 +87,11 @@ int launch_fill(float* dst, int64_t n, float value, cudaStream_t s);
 int launch_energy_stats(const float* e, int64_t B, double* stats, cudaStream_t s);
 int launch_reduce_partials(const float* partials, int n_parts, int64_t n, float* out,
                            cudaStream_t s);
+int launch_swo_weights(const float* z, const float* sign, const float* zt, const float* sign_t, int64_t B,
+                       float log_norm, float inv_total, float* weights, double* acc, cudaStream_t s);
+int launch_adam(float* params, float* m, float* v, int64_t n, const float* grad, const float* sums,
+                const double* stats, float inv_nb, float lr, const float* lr_dev, float b1, float b2,
+                float eps, uint64_t t, const uint64_t* t_dev, cudaStream_t s);
 
 // ---- pure RBM (num_layers == 0) fast path (rbm.cu) ----
 bool rbm_fast_supported(const cgsvmc_ansatz* a);

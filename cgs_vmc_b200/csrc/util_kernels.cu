@@ -256,6 +256,68 @@ __global__ void eloc_from_amps_kernel(const int2* __restrict__ ij, const float* 
   }
 }
 
+// SupervisedWavefunctionOptimizer (training.py:166-175): per walker
+//   r_b = sign sign_t exp(z_t + log_norm - z)   (= psi_target sqrt(2^N) / psi)
+//   loss  += sum_b (1 - r_b)^2                  (mean_b (psi - t)^2 / sg(psi)^2 times the batch size)
+//   w_b    = 2 (1 - r_b) / total                (d loss / d log psi_b)
+// acc (double [2]) += { sum (1 - r)^2, B }.
+__global__ void swo_weights_kernel(const float* __restrict__ z, const float* __restrict__ sign,
+                                   const float* __restrict__ zt, const float* __restrict__ sign_t,
+                                   int64_t B, float log_norm, float inv_total,
+                                   float* __restrict__ weights, double* acc) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float r = expf(zt[i] + log_norm - z[i]);
+    if (sign != nullptr) r *= sign[i];
+    if (sign_t != nullptr) r *= sign_t[i];
+    const float d = 1.0f - r;
+    weights[i] = 2.0f * d * inv_total;
+    s += (double)d * (double)d;
+  }
+  s = warp_sum(s);
+  __shared__ double sh[kThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sh[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    s = lane < kThreads / 32 ? sh[lane] : 0.0;
+    s = warp_sum(s);
+    if (lane == 0 && acc != nullptr) {
+      atomicAdd(&acc[0], s);
+      if (blockIdx.x == 0) atomicAdd(&acc[1], (double)B);
+    }
+  }
+}
+
+// tf.train.AdamOptimizer step (training.py:76-91, beta1 = 0.9, eps = 1e-8):
+//   m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2
+//   theta -= lr sqrt(1 - b2^t) / (1 - b1^t) m / (sqrt(v) + eps)
+// The gradient is either `grad[i]` or formed on the fly from the estimator
+// sums of EnergyGradientOptimizer (training.py:562-564):
+//   g = (S[1][i] - (stats[0] / stats[2]) S[0][i]) * inv_nb.
+// lr / t come from device scalars when given (CUDA-graph replays).
+__global__ void adam_kernel(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v,
+                            int64_t n, const float* __restrict__ grad, const float* __restrict__ sums,
+                            const double* __restrict__ stats, float inv_nb, float lr,
+                            const float* __restrict__ lr_dev, float b1, float b2, float eps,
+                            uint64_t t, const uint64_t* __restrict__ t_dev) {
+  if (lr_dev != nullptr) lr = *lr_dev;
+  if (t_dev != nullptr) t = *t_dev + 1;
+  const double td = (double)t;
+  const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, td)) / (1.0 - pow((double)b1, td)));
+  const float mean_e = stats != nullptr ? (float)(stats[0] / stats[2]) : 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float g = sums != nullptr ? (sums[n + i] * inv_nb - mean_e * (sums[i] * inv_nb)) : grad[i];
+    const float mi = b1 * m[i] + (1.0f - b1) * g;
+    const float vi = b2 * v[i] + (1.0f - b2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    params[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
 int blocks_for(int64_t work_items, int per_block) {
   const int64_t need = (work_items + per_block - 1) / per_block;
   return (int)std::max<int64_t>(1, std::min<int64_t>(need, 148 * 16));
@@ -316,6 +378,23 @@ int launch_energy_stats(const float* e, int64_t B, double* stats, cudaStream_t s
   if (B == 0) return CGSVMC_OK;
   energy_stats_kernel<<<blocks_for(B, kThreads * 8), kThreads, 0, s>>>(e, B, stats);
   return cuda_fail(cudaGetLastError(), "energy_stats launch");
+}
+
+int launch_swo_weights(const float* z, const float* sign, const float* zt, const float* sign_t, int64_t B,
+                       float log_norm, float inv_total, float* weights, double* acc, cudaStream_t s) {
+  if (B == 0) return CGSVMC_OK;
+  swo_weights_kernel<<<blocks_for(B, kThreads * 4), kThreads, 0, s>>>(z, sign, zt, sign_t, B, log_norm,
+                                                                     inv_total, weights, acc);
+  return cuda_fail(cudaGetLastError(), "swo_weights launch");
+}
+
+int launch_adam(float* params, float* m, float* v, int64_t n, const float* grad, const float* sums,
+                const double* stats, float inv_nb, float lr, const float* lr_dev, float b1, float b2,
+                float eps, uint64_t t, const uint64_t* t_dev, cudaStream_t s) {
+  if (n == 0) return CGSVMC_OK;
+  adam_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(params, m, v, n, grad, sums, stats, inv_nb, lr,
+                                                          lr_dev, b1, b2, eps, t, t_dev);
+  return cuda_fail(cudaGetLastError(), "adam launch");
 }
 
 int launch_reduce_partials(const float* partials, int n_parts, int64_t n, float* out,

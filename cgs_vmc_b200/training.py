@@ -53,27 +53,66 @@ class _Optimizer:
 
 class AdamOptimizer(_Optimizer):
   """tf.train.AdamOptimizer(lr, beta2=hparams.beta2): beta1 = 0.9, eps = 1e-8,
-  theta -= lr * sqrt(1 - b2^t) / (1 - b1^t) * m / (sqrt(v) + eps)."""
+  theta -= lr * sqrt(1 - b2^t) / (1 - b1^t) * m / (sqrt(v) + eps); one kernel
+  per update (cgsvmc_adam_step)."""
 
   def __init__(self, hparams):
     super().__init__(hparams)
     self.beta1, self.beta2, self.eps = 0.9, float(hparams.beta2), 1e-8
     self.m = self.v = None
     self.t = 0
+    self.t_dev = self.lr_dev = None      # device copies for captured steps
 
-  def apply_gradients(self, params, grad):
+  def _state(self, params):
     if self.m is None:
       self.m = torch.zeros_like(params)
       self.v = torch.zeros_like(params)
+
+  def apply_gradients(self, params, grad=None, sums=None, stats=None, num_batches=1.0):
+    """`grad`, or the energy gradient formed from (sums, stats, num_batches)
+    inside the update kernel (training.py:562-567)."""
+    self._state(params)
     self.t += 1
-    self.m.mul_(self.beta1).add_(grad, alpha=1 - self.beta1)
-    self.v.mul_(self.beta2).addcmul_(grad, grad, value=1 - self.beta2)
-    lr_t = self.learning_rate() * math.sqrt(1 - self.beta2 ** self.t) / (1 - self.beta1 ** self.t)
-    params.addcdiv_(self.m, self.v.sqrt().add_(self.eps), value=-lr_t)
+    if grad is not None:
+      grad = grad.contiguous()
+    _native.adam_step(params, self.m, self.v, grad=grad, sums=sums, stats=stats,
+                      num_batches=num_batches, lr=self.learning_rate(), beta1=self.beta1,
+                      beta2=self.beta2, eps=self.eps, t=self.t)
+
+  def device_state(self, params):
+    """(t_dev, lr_dev): step count and learning rate in device memory for a
+    captured update; sync_device() refreshes them before a replay."""
+    self._state(params)
+    if self.t_dev is None:
+      self.t_dev = torch.zeros(1, dtype=torch.int64, device=params.device)
+      self.lr_dev = torch.zeros(1, dtype=torch.float32, device=params.device)
+      self._lr_on_dev = self._t_on_dev = None
+    return self.t_dev, self.lr_dev
+
+  def sync_device(self, steps_in_replay):
+    """Call before replaying a graph that takes `steps_in_replay` captured
+    updates: pushes a changed learning rate, keeps the host count in step."""
+    lr = self.learning_rate()
+    if lr != self._lr_on_dev:
+      self.lr_dev.fill_(lr)
+      self._lr_on_dev = lr
+    if self._t_on_dev != self.t:           # eager updates were taken in between
+      self.t_dev.fill_(self.t)
+    self.t += steps_in_replay
+    self._t_on_dev = self.t
+
+  def apply_gradients_captured(self, params, grad):
+    """The update with t / lr read on the device (inside a graph capture)."""
+    t_dev, lr_dev = self.device_state(params)
+    _native.adam_step(params, self.m, self.v, grad=grad, lr_dev=lr_dev, beta1=self.beta1,
+                      beta2=self.beta2, eps=self.eps, t_dev=t_dev)
 
 
 class GradientDescentOptimizer(_Optimizer):
-  def apply_gradients(self, params, grad):
+  def apply_gradients(self, params, grad=None, sums=None, stats=None, num_batches=1.0):
+    if grad is None:
+      nb = float(num_batches)
+      grad = sums[1] / nb - (stats[0] / stats[2]).float() * sums[0] / nb
     params.add_(grad, alpha=-self.learning_rate())
 
 
@@ -233,7 +272,11 @@ class EnergyGradientOptimizer(WavefunctionOptimizer):
 
     def apply_gradients():                 # training.py:562-567
       reduce_once()
-      model.apply_gradients(global_gradient())
+      if len(model.leaf_params) == 1:      # gradient formed inside the update kernel
+        model.optimizers[0].apply_gradients(model.leaf_params[0], sums=total.sums, stats=total.stats,
+                                            num_batches=sums.n_batches)
+      else:
+        model.apply_gradients(global_gradient())
 
     def metrics():                         # mean_energy, training.py:555, 582
       reduce_once()
@@ -288,7 +331,19 @@ class EnergyGradientOptimizer(WavefunctionOptimizer):
 
 
 class SupervisedWavefunctionOptimizer:
-  """SWO with |psi|^2 sampling and the adjusted L2 loss, training.py:135-212."""
+  """SWO with |psi|^2 sampling and the adjusted L2 loss, training.py:135-212.
+
+  One batch = one sweep group + one optimizer step (training.py:208-212): the
+  ratio psi_target sqrt(2^N) / psi, the loss and the gradient weights are one
+  kernel (cgsvmc_swo_weights), the gradient one cgsvmc_weighted_grad_sum, the
+  Adam update one cgsvmc_adam_step; nothing is read back to the host.  Because
+  the parameters move every batch, the walker-sharded run all-reduces the
+  P-vector gradient every batch -- that exchange is part of the algorithm.
+  With `use_cuda_graph` (fast-path wavefunctions, Adam) sweep + train step are
+  replayed as captured CUDA graphs (two halves around the all-reduce when
+  sharded)."""
+
+  use_cuda_graph = True
 
   def build_opt_ops(self, wavefunction, target_wavefunction, hparams, shared_resources):
     n_sites = hparams.num_sites
@@ -299,31 +354,104 @@ class SupervisedWavefunctionOptimizer:
         shared_resources, configs, wavefunction)
     model = _Model(wavefunction, n_sites, hparams)
     target = _Model(target_wavefunction, n_sites)
-    grad = torch.zeros(1, model.num_params, dtype=torch.float32, device=model.device)
+    dev = model.device
+    grad = torch.zeros(1, model.num_params, dtype=torch.float32, device=dev)
+    weights = torch.zeros(1, local_batch, dtype=torch.float32, device=dev)
+    loss_acc = torch.zeros(2, dtype=torch.float64, device=dev)      # sum (1 - r)^2, walkers
     log_norm = 0.5 * n_sites * math.log(2.0)       # sqrt(2^N), training.py:170
+    total = float(hparams.batch_size)
 
-    def loss_and_weights():
-      # ratio = psi_target * sqrt(2^N) / psi, formed in the log domain
+    def loss_and_weights(acc):
+      # r = psi_target * sqrt(2^N) / psi in the log domain; loss = mean (1 - r)^2
       z, sg = model.log_psi(configs.packed)
       zt, st = target.log_psi(configs.packed)
-      ratio = sg * st * torch.exp(zt + log_norm - z)
-      total = float(hparams.batch_size)
-      loss = ((1.0 - ratio) ** 2).sum() / total        # mean (psi - t)^2 / sg(psi)^2
-      weights = (2.0 * (1.0 - ratio) / total).reshape(1, -1).contiguous()
-      return loss, weights
+      signed = not (model.fast and target.fast)
+      _native.swo_weights(z.contiguous(), zt.contiguous(), log_norm, total,
+                          sign=sg.contiguous() if signed else None,
+                          sign_target=st.contiguous() if signed else None,
+                          out=weights, loss_acc=acc)
 
-    def train_step():                      # optimizer.minimize(loss), training.py:175
-      loss, weights = loss_and_weights()
+    def gradient():
+      loss_and_weights(None)
       grad.zero_()
       model.weighted_grad_sum(configs.packed, weights, grad)
+
+    def train_step():                      # optimizer.minimize(loss), training.py:175
+      gradient()
       distributed.allreduce_(grad)
       model.apply_gradients(grad[0])
-      return loss
 
     def metrics():
-      loss, _ = loss_and_weights()
-      return float(distributed.allreduce_(loss.clone()).item())
+      loss_acc.zero_()
+      loss_and_weights(loss_acc)
+      acc = distributed.allreduce_(loss_acc.clone())
+      return float((acc[0] / acc[1]).item())
 
+    # ---- captured batch: sweep group + train step ---------------------------
+    n_sweep_steps = hparams.num_monte_carlo_sweeps * n_sites
+    graphable = (self.use_cuda_graph and model.fast and target.fast and
+                 all(isinstance(o, AdamOptimizer) for o in model.optimizers))
+    captured = {}
+
+    def capture():
+      state, ansatz, opt, params = configs.state, model.ansatz, model.optimizers[0], model.leaf_params[0]
+      opt.device_state(params)
+      lib = _native.load()
+
+      def front():       # sweep on the current parameters, then loss weights and the local gradient
+        _native.check(lib.cgsvmc_ansatz_params_changed(ansatz._handle))    # tables follow the last update
+        state.mc_steps_graph(ansatz, n_sweep_steps)
+        gradient()
+
+      def back():
+        opt.apply_gradients_captured(params, grad[0])
+
+      state.step_dev.fill_(state.step)
+      saved = (state.packed.clone(), state.accept_count.clone(), params.clone(), opt.m.clone(),
+               opt.v.clone(), opt.t_dev.clone())
+      side = torch.cuda.Stream(device=dev)
+      side.wait_stream(torch.cuda.current_stream())
+      with torch.cuda.stream(side):        # warm-up sizes every scratch buffer
+        front(); back()
+      torch.cuda.current_stream().wait_stream(side)
+      torch.cuda.synchronize()
+      for dst, src in zip((state.packed, state.accept_count, params, opt.m, opt.v, opt.t_dev), saved):
+        dst.copy_(src)
+      state.step_dev.fill_(state.step)
+      graphs = []
+      sharded = distributed.world_size() > 1
+      for body in ((front, back) if sharded else (lambda: (front(), back()),)):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+          body()
+        graphs.append(g)
+      captured.update(graphs=graphs, sharded=sharded, opt=opt, state=state, params=params)
+
+    def batch_step():
+      """One iteration of training.py:208-212."""
+      if not captured:
+        try:
+          capture()
+        except NotImplementedError:        # no capturable sampler for this shape: the two ops, eagerly
+          captured['eager'] = True
+      if captured.get('eager'):
+        mc_step(n_steps=n_sweep_steps)
+        train_step()
+        return
+      state, opt = captured['state'], captured['opt']
+      if state.step != captured.get('expected_step'):
+        state.step_dev.fill_(state.step)
+      opt.sync_device(1)
+      captured['graphs'][0].replay()
+      if captured['sharded']:
+        distributed.allreduce_(grad)
+        captured['graphs'][1].replay()
+      torch.autograd.graph.increment_version(captured['params'])
+      state.step += n_sweep_steps
+      state.proposed += n_sweep_steps * state.batch_size
+      captured['expected_step'] = state.step
+
+    self._batch_step = Op(batch_step, 'batch_step') if graphable else None
     return TrainOpsSupervised(
         accumulate_gradients=None, apply_gradients=Op(train_step, 'train_step'),
         reset_gradients=None, mc_step=mc_step, acc_rate=acc_rate,
@@ -333,7 +461,11 @@ class SupervisedWavefunctionOptimizer:
   def run_optimization_epoch(self, train_ops, session, hparams, epoch_number):
     """training.py:192-212."""
     del epoch_number
+    fused = getattr(self, '_batch_step', None)
     for _ in range(hparams.num_batches_per_epoch):
+      if fused is not None:       # the same two ops as one replayed graph
+        session.run(fused)
+        continue
       session.run(train_ops.mc_step,
                   n_steps=hparams.num_monte_carlo_sweeps * hparams.num_sites)
       session.run(train_ops.apply_gradients)

@@ -304,6 +304,39 @@ int cgsvmc_local_energy_from_amps(const cgsvmc_ham* ham, const uint64_t* packed,
 int cgsvmc_energy_stats(const float* e_loc, int64_t n_walkers, double* stats,
                         void* stream);
 
+/* Replaces the loss / gradient-weight arithmetic of
+ * SupervisedWavefunctionOptimizer.build_opt_ops (training.py:166-175) for one
+ * batch, in one kernel: with r_b = psi_target(s_b) sqrt(2^N) / psi(s_b) formed
+ * in the log domain from cgsvmc_log_amp of the two wavefunctions (log_norm =
+ * N/2 log 2 plus the difference of the exp_norm_shifts; sign arrays NULL = +1),
+ *   weights_out[b] = 2 (1 - r_b) * inv_total     (d loss / d log psi_b; feed to
+ *                                                 cgsvmc_weighted_grad_sum)
+ *   loss_acc (double [2], nullable) += { sum_b (1 - r_b)^2, B }
+ * so that loss = loss_acc[0] / loss_acc[1] is tf.reduce_mean((psi - t)^2 /
+ * stop_gradient(psi)^2). */
+int cgsvmc_swo_weights(const float* log_amp, const float* sign,
+                       const float* log_amp_target, const float* sign_target,
+                       int64_t n_walkers, float log_norm, float inv_total,
+                       float* weights_out, double* loss_acc, void* stream);
+
+/* Replaces optimizer.apply_gradients / optimizer.minimize with
+ * tf.train.AdamOptimizer(lr, beta2=hparams.beta2) (training.py:76-91, 175,
+ * 565-567) on the flat parameter buffer, in one kernel:
+ *   m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2
+ *   params -= lr sqrt(1 - b2^t) / (1 - b1^t) m / (sqrt(v) + eps).
+ * The gradient g is `grad` (float32 [n]) or, when `sums` is given instead, the
+ * energy gradient of training.py:562-564 formed on the fly from the estimator
+ * sums (float32 [2, n]) and statistics (double [4]) of cgsvmc_accumulate:
+ *   g = (sums[1] - stats[0] / stats[2] * sums[0]) * inv_num_batches.
+ * lr_dev / t_dev, when non-NULL, are device scalars read instead of lr / t
+ * (t_dev holds the number of steps taken so far and is advanced by one on the
+ * stream): the call is then CUDA-graph safe. */
+int cgsvmc_adam_step(float* params, float* m, float* v, int64_t n,
+                     const float* grad, const float* sums, const double* stats,
+                     float inv_num_batches, float lr, const float* lr_dev,
+                     float beta1, float beta2, float eps, uint64_t t,
+                     uint64_t* t_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -179,3 +179,108 @@ def test_supervised_optimizers_increase_overlap(optimizer):
     opt.run_optimization_epoch(ops, s, hp, epoch)
   after = _overlap(trainee, target, cfg)
   assert after > before and 1.0 - after < 0.5 * (1.0 - before), (before, after)
+
+
+# ---------------------------------------------------------------------------
+# SWO loss / weights and the optimizer update on the device
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['rbm_6x6', 'fc_chain20', 'conv2d_6x6_k3'])
+def test_swo_weights_kernel_golden(name):
+  """cgsvmc_swo_weights + cgsvmc_weighted_grad_sum against the loss and the
+  gradient the reference's SupervisedWavefunctionOptimizer graph produced
+  (training.py:166-175)."""
+  from cgs_vmc_b200 import _native
+  from gpu_util import make_native, packed_cuda
+  spec, g = load_golden(name)
+  a = make_native(spec, g['params_flat'])
+  target = make_native(spec, g['swo_target_params_flat'])
+  packed = packed_cuda(g['swo_configs'])
+  b = packed.shape[0]
+  z, zt = a.log_amp(packed), target.log_amp(packed)
+  log_norm = 0.5 * spec.n_sites * np.log(2.0) - float(g['swo_target_shift']) + float(g['shift'])
+  acc = torch.zeros(2, dtype=torch.float64, device='cuda')
+  w = _native.swo_weights(z, zt, log_norm, b, loss_acc=acc)
+  assert acc[1].item() == b
+  loss = (acc[0] / acc[1]).item()
+  assert abs(loss - float(g['swo_loss'])) <= 5e-4 * abs(loss) + 1e-6
+  grad = a.weighted_grad_sum(packed, w)[0].cpu().numpy()
+  ref = g['swo_gradient']
+  assert np.linalg.norm(grad - ref) <= 1e-3 * np.linalg.norm(ref) + 1e-6
+  # signs: r -> sign * sign_t * r
+  sg = torch.where(torch.arange(b, device='cuda') % 2 == 0, 1.0, -1.0).float()
+  w2 = _native.swo_weights(z, zt, log_norm, b, sign=sg)
+  r = 1.0 - w[0] * b / 2.0
+  torch.testing.assert_close(w2[0], 2.0 * (1.0 - sg * r) / b, rtol=1e-5, atol=1e-6)
+
+
+def test_adam_step_kernel_matches_tf_rule():
+  """cgsvmc_adam_step against tf.train.AdamOptimizer's update rule in float64
+  (training.py:76-91), with the gradient given and with the energy gradient
+  formed from the estimator sums (training.py:562-564); device-side t / lr."""
+  from cgs_vmc_b200 import _native
+  rng = np.random.default_rng(0)
+  n, b1, b2, eps, lr = 1000, 0.9, 0.99, 1e-8, 0.01
+  p0 = rng.normal(size=n)
+  params = torch.from_numpy(p0).float().cuda()
+  m, v = torch.zeros_like(params), torch.zeros_like(params)
+  pr, mr, vr = p0.astype(np.float32).astype(np.float64), np.zeros(n), np.zeros(n)
+  t_dev = torch.zeros(1, dtype=torch.int64, device='cuda')
+  lr_dev = torch.full((1,), lr, dtype=torch.float32, device='cuda')
+  for t in range(1, 6):
+    sums = rng.normal(size=(2, n)).astype(np.float32)
+    stats = np.array([-3.5 * 64, 900.0, 64.0, 0.0])
+    nb = 4.0
+    if t % 2:
+      g = rng.normal(size=n).astype(np.float32).astype(np.float64)
+      kw = dict(grad=torch.from_numpy(g).float().cuda())
+    else:
+      g = sums[1].astype(np.float64) / nb - (stats[0] / stats[2]) * sums[0].astype(np.float64) / nb
+      kw = dict(sums=torch.from_numpy(sums).cuda(), stats=torch.from_numpy(stats).cuda(), num_batches=nb)
+    version = params._version
+    if t <= 3:
+      _native.adam_step(params, m, v, lr=lr, beta1=b1, beta2=b2, eps=eps, t=t, **kw)
+    else:      # device scalars (CUDA-graph form): t_dev holds the steps taken so far
+      t_dev.fill_(t - 1)
+      _native.adam_step(params, m, v, lr_dev=lr_dev, beta1=b1, beta2=b2, eps=eps, t_dev=t_dev, **kw)
+      assert t_dev.item() == t
+    assert params._version > version          # ansatz handles see the change
+    mr = b1 * mr + (1 - b1) * g
+    vr = b2 * vr + (1 - b2) * g * g
+    pr = pr - lr * np.sqrt(1 - b2 ** t) / (1 - b1 ** t) * mr / (np.sqrt(vr) + eps)
+    np.testing.assert_allclose(params.cpu().numpy(), pr, rtol=2e-5, atol=2e-6)
+  with pytest.raises(ValueError):
+    _native.adam_step(params, m, v, lr=lr, t=1)           # neither grad nor sums
+
+
+def test_supervised_captured_batch_equals_eager_ops():
+  """SupervisedWavefunctionOptimizer: the replayed graph of one batch (sweep +
+  train step) leaves the same parameters and walkers as session.run(mc_step) x
+  N followed by session.run(apply_gradients) (training.py:208-212)."""
+  from cgs_vmc_b200 import graph_builders, training, utils, wavefunctions
+  from cgs_vmc_b200.session import Session
+  results = []
+  for use_graph in (True, False):
+    graph_builders.reset_num_epochs()
+    hp = utils.create_hparams(wavefunction_type='rbm', num_sites=16, num_fc_layers=0, fc_layer_size=12,
+                              batch_size=512, num_batches_per_epoch=3, learning_rates=[0.01] * 4)
+    target = wavefunctions.build_wavefunction(hp).seed(7)
+    trainee = wavefunctions.build_wavefunction(hp).seed(8)
+    target.native(16)
+    target._exp_norm_shift += 0.5 * 16 * np.log(2.0)
+    opt = training.SUPERVISED_OPTIMIZERS['SWO']()
+    opt.use_cuda_graph = use_graph
+    shared = {}
+    ops = opt.build_opt_ops(wavefunction=trainee, target_wavefunction=target, hparams=hp,
+                            shared_resources=shared)
+    assert (opt._batch_step is not None) == use_graph
+    s = Session()
+    for epoch in range(2):
+      opt.run_optimization_epoch(ops, s, hp, epoch)
+    loss = s.run(ops.metrics)
+    configs = shared[graph_builders.ResourceName.CONFIGS]
+    results.append((trainee.flat_parameters.clone(), configs.packed.clone(), loss, configs.state.step))
+  (p1, c1, l1, s1), (p2, c2, l2, s2) = results
+  assert s1 == s2 == 2 * 3 * 16
+  assert torch.equal(c1, c2)
+  torch.testing.assert_close(p1, p2, rtol=1e-5, atol=1e-6)
+  assert abs(l1 - l2) <= 1e-5 * abs(l2) + 1e-7
