@@ -63,6 +63,7 @@ struct TcDesc {
   int n_wbuf;               // weight buffers in shared memory (1 or 2)
   int tmem_cols;
   int n_pairs;              // ceil(kx / 2): MMAs per tile of layer 1
+  int ctas;                 // CTAs per SM the plan was sized for (1 or 2)
   const __half* w1img;      // [n_pairs][2][3C][8]   layer 1 B operand
   const __half* wimg;       // [n_tensor][taps][C/8][3C][8]
   const float* bias;        // [L - 1][C]  layers 1 .. L-1
@@ -245,14 +246,14 @@ struct Engine {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     tmem = *tmem_holder;
     // weights of the first tensor layer
-    if (threadIdx.x == 0 && d.n_wbuf == 2 && d.n_tensor > 0)
+    if (threadIdx.x == 0 && d.n_tensor > 0)
       bulk_load_async(wbuf, d.wimg, (uint32_t)d.wbuf_bytes, wbar);
   }
 
   __device__ void teardown() {
     // a prefetch issued by the last forward may still be in flight
-    if (d.n_wbuf == 2 && d.n_tensor > 0) {
-      if ((use_count & 1u) == 0) mbar_wait(wbar, wphase0); else mbar_wait(wbar + 1, wphase1);
+    if (d.n_tensor > 0) {
+      if (d.n_wbuf == 1 || (use_count & 1u) == 0) mbar_wait(wbar, wphase0); else mbar_wait(wbar + 1, wphase1);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -350,9 +351,6 @@ struct Engine {
         uint64_t* bar = wbar + buf;
         const uint32_t ph = buf ? wphase1 : wphase0;
         const int j = layer - 1;
-        if (d.n_wbuf == 1 && lane == 0)
-          bulk_load_async(wb, reinterpret_cast<const char*>(d.wimg) + (size_t)j * d.wbuf_bytes,
-                          (uint32_t)d.wbuf_bytes, bar);
         mbar_wait(bar, ph);
         if (d.n_wbuf == 2 && lane == 0) {   // prefetch the next layer's weights (wraps to the next forward)
           const int jn = (j + 1) % d.n_tensor;
@@ -428,6 +426,13 @@ struct Engine {
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // one weight buffer: the MMAs that read it have completed, so the next
+    // layer's weights (wrapping to the next forward) stream in under the epilogue
+    if (!first && d.n_wbuf == 1 && threadIdx.x == 0) {
+      const int jn = layer % d.n_tensor;          // (j + 1) % n_tensor with j = layer - 1
+      bulk_load_async(wbuf, reinterpret_cast<const char*>(d.wimg) + (size_t)jn * d.wbuf_bytes,
+                      (uint32_t)d.wbuf_bytes, wbar);
+    }
 
     // ---- epilogue: TMEM -> bias -> nonlinearity -> next operand planes / row sums ----
     const int q = warp & 3;
@@ -514,8 +519,8 @@ __device__ __forceinline__ Extras carve_extras(const TcDesc& d, char* smem) {
 }
 __host__ __device__ inline size_t extras_bytes(const TcDesc& d) { return (size_t)d.G * d.NW * 16 + (size_t)d.G * 12 + 16; }
 
-template <int CC>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CC, int CTAS>
+__global__ void __launch_bounds__(kThreads, CTAS)
 tc_log_amp_kernel(TcDesc d, const uint64_t* __restrict__ packed, int64_t B, float* __restrict__ out) {
   extern __shared__ __align__(1024) char smem[];
   Engine eng(d);
@@ -548,8 +553,8 @@ __device__ __forceinline__ int kth_set_bit(const uint64_t* words, int nw, int k)
 // graph_builders.py:54-89 x n_steps; a CTA owns G walkers for all steps, one
 // forward pass per proposal (the reference runs two), z of the current
 // configuration cached.  Same Philox stream as every other sampler kernel.
-template <int CC>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CC, int CTAS>
+__global__ void __launch_bounds__(kThreads, CTAS)
 tc_mc_kernel(TcDesc d, uint64_t* __restrict__ packed, int64_t B, int n_steps, uint64_t seed,
              uint64_t walker0, uint64_t step0, const uint64_t* __restrict__ step0_dev,
              unsigned long long* accept_count, float* __restrict__ log_amp_out) {
@@ -619,8 +624,8 @@ tc_mc_kernel(TcDesc d, uint64_t* __restrict__ packed, int64_t B, int n_steps, ui
 
 // operators.py:227-259: a CTA takes one walker at a time, lists its antiparallel
 // bonds and evaluates the base configuration and every flipped one G at a time.
-template <int CC>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CC, int CTAS>
+__global__ void __launch_bounds__(kThreads, CTAS)
 tc_eloc_kernel(TcDesc d, const int2* __restrict__ bonds_ij, const float* __restrict__ bonds_jx,
                const float* __restrict__ bonds_jz, int n_bonds, const uint64_t* __restrict__ packed,
                int64_t B, float* __restrict__ e_loc, float* __restrict__ log_amp_out,
@@ -765,7 +770,24 @@ bool tc_enabled() {
 
 // Geometry and shared-memory plan; false when the network is outside the
 // tensor-core path (the SIMT tile kernels of net.cu take over).
+// CTAs per SM the kernels are planned for.  Two (default): each CTA runs its
+// layers as [MMAs of all tiles] -> [epilogue of all tiles]; with two resident
+// CTAs the tensor pipe works for one while the other runs its epilogue, and the
+// single weight buffer is refilled under the epilogue.  CGSVMC_CONV_TC_CTAS=1
+// selects the one-CTA plan (larger batches, double-buffered weights).
+int tc_ctas_wanted() {
+  const char* e = getenv("CGSVMC_CONV_TC_CTAS");
+  return e != nullptr && atoi(e) == 1 ? 1 : 2;
+}
+
+bool make_desc_ctas(const cgsvmc_ansatz* a, size_t extra_bytes_per_cfg, size_t extra_fixed, int ctas, TcDesc* out);
+
 bool make_desc_host(const cgsvmc_ansatz* a, size_t extra_bytes_per_cfg, size_t extra_fixed, TcDesc* out) {
+  if (tc_ctas_wanted() == 2 && make_desc_ctas(a, extra_bytes_per_cfg, extra_fixed, 2, out)) return true;
+  return make_desc_ctas(a, extra_bytes_per_cfg, extra_fixed, 1, out);
+}
+
+bool make_desc_ctas(const cgsvmc_ansatz* a, size_t extra_bytes_per_cfg, size_t extra_fixed, int ctas, TcDesc* out) {
   const cgsvmc_ansatz_desc& s = a->desc;
   if (s.kind != CGSVMC_ANSATZ_CONV_1D && s.kind != CGSVMC_ANSATZ_CONV_2D) return false;
   if (s.num_layers < 3 || (s.num_filters != 16 && s.num_filters != 32)) return false;
@@ -786,19 +808,23 @@ bool make_desc_host(const cgsvmc_ansatz* a, size_t extra_bytes_per_cfg, size_t e
   d.n_tensor = d.L - 2;
   d.n_pairs = (d.kx + 1) / 2;
   d.wbuf_bytes = d.kx * d.ky * 3 * d.C * d.C * 2;
-  const size_t limit = (size_t)a->max_smem_optin;
+  // two CTAs share the SM's 228 KB, 1 KB of each CTA's share is reserved by the
+  // driver; a little is kept for the kernels' static __shared__ variables
+  const size_t limit = ctas == 1 ? (size_t)a->max_smem_optin : (size_t)(233472 / 2 - 1024 - 256);
+  const int tmem_limit = 512 / ctas;
+  d.ctas = ctas;
   bool found = false;
   // double-buffered weights (the next layer's load overlaps the MMAs) when at
   // least two configurations still fit, else one buffer and a larger batch
-  for (int n_wbuf = 2; n_wbuf >= 1 && !found; --n_wbuf) {
-    for (int G = 16; G >= (n_wbuf == 2 ? 2 : 1); --G) {
+  for (int n_wbuf = ctas == 1 ? 2 : 1; n_wbuf >= 1 && !found; --n_wbuf) {
+    for (int G = 16; G >= (n_wbuf == 2 || ctas == 2 ? 2 : 1); --G) {
       TcDesc t = d;
       t.n_wbuf = n_wbuf; t.G = G; t.GW = G * t.PW;
       t.rows_out = t.X * t.GW;
       t.n_tiles = (t.rows_out + 127) / 128;
       t.rows_total = (t.n_tiles * 128 + (t.kx - 1) * t.GW + t.ky + 7) / 8 * 8;
       t.rows_total = std::max(t.rows_total, (t.PH * t.GW + 8 + 7) / 8 * 8);
-      if (t.rows_total > 16383 || t.n_tiles * 3 * t.C > 512) continue;
+      if (t.rows_total > 16383 || t.n_tiles * 3 * t.C > tmem_limit) continue;
       int cols = 32;
       while (cols < t.n_tiles * 3 * t.C) cols *= 2;
       t.tmem_cols = cols;
@@ -874,19 +900,31 @@ bool conv_tc_supported(const cgsvmc_ansatz* a, const cgsvmc_ham* h) {
   return make_desc_host(a, 0, fixed, &d);
 }
 
+// Launches KERNEL<C, CTAS> for the plan `d` (C in {16, 32}, one or two CTAs per SM).
+#define CGSVMC_TC_LAUNCH(KERNEL, grid, smem, st, ...)                                           \
+  do {                                                                                          \
+    if (d.C == 16 && d.ctas == 2) {                                                             \
+      if (int rc = opt_in(KERNEL<16, 2>, smem)) return rc;                                      \
+      KERNEL<16, 2><<<grid, kThreads, smem, st>>>(__VA_ARGS__);                                 \
+    } else if (d.C == 16) {                                                                     \
+      if (int rc = opt_in(KERNEL<16, 1>, smem)) return rc;                                      \
+      KERNEL<16, 1><<<grid, kThreads, smem, st>>>(__VA_ARGS__);                                 \
+    } else if (d.ctas == 2) {                                                                   \
+      if (int rc = opt_in(KERNEL<32, 2>, smem)) return rc;                                      \
+      KERNEL<32, 2><<<grid, kThreads, smem, st>>>(__VA_ARGS__);                                 \
+    } else {                                                                                    \
+      if (int rc = opt_in(KERNEL<32, 1>, smem)) return rc;                                      \
+      KERNEL<32, 1><<<grid, kThreads, smem, st>>>(__VA_ARGS__);                                 \
+    }                                                                                           \
+  } while (0)
+
 int conv_tc_log_amp(cgsvmc_ansatz* a, const uint64_t* packed, int64_t B, float* out, cudaStream_t st) {
   TcDesc d;
   if (!make_desc_host(a, 0, 0, &d)) { set_error("conv_tc: unsupported network"); return CGSVMC_ERR_UNSUPPORTED; }
   if (int rc = build_tc_image(a, &d, st)) return rc;
   const size_t smem = smem_plan(d).total + extras_bytes(d);
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((B + d.G - 1) / d.G, a->num_sms));
-  if (d.C == 16) {
-    if (int rc = opt_in(tc_log_amp_kernel<16>, smem)) return rc;
-    tc_log_amp_kernel<16><<<grid, kThreads, smem, st>>>(d, packed, B, out);
-  } else {
-    if (int rc = opt_in(tc_log_amp_kernel<32>, smem)) return rc;
-    tc_log_amp_kernel<32><<<grid, kThreads, smem, st>>>(d, packed, B, out);
-  }
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((B + d.G - 1) / d.G, (int64_t)a->num_sms * d.ctas));
+  CGSVMC_TC_LAUNCH(tc_log_amp_kernel, grid, smem, st, d, packed, B, out);
   return cuda_fail(cudaGetLastError(), "conv_tc log_amp launch");
 }
 
@@ -896,7 +934,7 @@ int conv_tc_mc_steps(cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int n_steps,
   TcDesc d;
   if (!make_desc_host(a, 0, 0, &d)) { set_error("conv_tc: unsupported network"); return CGSVMC_ERR_UNSUPPORTED; }
   // do not starve the grid: fewer walkers per CTA when there are few walkers
-  while (d.G > 1 && (B + d.G - 1) / d.G < a->num_sms) {
+  while (d.G > 1 && (B + d.G - 1) / d.G < (int64_t)a->num_sms * d.ctas) {
     TcDesc t = d;
     t.G = d.G - 1; t.GW = t.G * t.PW; t.rows_out = t.X * t.GW;
     t.n_tiles = (t.rows_out + 127) / 128;
@@ -908,16 +946,9 @@ int conv_tc_mc_steps(cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int n_steps,
   }
   if (int rc = build_tc_image(a, &d, st)) return rc;
   const size_t smem = smem_plan(d).total + extras_bytes(d);
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((B + d.G - 1) / d.G, a->num_sms));
-  if (d.C == 16) {
-    if (int rc = opt_in(tc_mc_kernel<16>, smem)) return rc;
-    tc_mc_kernel<16><<<grid, kThreads, smem, st>>>(d, packed, B, n_steps, seed, walker0, step0,
-                                                  a->step_counter_dev, accept_count, log_amp_out);
-  } else {
-    if (int rc = opt_in(tc_mc_kernel<32>, smem)) return rc;
-    tc_mc_kernel<32><<<grid, kThreads, smem, st>>>(d, packed, B, n_steps, seed, walker0, step0,
-                                                  a->step_counter_dev, accept_count, log_amp_out);
-  }
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((B + d.G - 1) / d.G, (int64_t)a->num_sms * d.ctas));
+  CGSVMC_TC_LAUNCH(tc_mc_kernel, grid, smem, st, d, packed, B, n_steps, seed, walker0, step0,
+                   a->step_counter_dev, accept_count, log_amp_out);
   return cuda_fail(cudaGetLastError(), "conv_tc mc launch");
 }
 
@@ -929,16 +960,9 @@ int conv_tc_local_energy(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* 
   if (!make_desc_host(a, 0, fixed, &d)) { set_error("conv_tc: unsupported network"); return CGSVMC_ERR_UNSUPPORTED; }
   if (int rc = build_tc_image(a, &d, st)) return rc;
   const size_t smem = smem_plan(d).total + extras_bytes(d) + fixed;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(B, a->num_sms));
-  if (d.C == 16) {
-    if (int rc = opt_in(tc_eloc_kernel<16>, smem)) return rc;
-    tc_eloc_kernel<16><<<grid, kThreads, smem, st>>>(d, h->ij, h->jx, h->jz, h->n_bonds, packed, B, e_loc,
-                                                    log_amp_out, diag_out, off_out);
-  } else {
-    if (int rc = opt_in(tc_eloc_kernel<32>, smem)) return rc;
-    tc_eloc_kernel<32><<<grid, kThreads, smem, st>>>(d, h->ij, h->jx, h->jz, h->n_bonds, packed, B, e_loc,
-                                                    log_amp_out, diag_out, off_out);
-  }
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)a->num_sms * d.ctas));
+  CGSVMC_TC_LAUNCH(tc_eloc_kernel, grid, smem, st, d, h->ij, h->jx, h->jz, h->n_bonds, packed, B, e_loc,
+                   log_amp_out, diag_out, off_out);
   return cuda_fail(cudaGetLastError(), "conv_tc local_energy launch");
 }
 
