@@ -283,10 +283,10 @@ class EnergyGradientWorkload:
     rebuilt = getattr(self, '_seen_version', None) != version
     self._seen_version = version
     self.graphed.replay()
-    # pure RBM: fused estimator + sweep kernel, reduction (+ table build and
-    # bond-pair table after a parameter update); tile networks: fill, local
-    # energy, copy, gradient, reduction, statistics, sampler, counter
-    self.launches += (2 + (2 if rebuilt else 0)) if self.fused else 8
+    # pure RBM: ONE kernel (estimators + sweep + cross-CTA reduction; + table
+    # build and bond-pair table after a parameter update); tile networks: fill,
+    # local energy, copy, gradient, reduction, statistics, sampler, counter
+    self.launches += (1 + (2 if rebuilt else 0)) if self.fused else 8
 
   def epoch_end(self):
     """training.py:618-622: apply_gradients (all-reduce over the walker shards,
@@ -673,9 +673,9 @@ def run_ours(args, rank, world, local_rank):
       'config_detail': {
           'n_params': P,
           'l2': 'flushed: %d MiB memset between steps, outside the per-step CUDA-event pairs' % (L2_FLUSH_BYTES >> 20),
-          'launch': 'one captured CUDA graph per step: cgsvmc_batch_step = fused estimator + sweep kernel and '
-                    'the deterministic reduction; the parameter tables are rebuilt in the first step after '
-                    'every Adam update',
+          'launch': 'one captured CUDA graph per step holding cgsvmc_batch_step = ONE cooperative kernel '
+                    '(estimators + sweep + deterministic cross-CTA reduction); the parameter tables are '
+                    'rebuilt in the first step after every Adam update',
           'timed_region': 'whole epochs of %d steps: every step plus the epoch end (float64 all-reduce of '
                           '[2P+4], gradient + Adam kernel, mean energy to the host, reset)' % epoch_len,
           'parallelism': 'walkers sharded, params replicated' + (

@@ -30,7 +30,7 @@ EXPORTS = [
     'cgsvmc_flip_enum', 'cgsvmc_local_energy', 'cgsvmc_weighted_grad_sum',
     'cgsvmc_energy_stats', 'cgsvmc_accumulate', 'cgsvmc_batch_step',
     'cgsvmc_propose_exchange', 'cgsvmc_accept_exchange', 'cgsvmc_local_energy_from_amps',
-    'cgsvmc_swo_weights', 'cgsvmc_adam_step',
+    'cgsvmc_swo_weights', 'cgsvmc_adam_step', 'cgsvmc_batch_step_fed',
 ]
 
 
@@ -86,6 +86,7 @@ def load():
   lib.cgsvmc_accept_exchange.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]
   lib.cgsvmc_local_energy_from_amps.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
   f32 = ctypes.c_float
+  lib.cgsvmc_batch_step_fed.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, u64, u64, u64, vp, vp, vp, vp]
   lib.cgsvmc_swo_weights.argtypes = [vp, vp, vp, vp, i64, f32, f32, vp, vp, vp]
   lib.cgsvmc_adam_step.argtypes = [vp, vp, vp, i64, vp, vp, vp, f32, f32, vp, f32, f32, f32, u64, vp, vp]
   for name in EXPORTS:
@@ -310,6 +311,35 @@ class Ansatz:
                                    _ptr(log_amp_out), _ptr(sums), _ptr(stats), int(n_steps),
                                    int(seed), int(walker_id0), int(step0), _ptr(step_counter),
                                    _ptr(accept_count), _stream()))
+
+
+  def batch_step_fed(self, ham, configs_f32, packed_out, sums, stats, n_steps, seed, walker_id0,
+                     step_counter, accept_count=None, e_loc_out=None, stats_out=None):
+    """batch_step for a host-fed caller (cgsvmc_batch_step_fed): `configs_f32`
+    (device float32 [B, N] of +-1, or None to step `packed_out` in place) is
+    packed inside the walker kernel, `stats_out` (float64 [4]; a pinned host
+    tensor is written directly from the device) receives the updated energy
+    statistics.  CUDA-graph safe (device-side step counter)."""
+    self._sync_params()
+    b = packed_out.shape[0]
+    _want(packed_out, torch.int64, (b, n_words(self.n_sites)), 'packed_out')
+    if configs_f32 is not None:
+      _want(configs_f32, torch.float32, (b, self.n_sites), 'configs_f32')
+    _want(sums, torch.float32, (2, self.num_params), 'sums')
+    _want(stats, torch.float64, (4,), 'stats')
+    _want(step_counter, torch.int64, (1,), 'step_counter')
+    if accept_count is not None:
+      _want(accept_count, torch.int64, (1,), 'accept_count')
+    if e_loc_out is not None:
+      _want(e_loc_out, torch.float32, (b,), 'e_loc_out')
+    if stats_out is not None:
+      if stats_out.dtype != torch.float64 or stats_out.numel() != 4 or not stats_out.is_contiguous() or not (
+          stats_out.is_cuda or stats_out.is_pinned()):
+        raise ValueError('stats_out must be a contiguous float64 [4] tensor on the device or in pinned host memory')
+    check(load().cgsvmc_batch_step_fed(self._handle, ham._handle, _ptr(configs_f32), _ptr(packed_out), b,
+                                       _ptr(e_loc_out), None, _ptr(sums), _ptr(stats), int(n_steps),
+                                       int(seed), int(walker_id0), 0, _ptr(step_counter),
+                                       _ptr(accept_count), _ptr(stats_out), _stream()))
 
 
 class Hamiltonian:

@@ -174,6 +174,7 @@ int cgsvmc_ansatz_destroy(cgsvmc_ansatz* a) {
   for (void* p : a->retired) cudaFree(p);
   if (a->tables != nullptr) cudaFree(a->tables);
   if (a->acc_weights != nullptr) cudaFree(a->acc_weights);
+  if (a->grid_sync != nullptr) cudaFree(a->grid_sync);
   for (auto& pt : a->pair_tables)
     if (pt.buf != nullptr) cudaFree(pt.buf);
   delete a;
@@ -426,11 +427,11 @@ int cgsvmc_accumulate(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_
   return launch_energy_stats(w + B, B, stats, st);
 }
 
-int cgsvmc_batch_step(const cgsvmc_ansatz* a, const cgsvmc_ham* h, uint64_t* packed, int64_t B,
-                      float* e_loc_out, float* log_amp_out, float* sums, double* stats,
-                      int32_t n_steps, uint64_t seed, uint64_t walker_id0, uint64_t step0,
-                      uint64_t* step_counter, unsigned long long* accept_count, void* stream) {
-  NvtxRange range("cgsvmc:K2+K3+K4+K5 batch_step");
+static int batch_step_impl(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const float* configs_f32,
+                           uint64_t* packed, int64_t B, float* e_loc_out, float* log_amp_out, float* sums,
+                           double* stats, int32_t n_steps, uint64_t seed, uint64_t walker_id0, uint64_t step0,
+                           uint64_t* step_counter, unsigned long long* accept_count, double* stats_out,
+                           void* stream) {
   if (int rc = check_ready(a)) return rc;
   if (h == nullptr) return invalid("batch_step: NULL hamiltonian");
   if (h->n_sites != a->desc.n_sites) return invalid("batch_step: hamiltonian and ansatz n_sites differ");
@@ -441,18 +442,44 @@ int cgsvmc_batch_step(const cgsvmc_ansatz* a, const cgsvmc_ham* h, uint64_t* pac
   if (rbm2_supported(a, h)) {
     cgsvmc_ansatz* am = const_cast<cgsvmc_ansatz*>(a);
     Rbm2Sweep sw = {n_steps, seed, walker_id0, step_counter != nullptr ? 0 : step0, accept_count,
-                    step_counter};   // the reduction kernel advances the counter
+                    step_counter,   // the reduction advances the counter
+                    configs_f32, stats_out};
     am->step_counter_dev = step_counter;
     const int rc = rbm2_walker(am, h, packed, B, e_loc_out, log_amp_out, nullptr, nullptr, true, nullptr, 2,
                                sums, stats, st, &sw);
     am->step_counter_dev = nullptr;
     return rc;
   }
+  if (configs_f32 != nullptr)
+    if (int rc = launch_pack(configs_f32, B, a->desc.n_sites, packed, st)) return rc;
   if (int rc = cgsvmc_accumulate(a, h, packed, B, e_loc_out, log_amp_out, sums, stats, stream)) return rc;
+  if (stats_out != nullptr)
+    if (int rc = cuda_fail(cudaMemcpyAsync(stats_out, stats, 4 * sizeof(double), cudaMemcpyDefault, st),
+                           "batch_step stats copy"))
+      return rc;
   if (step_counter != nullptr)
     return cgsvmc_mc_steps_graph(a, packed, B, n_steps, seed, walker_id0, step_counter, accept_count,
                                  nullptr, stream);
   return cgsvmc_mc_steps(a, packed, B, n_steps, seed, walker_id0, step0, accept_count, nullptr, stream);
+}
+
+int cgsvmc_batch_step(const cgsvmc_ansatz* a, const cgsvmc_ham* h, uint64_t* packed, int64_t B,
+                      float* e_loc_out, float* log_amp_out, float* sums, double* stats,
+                      int32_t n_steps, uint64_t seed, uint64_t walker_id0, uint64_t step0,
+                      uint64_t* step_counter, unsigned long long* accept_count, void* stream) {
+  NvtxRange range("cgsvmc:K2+K3+K4+K5 batch_step");
+  return batch_step_impl(a, h, nullptr, packed, B, e_loc_out, log_amp_out, sums, stats, n_steps, seed,
+                         walker_id0, step0, step_counter, accept_count, nullptr, stream);
+}
+
+int cgsvmc_batch_step_fed(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const float* configs_f32,
+                          uint64_t* packed_out, int64_t B, float* e_loc_out, float* log_amp_out,
+                          float* sums, double* stats, int32_t n_steps, uint64_t seed, uint64_t walker_id0,
+                          uint64_t step0, uint64_t* step_counter, unsigned long long* accept_count,
+                          double* stats_out, void* stream) {
+  NvtxRange range("cgsvmc:K0+K2+K3+K4+K5 batch_step_fed");
+  return batch_step_impl(a, h, configs_f32, packed_out, B, e_loc_out, log_amp_out, sums, stats, n_steps, seed,
+                         walker_id0, step0, step_counter, accept_count, stats_out, stream);
 }
 
 int cgsvmc_propose_exchange(const uint64_t* packed, int64_t B, int32_t N, uint64_t seed,

@@ -47,6 +47,20 @@
 namespace cgsvmc {
 namespace {
 
+// Development aid (-DCGSVMC_RBM2_TIMING build, profiles/run_conv_tc_phases.py):
+// thread 0 of every CTA accumulates the cycles its tensor layers spend in the
+// MMA phase (issue until the commit barrier flips) and in the epilogue.
+#ifdef CGSVMC_RBM2_TIMING
+__device__ unsigned long long g_tc_phase[4];   // MMA cycles, epilogue cycles, layers, forwards
+#define TC_PHASE_T0() const long long tc_t0_ = clock64()
+#define TC_PHASE_ADD(IDX, T0) do { if (threadIdx.x == 0) atomicAdd(&g_tc_phase[IDX], (unsigned long long)(clock64() - (T0))); } while (0)
+#define TC_PHASE_COUNT(IDX) do { if (threadIdx.x == 0) atomicAdd(&g_tc_phase[IDX], 1ull); } while (0)
+#else
+#define TC_PHASE_T0() do {} while (0)
+#define TC_PHASE_ADD(IDX, T0) do {} while (0)
+#define TC_PHASE_COUNT(IDX) do {} while (0)
+#endif
+
 constexpr int kThreads = 256;
 constexpr float kSplitScale = 2048.f;   // S = 2^11: keeps the lower split terms out of the fp16 subnormals
 constexpr int kWarps = 8;
@@ -344,6 +358,7 @@ struct Engine {
   __device__ void tensor_layer(int layer, int n_cfg) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool first = layer == 0;
+    TC_PHASE_T0();
     const uint32_t buf = (!first && d.n_wbuf == 2) ? (use_count & 1u) : 0u;
     if (warp == 0) {
       char* wb = wbuf + (size_t)buf * d.wbuf_bytes;
@@ -426,6 +441,10 @@ struct Engine {
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    TC_PHASE_ADD(0, tc_t0_);
+#ifdef CGSVMC_RBM2_TIMING
+    const long long tc_t1_ = clock64();
+#endif
     // one weight buffer: the MMAs that read it have completed, so the next
     // layer's weights (wrapping to the next forward) stream in under the epilogue
     if (!first && d.n_wbuf == 1 && threadIdx.x == 0) {
@@ -475,11 +494,14 @@ struct Engine {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    TC_PHASE_ADD(1, tc_t1_);
+    TC_PHASE_COUNT(2);
   }
 
   // z[g] for g < n_cfg; cfg: [G][NW] packed spins in shared memory.
   template <int CC>
   __device__ void forward(const uint64_t* cfg, int n_cfg, float* z) {
+    TC_PHASE_COUNT(3);
     write_spin_plane(cfg, n_cfg);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -967,3 +989,15 @@ int conv_tc_local_energy(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* 
 }
 
 }  // namespace cgsvmc
+
+#ifdef CGSVMC_RBM2_TIMING
+// Development build only: reads (and clears) the conv_tc phase counters
+// [MMA cycles, epilogue cycles, tensor layers, forwards], summed over CTAs.
+extern "C" int cgsvmc_debug_conv_tc_phases(unsigned long long* host_out) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(host_out, cgsvmc::g_tc_phase, 4 * sizeof(unsigned long long));
+  unsigned long long zero[4] = {0, 0, 0, 0};
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(cgsvmc::g_tc_phase, zero, sizeof(zero));
+  return e == cudaSuccess ? 0 : -2;
+}
+#endif

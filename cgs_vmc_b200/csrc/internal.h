@@ -32,6 +32,7 @@ struct cgsvmc_ansatz {
   bool tables_valid = false;       // tables match the bound parameters
   bool track_params = false;       // rebuild tables only after bind_params / params_changed
   const uint64_t* step_counter_dev = nullptr;   // set during cgsvmc_mc_steps_graph: device-side step offset
+  unsigned int* grid_sync = nullptr;   // owned: arrive / depart counters of the in-kernel cross-CTA reduction (rbm2)
   float* acc_weights = nullptr;    // owned: [2, B] weight rows of cgsvmc_accumulate (tile networks)
   size_t acc_weights_bytes = 0;
   // owned: bond-pair tables of the rbm2 walker kernel ([2 n_bonds][HP]), one per
@@ -125,6 +126,8 @@ struct Rbm2Sweep {
   uint64_t seed, walker0, step0;
   unsigned long long* accept_count;
   uint64_t* advance_counter;   // device step counter to advance by n_steps afterwards, or NULL
+  const float* configs_f32;    // optional: the walkers as float32 [B][N] of +-1 (packed is then output only)
+  double* stats_snapshot;      // optional: copy of the updated statistics (may be mapped host memory)
 };
 int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, int64_t B,
                 float* e_loc, float* log_amp, float* diag, float* off, bool do_grad,

@@ -75,7 +75,7 @@ prep_kernel(Image im, const float* __restrict__ a, const float* __restrict__ a0,
 __global__ void __launch_bounds__(256)
 reduce_kernel(const float* __restrict__ partials, int n_cta, int64_t stride, int64_t n_out,
               float* __restrict__ out, const double* __restrict__ stat_partials, int64_t B,
-              double* __restrict__ stats, uint64_t* counter, uint64_t advance) {
+              double* __restrict__ stats, uint64_t* counter, uint64_t advance, double* stats_snapshot) {
   __shared__ float sm[8][32];
   constexpr int U = 19;                       // 8 x 19 = 152 >= 148 CTAs in one sweep
   const int col = threadIdx.x & 31, slice = threadIdx.x >> 5;
@@ -105,9 +105,13 @@ reduce_kernel(const float* __restrict__ partials, int n_cta, int64_t stride, int
     e = warp_sum(e);
     e2 = warp_sum(e2);
     if (threadIdx.x == 0) {
-      stats[0] += e;
-      stats[1] += e2;
-      stats[2] += (double)B;
+      const double s0 = stats[0] + e, s1 = stats[1] + e2, s2 = stats[2] + (double)B;
+      stats[0] = s0; stats[1] = s1; stats[2] = s2;
+      if (stats_snapshot != nullptr) {      // may be mapped host memory
+        volatile double* snap = stats_snapshot;
+        snap[0] = s0; snap[1] = s1; snap[2] = s2; snap[3] = stats[3];
+        __threadfence_system();
+      }
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 32 && counter != nullptr) *counter += advance;
@@ -308,6 +312,25 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
     A.n_steps = sweep->n_steps; A.seed = sweep->seed; A.walker0 = sweep->walker0;
     A.step0 = sweep->step0; A.step0_dev = a->step_counter_dev; A.accept_count = sweep->accept_count;
   }
+  if (mc) A.configs_f32 = sweep->configs_f32;
+  // The cross-CTA reduction runs inside the walker kernel when the device can
+  // launch it cooperatively (all CTAs co-resident: grid <= number of SMs, one
+  // CTA per SM) and the staging buffer is large enough for its scratch.
+  // CGSVMC_RBM2_FUSED_REDUCE=0 keeps the separate reduction kernel.
+  // (read at every call so that tests can compare the two paths)
+  const char* fuse_env = getenv("CGSVMC_RBM2_FUSED_REDUCE");
+  const bool fuse_off = fuse_env != nullptr && atoi(fuse_env) == 0;
+  bool fuse = false;
+  if (do_grad && !fuse_off && pl.grid <= a->num_sms) {
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, a->device);
+    const int threads = variant_slots(pl.lpw, pl.kjv) / (32 / pl.lpw) * 32;
+    fuse = coop != 0 && (size_t)slots * pl.im.HP >= (size_t)(threads / 32) * 96;
+  }
+  if (fuse && a->grid_sync == nullptr) {
+    if (int rc = cuda_fail(cudaMalloc(&a->grid_sync, 128), "grid_sync alloc")) return rc;
+    if (int rc = cuda_fail(cudaMemset(a->grid_sync, 0, 128), "grid_sync clear")) return rc;
+  }
   if (do_grad) {
     const size_t part_bytes = (size_t)pl.grid * 2 * P * sizeof(float);
     const size_t part_pad = (part_bytes + 15) / 16 * 16;
@@ -316,6 +339,15 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
     A.stat_partials = stats != nullptr
         ? reinterpret_cast<double*>(reinterpret_cast<char*>(a->scratch) + part_pad) : nullptr;
   }
+  uint64_t* const step_counter = mc ? sweep->advance_counter : nullptr;
+  double* const snapshot = mc ? sweep->stats_snapshot : nullptr;
+  if (fuse) {
+    A.fuse_reduce = 1;
+    A.sync = a->grid_sync;
+    A.out = out; A.n_out = (int64_t)K * P; A.stats = stats;
+    A.counter = step_counter; A.advance = mc ? (uint64_t)sweep->n_steps : 0ull;
+    A.stats_snapshot = snapshot;
+  }
   int rc;
   switch (pl.nw) {
     case 1: rc = launch_walker_nw1(pl, a->tables, A, st); break;
@@ -323,12 +355,11 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
     default: rc = launch_walker_nw4(pl, a->tables, A, st); break;
   }
   if (rc) return rc;
-  if (do_grad) {
+  if (do_grad && !fuse) {
     const int64_t n_out = (int64_t)K * P;
     const int blocks = (int)((n_out + 31) / 32);
-    uint64_t* counter = mc ? sweep->advance_counter : nullptr;
     reduce_kernel<<<blocks, 256, 0, st>>>(A.partials, pl.grid, 2 * P, n_out, out, A.stat_partials, B, stats,
-                                          counter, mc ? (uint64_t)sweep->n_steps : 0ull);
+                                          step_counter, mc ? (uint64_t)sweep->n_steps : 0ull, snapshot);
     return cuda_fail(cudaGetLastError(), "rbm2 reduce launch");
   }
   return CGSVMC_OK;

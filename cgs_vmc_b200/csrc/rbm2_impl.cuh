@@ -743,7 +743,139 @@ struct WalkerArgs {
   // bond-pair table (PT kernels): [2 n_bonds][HP], row 2 k + o = F[d] * G[u]
   // for bond k with d = (o ? j_k : i_k) raised and the other end lowered
   const float* pair_table;
+  // walkers given as the reference's float32 [B][N] of +-1 instead of packed
+  // words (the packed configurations are still written to packed_rw)
+  const float* configs_f32;
+  // cross-CTA reduction inside this kernel (cooperative launch: every CTA is
+  // resident, so a CTA may wait for the others): out[f] += sum_cta partials,
+  // stats += the energy sums, *counter += advance, stats copied to
+  // stats_snapshot (may be mapped host memory)
+  int fuse_reduce;
+  unsigned int* sync;       // [2] arrive / depart counters, zero between launches
+  float* out;
+  int64_t n_out;
+  double* stats;
+  uint64_t* counter;
+  uint64_t advance;
+  double* stats_snapshot;
 };
+
+// Configuration of walker bb as packed words: from the packed array or, when
+// the caller feeds float32 [B][N] of +-1 (graph_builders.py:92-125 layout),
+// bit-packed here by the walker's lane group (LPW sites per ballot; LPW divides
+// 64, so a ballot never straddles a word).  Warp-collective.
+template <int NW, int LPW>
+__device__ __forceinline__ void load_walker(const WalkerArgs& A, const Image& im, int64_t bb, int sub,
+                                            int grp, uint64_t (&s)[NW]) {
+  if (A.configs_f32 == nullptr) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s[w] = w < im.words ? A.packed[bb * im.words + w] : 0ull;
+    return;
+  }
+#pragma unroll
+  for (int w = 0; w < NW; ++w) s[w] = 0ull;
+  const float* row = A.configs_f32 + bb * im.N;
+  for (int i0 = 0; i0 < im.N; i0 += LPW) {
+    const int i = i0 + sub;
+    const bool up = i < im.N && row[i] > 0.f;
+    const uint32_t vote = __ballot_sync(CGSVMC_FULL_MASK, up);
+    const uint64_t gbits = (uint64_t)((vote >> (grp * LPW)) & ((1u << LPW) - 1u));
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+      if ((i0 >> 6) == w) s[w] |= gbits << (i0 & 63);
+  }
+}
+
+// Cross-CTA reduction at the end of the walker kernel (replaces a separate
+// reduction launch: ~7.5 us of kernel + launch gap per C2 step).  Requires a
+// cooperative launch.  Every CTA publishes its partial sums, waits until all
+// CTAs of the grid have done so, and reduces its share of the output columns
+// over the CTA slices in a fixed order (deterministic): 32 columns x RG row
+// groups per pass, all of a thread's loads in flight before its first add.
+// CTA 0 also folds the energy statistics, advances the device-side Philox
+// step counter of a captured step and publishes the statistics snapshot.
+template <int THREADS>
+__device__ __forceinline__ void grid_reduce(const WalkerArgs& A, float* red) {
+  constexpr int RG = THREADS / 32;     // row groups (warps)
+  constexpr int RU = 10;               // partial rows per thread and pass: RG * RU >= 148 CTAs in one pass
+  constexpr int CU = 3;                // column chunks of 32 per pass
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_cta = (int)gridDim.x;
+  __syncthreads();                     // this CTA's partial stores are issued
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&A.sync[0], 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(A.sync) : "memory");
+    } while (seen < (unsigned int)n_cta);
+  }
+  __syncthreads();
+  const int64_t stride = 2 * A.P;
+  const int64_t per = (A.n_out + n_cta - 1) / n_cta;
+  const int64_t c0 = (int64_t)blockIdx.x * per, c1 = min(A.n_out, c0 + per);
+  for (int64_t cbase = c0; cbase < c1; cbase += 32 * CU) {
+    float acc[CU];
+#pragma unroll
+    for (int u = 0; u < CU; ++u) acc[u] = 0.f;
+    for (int r0 = warp; r0 < n_cta; r0 += RG * RU) {
+      float v[CU][RU];
+#pragma unroll
+      for (int u = 0; u < CU; ++u) {
+        const int64_t col = cbase + 32 * u + lane;
+#pragma unroll
+        for (int k = 0; k < RU; ++k) {
+          const int r = r0 + RG * k;
+          v[u][k] = (col < c1 && r < n_cta) ? __ldcg(A.partials + (size_t)r * stride + col) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < CU; ++u)
+#pragma unroll
+        for (int k = 0; k < RU; ++k) acc[u] += v[u][k];
+    }
+#pragma unroll
+    for (int u = 0; u < CU; ++u) red[warp * (32 * CU) + 32 * u + lane] = acc[u];
+    __syncthreads();
+    if (threadIdx.x < 32 * CU) {
+      const int64_t col = cbase + threadIdx.x;
+      if (col < c1) {
+        float total = 0.f;
+#pragma unroll
+        for (int w = 0; w < RG; ++w) total += red[w * (32 * CU) + threadIdx.x];
+        A.out[col] += total;
+      }
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && warp == 0 && A.stats != nullptr) {
+    double e = 0.0, e2 = 0.0;
+    if (A.stat_partials != nullptr)
+      for (int c = lane; c < n_cta; c += 32) { e += __ldcg(A.stat_partials + 2 * c); e2 += __ldcg(A.stat_partials + 2 * c + 1); }
+    e = warp_sum(e);
+    e2 = warp_sum(e2);
+    if (lane == 0) {
+      const double s0 = A.stats[0] + e, s1 = A.stats[1] + e2, s2 = A.stats[2] + (double)A.B;
+      A.stats[0] = s0; A.stats[1] = s1; A.stats[2] = s2;
+      if (A.stats_snapshot != nullptr) {
+        volatile double* snap = A.stats_snapshot;
+        snap[0] = s0; snap[1] = s1; snap[2] = s2; snap[3] = A.stats[3];
+        __threadfence_system();
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 32 && A.counter != nullptr) *A.counter += A.advance;
+  // depart: the last CTA to leave re-arms the counters for the next launch
+  // (every CTA has left the wait loop before it departs)
+  if (threadIdx.x == 0) {
+    const unsigned int gone = atomicAdd(&A.sync[1], 1u);
+    if (gone == (unsigned int)n_cta - 1u) {
+      A.sync[0] = 0u;
+      A.sync[1] = 0u;
+      __threadfence();
+    }
+  }
+}
 
 // MC: after the estimators of a walker are done (and its gradient inputs are
 // staged in shared memory) its lane group continues with n_steps Metropolis
@@ -795,8 +927,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
     const int64_t b0 = (int64_t)blockIdx.x * A.wpc;
     const int n_valid = (int)min((int64_t)A.wpc, A.B - b0);
     const int64_t bb = b0 + min(slot, n_valid - 1);
-#pragma unroll
-    for (int w = 0; w < NW; ++w) s_first[w] = w < im.words ? A.packed[bb * im.words + w] : 0ull;
+    load_walker<NW, LPW>(A, im, bb, sub, grp, s_first);
   }
   if (PT) bulk_load(smem, img_g + img_skip, (uint32_t)(im.total - img_skip) * 4u, bar,
                     pair_s, A.pair_table, (uint32_t)(2 * A.n_bonds * HP) * 4u,
@@ -841,9 +972,12 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
     uint64_t s[NW];
     float p[KJ], m[KJ];
     if (warp_on) {
+      if (batch_no == 0) {
 #pragma unroll
-      for (int w = 0; w < NW; ++w)
-        s[w] = batch_no == 0 ? s_first[w] : (w < im.words ? A.packed[bb * im.words + w] : 0ull);
+        for (int w = 0; w < NW; ++w) s[w] = s_first[w];
+      } else {
+        load_walker<NW, LPW>(A, im, bb, sub, grp, s);
+      }
       const bool want_z = A.log_amp != nullptr;
       float z = init_state<NW, LPW, KJV, WS>(t, im, s, sub, p, m, want_z);
       if (want_z) {
@@ -1074,6 +1208,9 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
     }
   }
   RBM2_MARK(1, 8);
+  if (A.do_grad && A.fuse_reduce)
+    grid_reduce<THREADS>(A, T_s);      // the staging buffer is free: every tile pass ended with a CTA barrier
+  RBM2_MARK(1, 9);
 }
 
 // ---------------------------------------------------------------------------
@@ -1115,7 +1252,18 @@ int launch_walker_variant(const Plan& pl, const float* img, const WalkerArgs& A,
   do {                                                                            \
     auto kern = walker_kernel<NW, LPW, KJV, WSV, MCV, PTV>;                       \
     if (int rc = opt_in_smem(kern, pl.walker_smem)) return rc;                    \
-    kern<<<pl.grid, THREADS, pl.walker_smem, st>>>(pl.im, img, A);                \
+    if (A.fuse_reduce) {                                                          \
+      cudaLaunchConfig_t cfg = {};                                                \
+      cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3(THREADS);                  \
+      cfg.dynamicSmemBytes = pl.walker_smem; cfg.stream = st;                     \
+      cudaLaunchAttribute attr[1];                                                \
+      attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;   \
+      cfg.attrs = attr; cfg.numAttrs = 1;                                         \
+      cudaError_t le = cudaLaunchKernelEx(&cfg, kern, pl.im, img, A);             \
+      if (le != cudaSuccess) return cuda_fail(le, "rbm2 cooperative walker launch"); \
+    } else {                                                                      \
+      kern<<<pl.grid, THREADS, pl.walker_smem, st>>>(pl.im, img, A);              \
+    }                                                                             \
   } while (0)
   if (pl.pt) {                       // planned only for LPW == 8 with the image in shared memory
     if (LPW == 8) { if (mc) RBM2_LAUNCH_WALKER(true, true, (LPW == 8)); else RBM2_LAUNCH_WALKER(true, false, (LPW == 8)); }

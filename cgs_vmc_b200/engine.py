@@ -188,22 +188,22 @@ class HostFedBatchStep(_CapturedStep):
   """The batch step for a caller that keeps the reference's float32 [B, N]
   configuration tensor in HOST memory (graph_builders.py:92-125 viewed from
   outside the session): every submit() uploads one pinned host batch on a copy
-  stream and bit-packs it there (cgsvmc_pack_configs; double-buffered, so
-  upload and packing of batch k overlap the compute of batch k - 1), then
-  replays one captured graph per buffer slot -- the batch step on the slot's
-  walker buffer and the device->host copy of the step's
-  result, the energy statistics (sum E, sum E^2, n: the metric the reference
-  reads back, training.py:619-620), into pinned host memory.  result() blocks
-  until the oldest outstanding batch has landed.  The [2, P] gradient sums are
-  accumulated on the device like the reference's local variables and read with
-  fetch_sums() when the optimizer needs them (once per epoch)."""
+  stream (double-buffered: the upload of batch k overlaps the compute of batch
+  k - 1) and replays one captured graph per buffer slot holding
+  cgsvmc_batch_step_fed -- the walker kernel bit-packs the float32
+  configurations itself and stores the step's result, the energy statistics
+  (sum E, sum E^2, n: the metric the reference reads back, training.py:619-620),
+  straight into pinned host memory, so neither a packing launch nor a copy
+  node sits between two steps.  result() blocks until the oldest outstanding
+  batch has landed.  The [2, P] gradient sums are accumulated on the device
+  like the reference's local variables; fetch_sums() copies them out."""
 
   def __init__(self, state, ansatz, ham, sums, n_steps):
     dev = state.packed.device
     B, N, P = state.batch_size, state.n_sites, ansatz.num_params
     self.copy_stream = torch.cuda.Stream(device=dev)
     self.dev_cfg = [torch.empty(B, N, dtype=torch.float32, device=dev) for _ in range(2)]
-    self.host_stats = [torch.empty(4, dtype=torch.float64).pin_memory() for _ in range(2)]
+    self.host_stats = [torch.zeros(4, dtype=torch.float64).pin_memory() for _ in range(2)]
     self.host_sums = torch.empty(2, P, dtype=torch.float32).pin_memory()
     self.uploaded = [torch.cuda.Event() for _ in range(2)]
     self.landed = [torch.cuda.Event() for _ in range(2)]
@@ -214,44 +214,46 @@ class HostFedBatchStep(_CapturedStep):
     self._collected = 0
     for c in self.dev_cfg:
       c.copy_(state.configs())
-    # one walker buffer per slot: the upload AND the packing of batch k run on the
-    # copy stream while batch k - 1 computes; the graphs step the slot's buffer
-    # (after a submit `state.packed` is rebound to the buffer just stepped)
+    # one walker buffer per slot (after a submit `state.packed` is rebound to
+    # the buffer just stepped); variants 0 / 1 step a slot from its float32
+    # upload, 2 / 3 from a bit-packed upload
     self.slot_packed = [state.packed.clone() for _ in range(2)]
-    self.slot_state = [types.SimpleNamespace(
-        packed=self.slot_packed[i], seed=state.seed, walker_id0=state.walker_id0,
-        step_dev=state.step_dev, accept_count=state.accept_count, batch_size=B, n_sites=N)
-        for i in range(2)]
-    self._prepare(state, ansatz, ham, sums, n_steps, (0, 1))
+    self._prepare(state, ansatz, ham, sums, n_steps, (0, 1, 2, 3))
     for p in self.slot_packed:               # the warm-up stepped slot 0
       p.copy_(state.packed)
     main = torch.cuda.current_stream()
     for ev in self.landed:
       ev.record(main)
 
-  def _body(self, slot):
-    self.sums.batch_step(self.ham, self.slot_state[slot], self.n_steps, on_device_counter=True)
-    self.host_stats[slot].copy_(self.sums.stats, non_blocking=True)
+  def _body(self, variant):
+    slot, from_packed = variant & 1, variant >= 2
+    st = self.state
+    self.ansatz.batch_step_fed(self.ham, None if from_packed else self.dev_cfg[slot],
+                               self.slot_packed[slot], self.sums.sums, self.sums.stats, self.n_steps,
+                               st.seed, st.walker_id0, st.step_dev, accept_count=st.accept_count,
+                               e_loc_out=self.sums.weights[1], stats_out=self.host_stats[slot])
 
   def submit(self, host_configs):
     """host_configs: pinned host tensor, either the reference's float32 [B, N]
-    of +-1 (uploaded and bit-packed on the copy stream) or the library's own
-    walker layout, int64 [B, ceil(N / 64)] bit-packed (uploaded as is: 8 bytes
-    per walker up to 64 sites instead of 4 N).  Asynchronous."""
+    of +-1 or the library's own walker layout, int64 [B, ceil(N / 64)]
+    bit-packed (8 bytes per walker up to 64 sites instead of 4 N).
+    Asynchronous."""
     slot = self._submitted & 1
     main = torch.cuda.current_stream()
+    from_packed = host_configs.dtype == torch.int64
     with torch.cuda.stream(self.copy_stream):
       self.copy_stream.wait_event(self.landed[slot])
-      if host_configs.dtype == torch.int64:
+      if from_packed:
         if tuple(host_configs.shape) != tuple(self.slot_packed[slot].shape):
           raise ValueError('Size of existing variable does not match.')
         self.slot_packed[slot].copy_(host_configs, non_blocking=True)
       else:
+        if tuple(host_configs.shape) != tuple(self.dev_cfg[slot].shape):
+          raise ValueError('Size of existing variable does not match.')
         self.dev_cfg[slot].copy_(host_configs, non_blocking=True)
-        _native.pack_configs(self.dev_cfg[slot], out=self.slot_packed[slot])
       self.uploaded[slot].record(self.copy_stream)
     main.wait_event(self.uploaded[slot])
-    self._replay(slot)
+    self._replay(slot + (2 if from_packed else 0))
     self.state.packed = self.slot_packed[slot]
     # one event: the step's statistics have landed on the host AND the slot's
     # buffers may be refilled

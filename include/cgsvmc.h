@@ -262,6 +262,22 @@ int cgsvmc_batch_step(const cgsvmc_ansatz* ansatz, const cgsvmc_ham* ham,
                       uint64_t* step_counter, unsigned long long* accept_count,
                       void* stream);
 
+/* cgsvmc_batch_step for a caller that holds the walkers in the reference's own
+ * layout (the float32 [B, N] variable of graph_builders.py:92-125) and reads
+ * the energy statistics back every batch (training.py:619-620): configs_f32
+ * (device float32 [n_walkers, n_sites] of +-1; NULL = take packed_out as the
+ * input like cgsvmc_batch_step) is bit-packed by the walker kernel itself, the
+ * swept configurations are written to packed_out, and the updated statistics
+ * (double [4]) are also stored to stats_out when it is non-NULL -- stats_out may
+ * be mapped pinned host memory, so no copy node follows the kernel. */
+int cgsvmc_batch_step_fed(const cgsvmc_ansatz* ansatz, const cgsvmc_ham* ham,
+                          const float* configs_f32, uint64_t* packed_out,
+                          int64_t n_walkers, float* e_loc_out, float* log_amp_out,
+                          float* sums, double* stats, int32_t n_steps,
+                          uint64_t seed, uint64_t walker_id0, uint64_t step0,
+                          uint64_t* step_counter, unsigned long long* accept_count,
+                          double* stats_out, void* stream);
+
 /* ---- amplitude-agnostic sampler / local energy ------------------------- */
 /* For wavefunctions whose amplitude is not a single fused kernel: output
  * activations other than exp (layers.py:13-21, wavefunctions.py:350-353) give

@@ -634,6 +634,8 @@ def test_host_fed_batch_step(native):
       a.params.mul_(0.95)
     cfg = bits.random_sz0_configs(36, B, gen).astype(np.float32)
     host = torch.from_numpy(cfg).pin_memory()
+    if k == 2:      # the library's own bit-packed layout from the host
+      host = native.pack_configs(torch.from_numpy(cfg).cuda()).cpu().pin_memory()
     fed.submit(host)
     got_stats = fed.result()
     ref_sums.accumulate(ham, native.pack_configs(torch.from_numpy(cfg).cuda()))
@@ -712,3 +714,38 @@ def test_error_behaviour(native):
     a.local_energy(ham, native.random_configs(4, 8, seed=1))
   # empty batch is a no-op
   assert a.log_amp(torch.zeros(0, 1, dtype=torch.int64, device='cuda')).shape == (0,)
+
+
+@pytest.mark.parametrize('n_side,hidden,batch', [(6, 144, 8192), (6, 144, 300), (16, 256, 2000), (4, 24, 130)])
+def test_in_kernel_reduction_equals_reduction_kernel(native, n_side, hidden, batch, monkeypatch):
+  """The cross-CTA reduction at the end of the (cooperatively launched) walker
+  kernel against the separate reduction kernel (CGSVMC_RBM2_FUSED_REDUCE=0):
+  same trajectories, local energies, statistics and step counter; gradient sums
+  equal up to the summation order; and no state is left behind between
+  launches (the arrive / depart counters re-arm themselves)."""
+  from cgs_vmc_b200 import engine
+  n = n_side * n_side
+  spec = oansatz.AnsatzSpec('rbm', n, num_layers=0, layer_size=hidden, size_x=n_side, size_y=n_side)
+  a, _, _ = _setup(spec, seed=11, batch=1)
+  ij, jx, jz = lattices.heisenberg_couplings(lattices.square_nn_bonds(n_side))
+  ham = native.Hamiltonian(ij, jx, jz, n)
+  out = []
+  for fused in ('1', '0'):
+    monkeypatch.setenv('CGSVMC_RBM2_FUSED_REDUCE', fused)
+    st = engine.WalkerState(batch, n, seed=9, walker_id0=3)
+    sums = engine.EnergyGradientSums(a, batch)
+    energies = []
+    for rep in range(3):
+      energies.append(sums.batch_step(ham, st, n).clone())
+      sums.accumulate(ham, st.packed)              # the gradient-only launch reduces the same way
+    w = torch.ones(1, batch, device='cuda')
+    extra = a.weighted_grad_sum(st.packed, w)      # K = 1: odd number of output columns
+    torch.cuda.synchronize()
+    out.append((st.packed.clone(), torch.stack(energies), sums.sums.clone(), sums.stats.clone(),
+                st.accept_count.clone(), extra.clone()))
+  (p1, e1, s1, t1, c1, x1), (p0, e0, s0, t0, c0, x0) = out
+  assert torch.equal(p1, p0) and torch.equal(e1, e0) and torch.equal(c1, c0)
+  assert t1[2].item() == 6 * batch
+  np.testing.assert_allclose(t1.cpu().numpy(), t0.cpu().numpy(), rtol=1e-13)
+  _close_sums(s1, s0)
+  _close_sums(x1, x0)
