@@ -17,7 +17,13 @@
 //       no-swizzle UMMA operand planes [split][8-channel chunk][row][16 B], so
 //       that row r of ANY tap-shifted window is `start + 16 r`: the A operand of
 //       tap (dx, dy) is the same descriptor with the start address advanced by
-//       (dx * G * PW + dy) rows -- no im2col, no copies.  The weights of a tap
+//       (dx * G * PW + dy) rows -- no im2col, no copies.  When eight or more
+//       configurations fit, they are INTERLEAVED instead (row = xx * G * PW +
+//       yy * G + g, G a multiple of 8): every tap shift is then a multiple of 8
+//       rows = 128 bytes, so the 8-row x 16-byte core matrices the tensor core
+//       fetches stay aligned to shared-memory lines (a misaligned core matrix
+//       costs two wavefronts: measured 181 against 96 cycles per tap).  The
+//       weights of a tap
 //       are the B operand [b1 | b2 | b3] concatenated along N, so per tap and
 //       16 input channels three MMAs cover the six significant products while
 //       each activation plane is fetched from shared memory once:
@@ -78,6 +84,9 @@ struct TcDesc {
   int tmem_cols;
   int n_pairs;              // ceil(kx / 2): MMAs per tile of layer 1
   int ctas;                 // CTAs per SM the plan was sized for (1 or 2)
+  int il;                   // 1: configurations interleaved, row = xx * GW + yy * G + g (G % 8 == 0);
+                            // 0: side by side, row = xx * GW + g * PW + yy
+  int ystep;                // rows per step in y: G (interleaved) or 1
   const __half* w1img;      // [n_pairs][2][3C][8]   layer 1 B operand
   const __half* wimg;       // [n_tensor][taps][C/8][3C][8]
   const float* bias;        // [L - 1][C]  layers 1 .. L-1
@@ -236,7 +245,7 @@ struct Engine {
       reinterpret_cast<uint32_t*>(w1s)[e] = reinterpret_cast<const uint32_t*>(d.w1img)[e];
     for (int e = threadIdx.x; e < (d.L - 1) * d.C; e += kThreads) bias_s[e] = d.bias[e];
     for (int e = threadIdx.x; e < d.C + 1; e += kThreads) wsum_s[e] = d.wsum[e];
-    for (int e = threadIdx.x; e < taps; e += kThreads) tap_shift[e] = (e / d.ky) * d.GW + e % d.ky;
+    for (int e = threadIdx.x; e < taps; e += kThreads) tap_shift[e] = (e / d.ky) * d.GW + (e % d.ky) * d.ystep;
     // the planes are read beyond the written rows by junk output rows: keep
     // the bit patterns finite
     for (int e = threadIdx.x; e < 3 * CH * plane_halfs / 2; e += kThreads)
@@ -307,7 +316,7 @@ struct Engine {
       for (int sy = -1; sy <= 1; ++sy) {
         const int yy = y0 + sy * d.Y;
         if (yy < 0 || yy >= d.PW) continue;
-        const int R = xx * d.GW + g * d.PW + yy;
+        const int R = xx * d.GW + (d.il ? yy * d.G + g : g * d.PW + yy);
         __half* base = act + R * 8;
 #pragma unroll
         for (int sp = 0; sp < 3; ++sp)
@@ -331,7 +340,7 @@ struct Engine {
     const int rows = d.PH * d.GW;
     for (int R = threadIdx.x; R < rows; R += kThreads) {
       const int xx = R / d.GW, rem = R - xx * d.GW;
-      const int g = rem / d.PW, yy = rem - g * d.PW;
+      const int g = d.il ? rem % d.G : rem / d.PW, yy = d.il ? rem / d.G : rem - g * d.PW;
       uint32_t w[4] = {0u, 0u, 0u, 0u};
       if (g < n_cfg) {
         int sx = xx - d.pad_x; sx += sx < 0 ? d.X : 0; sx -= sx >= d.X ? d.X : 0;
@@ -408,7 +417,7 @@ struct Engine {
           for (int dx = 0; dx < d.kx; ++dx)
           for (int dy = 0; dy < d.ky; ++dy) {
             const int tap = dx * d.ky + dy;
-            const uint32_t a_row = a_tile + (uint32_t)(dx * d.GW + dy);
+            const uint32_t a_row = a_tile + (uint32_t)(dx * d.GW + dy * d.ystep);
             const uint32_t b_row = b_units + (uint32_t)tap * b_tap_units;
 #pragma unroll
             for (int ks = 0; ks < CC / 16; ++ks) {
@@ -473,7 +482,7 @@ struct Engine {
       }
       const int R = t * 128 + 32 * q + lane;
       const int x = R / d.GW, rem = R - x * d.GW;
-      const int g = rem / d.PW, y = rem - g * d.PW;
+      const int g = d.il ? rem % d.G : rem / d.PW, y = d.il ? rem / d.G : rem - g * d.PW;
       const bool valid = x < d.X && y < d.Y && g < n_cfg;
       if (relu) {
 #pragma unroll
@@ -511,7 +520,7 @@ struct Engine {
       float s = 0.f;
       for (int pos = lane; pos < d.N; pos += 32) {
         const int x = pos / d.Y, y = pos - x * d.Y;
-        s += rowsum[x * d.GW + g * d.PW + y];
+        s += rowsum[x * d.GW + (d.il ? y * d.G + g : g * d.PW + y)];
       }
       s = warp_sum(s);
       if (lane == 0) z[g] = s + wsum_s[d.C];
@@ -801,15 +810,41 @@ int tc_ctas_wanted() {
   const char* e = getenv("CGSVMC_CONV_TC_CTAS");
   return e != nullptr && atoi(e) == 1 ? 1 : 2;
 }
-
-bool make_desc_ctas(const cgsvmc_ansatz* a, size_t extra_bytes_per_cfg, size_t extra_fixed, int ctas, TcDesc* out);
-
-bool make_desc_host(const cgsvmc_ansatz* a, size_t extra_bytes_per_cfg, size_t extra_fixed, TcDesc* out) {
-  if (tc_ctas_wanted() == 2 && make_desc_ctas(a, extra_bytes_per_cfg, extra_fixed, 2, out)) return true;
-  return make_desc_ctas(a, extra_bytes_per_cfg, extra_fixed, 1, out);
+// CGSVMC_CONV_TC_IL=0 keeps the side-by-side layout (development comparison).
+bool tc_interleave_wanted() {
+  const char* e = getenv("CGSVMC_CONV_TC_IL");
+  return e == nullptr || atoi(e) != 0;
 }
 
-bool make_desc_ctas(const cgsvmc_ansatz* a, size_t extra_bytes_per_cfg, size_t extra_fixed, int ctas, TcDesc* out) {
+// rows / tiles / TMEM columns of a plan with G configurations
+void size_plan(TcDesc* t, int G) {
+  t->G = G; t->GW = G * t->PW;
+  t->ystep = t->il ? G : 1;
+  t->rows_out = t->X * t->GW;
+  t->n_tiles = (t->rows_out + 127) / 128;
+  // the junk output rows of the last tile read up to the largest tap shift further
+  t->rows_total = (t->n_tiles * 128 + (t->kx - 1) * t->GW + (t->ky - 1) * t->ystep + 1 + 7) / 8 * 8;
+  t->rows_total = std::max(t->rows_total, (t->PH * t->GW + 8 + 7) / 8 * 8);
+  int cols = 32;
+  while (cols < t->n_tiles * 3 * t->C) cols *= 2;
+  t->tmem_cols = cols;
+}
+
+bool make_desc_plan(const cgsvmc_ansatz* a, size_t extra_bytes_per_cfg, size_t extra_fixed, int ctas, int il,
+                    TcDesc* out);
+
+// Plans in order of measured throughput: interleaved configurations (aligned
+// tap shifts) with two CTAs per SM, with one, then the side-by-side layout.
+bool make_desc_host(const cgsvmc_ansatz* a, size_t extra_bytes_per_cfg, size_t extra_fixed, TcDesc* out) {
+  const int max_ctas = tc_ctas_wanted();
+  for (int il = tc_interleave_wanted() ? 1 : 0; il >= 0; --il)
+    for (int ctas = max_ctas; ctas >= 1; --ctas)
+      if (make_desc_plan(a, extra_bytes_per_cfg, extra_fixed, ctas, il, out)) return true;
+  return false;
+}
+
+bool make_desc_plan(const cgsvmc_ansatz* a, size_t extra_bytes_per_cfg, size_t extra_fixed, int ctas, int il,
+                    TcDesc* out) {
   const cgsvmc_ansatz_desc& s = a->desc;
   if (s.kind != CGSVMC_ANSATZ_CONV_1D && s.kind != CGSVMC_ANSATZ_CONV_2D) return false;
   if (s.num_layers < 3 || (s.num_filters != 16 && s.num_filters != 32)) return false;
@@ -835,21 +870,19 @@ bool make_desc_ctas(const cgsvmc_ansatz* a, size_t extra_bytes_per_cfg, size_t e
   const size_t limit = ctas == 1 ? (size_t)a->max_smem_optin : (size_t)(233472 / 2 - 1024 - 256);
   const int tmem_limit = 512 / ctas;
   d.ctas = ctas;
+  d.il = il;
   bool found = false;
-  // double-buffered weights (the next layer's load overlaps the MMAs) when at
-  // least two configurations still fit, else one buffer and a larger batch
-  for (int n_wbuf = ctas == 1 ? 2 : 1; n_wbuf >= 1 && !found; --n_wbuf) {
-    for (int G = 16; G >= (n_wbuf == 2 || ctas == 2 ? 2 : 1); --G) {
+  // side by side, one CTA per SM: double-buffered weights (the next layer's load
+  // overlaps the MMAs) when at least two configurations still fit; otherwise one
+  // buffer, refilled under the epilogue
+  for (int n_wbuf = (ctas == 1 && !il) ? 2 : 1; n_wbuf >= 1 && !found; --n_wbuf) {
+    const int g_min = il ? 8 : ((n_wbuf == 2 || ctas == 2) ? 2 : 1);
+    const int g_step = il ? 8 : 1;
+    for (int G = 16; G >= g_min; G -= g_step) {
       TcDesc t = d;
-      t.n_wbuf = n_wbuf; t.G = G; t.GW = G * t.PW;
-      t.rows_out = t.X * t.GW;
-      t.n_tiles = (t.rows_out + 127) / 128;
-      t.rows_total = (t.n_tiles * 128 + (t.kx - 1) * t.GW + t.ky + 7) / 8 * 8;
-      t.rows_total = std::max(t.rows_total, (t.PH * t.GW + 8 + 7) / 8 * 8);
+      t.n_wbuf = n_wbuf;
+      size_plan(&t, G);
       if (t.rows_total > 16383 || t.n_tiles * 3 * t.C > tmem_limit) continue;
-      int cols = 32;
-      while (cols < t.n_tiles * 3 * t.C) cols *= 2;
-      t.tmem_cols = cols;
       const size_t need = smem_plan(t).total + (size_t)G * t.NW * 16 + (size_t)G * 12 + 16 +
                           extra_bytes_per_cfg * G + extra_fixed + 1024;
       if (need <= limit) { d = t; found = true; break; }
@@ -956,16 +989,9 @@ int conv_tc_mc_steps(cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int n_steps,
   TcDesc d;
   if (!make_desc_host(a, 0, 0, &d)) { set_error("conv_tc: unsupported network"); return CGSVMC_ERR_UNSUPPORTED; }
   // do not starve the grid: fewer walkers per CTA when there are few walkers
-  while (d.G > 1 && (B + d.G - 1) / d.G < (int64_t)a->num_sms * d.ctas) {
-    TcDesc t = d;
-    t.G = d.G - 1; t.GW = t.G * t.PW; t.rows_out = t.X * t.GW;
-    t.n_tiles = (t.rows_out + 127) / 128;
-    t.rows_total = std::max((t.n_tiles * 128 + (t.kx - 1) * t.GW + t.ky + 7) / 8 * 8, (t.PH * t.GW + 8 + 7) / 8 * 8);
-    int cols = 32;
-    while (cols < t.n_tiles * 3 * t.C) cols *= 2;
-    t.tmem_cols = cols;
-    d = t;
-  }
+  // (interleaved plans keep G a multiple of 8)
+  const int g_step = d.il ? 8 : 1;
+  while (d.G > g_step && (B + d.G - 1) / d.G < (int64_t)a->num_sms * d.ctas) size_plan(&d, d.G - g_step);
   if (int rc = build_tc_image(a, &d, st)) return rc;
   const size_t smem = smem_plan(d).total + extras_bytes(d);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((B + d.G - 1) / d.G, (int64_t)a->num_sms * d.ctas));

@@ -342,7 +342,9 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
   uint64_t* const step_counter = mc ? sweep->advance_counter : nullptr;
   double* const snapshot = mc ? sweep->stats_snapshot : nullptr;
   if (fuse) {
-    A.fuse_reduce = 1;
+    // 2 = plain launch (development comparison: the spin wait then relies on
+    // the grid being co-resident because nothing else runs on the device)
+    A.fuse_reduce = (fuse_env != nullptr && atoi(fuse_env) == 2) ? 2 : 1;
     A.sync = a->grid_sync;
     A.out = out; A.n_out = (int64_t)K * P; A.stats = stats;
     A.counter = step_counter; A.advance = mc ? (uint64_t)sweep->n_steps : 0ull;

@@ -1252,7 +1252,7 @@ int launch_walker_variant(const Plan& pl, const float* img, const WalkerArgs& A,
   do {                                                                            \
     auto kern = walker_kernel<NW, LPW, KJV, WSV, MCV, PTV>;                       \
     if (int rc = opt_in_smem(kern, pl.walker_smem)) return rc;                    \
-    if (A.fuse_reduce) {                                                          \
+    if (A.fuse_reduce == 1) {                                                     \
       cudaLaunchConfig_t cfg = {};                                                \
       cfg.gridDim = dim3(pl.grid); cfg.blockDim = dim3(THREADS);                  \
       cfg.dynamicSmemBytes = pl.walker_smem; cfg.stream = st;                     \
