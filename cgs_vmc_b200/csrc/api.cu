@@ -278,6 +278,8 @@ int cgsvmc_log_amp(const cgsvmc_ansatz* a, const uint64_t* packed, int64_t B, fl
   if (rbm_fast_supported(a)) return rbm_log_amp(a, packed, B, log_amp, (cudaStream_t)stream);
   if (conv_tc_supported(a, nullptr))
     return conv_tc_log_amp(const_cast<cgsvmc_ansatz*>(a), packed, B, log_amp, (cudaStream_t)stream);
+  if (fc_tc_supported(a, nullptr))
+    return fc_tc_log_amp(const_cast<cgsvmc_ansatz*>(a), packed, B, log_amp, (cudaStream_t)stream);
   return net_log_amp(a, packed, B, log_amp, (cudaStream_t)stream);
 }
 
@@ -298,6 +300,9 @@ int cgsvmc_mc_steps(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int32_t
   if (conv_tc_supported(a, nullptr))
     return conv_tc_mc_steps(const_cast<cgsvmc_ansatz*>(a), packed, B, n_steps, seed, walker_id0, step0,
                             accept_count, log_amp_out, (cudaStream_t)stream);
+  if (fc_tc_supported(a, nullptr))
+    return fc_tc_mc_steps(const_cast<cgsvmc_ansatz*>(a), packed, B, n_steps, seed, walker_id0, step0,
+                          accept_count, log_amp_out, (cudaStream_t)stream);
   return net_mc_steps(a, packed, B, n_steps, seed, walker_id0, step0, accept_count, log_amp_out,
                       (cudaStream_t)stream);
 }
@@ -364,6 +369,9 @@ int cgsvmc_local_energy(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint6
   if (conv_tc_supported(a, h))
     return conv_tc_local_energy(const_cast<cgsvmc_ansatz*>(a), h, packed, B, e_loc, log_amp_out, diag_out,
                                 offdiag_ratio_out, (cudaStream_t)stream);
+  if (fc_tc_supported(a, h))
+    return fc_tc_local_energy(const_cast<cgsvmc_ansatz*>(a), h, packed, B, e_loc, log_amp_out, diag_out,
+                              offdiag_ratio_out, (cudaStream_t)stream);
   return net_local_energy(a, h, packed, B, e_loc, log_amp_out, diag_out, offdiag_ratio_out,
                           (cudaStream_t)stream);
 }

@@ -49,9 +49,12 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "tc_common.cuh"
 
 namespace cgsvmc {
 namespace {
+
+using namespace tc;
 
 // Development aid (-DCGSVMC_RBM2_TIMING build, profiles/run_conv_tc_phases.py):
 // thread 0 of every CTA accumulates the cycles its tensor layers spend in the
@@ -67,8 +70,23 @@ __device__ unsigned long long g_tc_phase[4];   // MMA cycles, epilogue cycles, l
 #define TC_PHASE_COUNT(IDX) do {} while (0)
 #endif
 
+// Activation split planes held in shared memory.  Every MMA reads a 128 x 16
+// fp16 A tile (4 KB) from shared memory, which takes ~64 cycles whatever N is
+// (measured: 181 cycles per tap for three MMAs with N = 48 / 32 / 16, aligned
+// or not), so with C = 16 filters the MMA phase is bound by the NUMBER of
+// activation planes, not by the tensor pipe.  Two planes: v = a1 + a2 / S with
+// 22 mantissa bits (|error| <= 2^-23 |v|, below the rounding of a float32
+// accumulation over the 25 C products of an output) against the full three-way
+// split of the weights: products a1 b1, a1 b2, a1 b3, a2 b1, a2 b2.
+// Three planes restore the exact float32 activations (CGSVMC_TC_ACT_SPLITS=3 at
+// compile time) at 1.5x the MMA time.
+#ifndef CGSVMC_TC_ACT_SPLITS
+#define CGSVMC_TC_ACT_SPLITS 2
+#endif
+constexpr int kActSplits = CGSVMC_TC_ACT_SPLITS;
+static_assert(kActSplits == 2 || kActSplits == 3, "two or three activation planes");
+
 constexpr int kThreads = 256;
-constexpr float kSplitScale = 2048.f;   // S = 2^11: keeps the lower split terms out of the fp16 subnormals
 constexpr int kWarps = 8;
 constexpr int kMaxTaps = 64;
 
@@ -100,7 +118,7 @@ struct SmemPlan {
 __host__ __device__ inline SmemPlan smem_plan(const TcDesc& d) {
   SmemPlan p;
   size_t off = 0;
-  p.act = off; off += (size_t)3 * (d.C / 8) * d.rows_total * 16;
+  p.act = off; off += (size_t)kActSplits * (d.C / 8) * d.rows_total * 16;
   p.wbuf = off; off += (size_t)d.n_wbuf * d.wbuf_bytes;
   p.w1 = off; off += (size_t)d.n_pairs * 2 * 3 * d.C * 16;
   p.consts = off; off += ((size_t)(d.L - 1) * d.C + d.C + 4 + (size_t)d.kx * d.ky) * 4;
@@ -109,97 +127,6 @@ __host__ __device__ inline SmemPlan smem_plan(const TcDesc& d) {
   p.bars = off; off += 64;
   p.total = off;
   return p;
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-__device__ __forceinline__ float tc_activate(int act, float x) {
-  switch (act) {
-    case CGSVMC_ACT_RELU: return fmaxf(x, 0.f);
-    case CGSVMC_ACT_TANH: return tanh_accurate(x);
-    case CGSVMC_ACT_SIGMOID: return 1.f / (1.f + expf(-x));
-    case CGSVMC_ACT_IDENTITY: return x;
-    case CGSVMC_ACT_COS: return cosf(x);
-    case CGSVMC_ACT_EXP: return expf(x);
-    default: return tanf(x);
-  }
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t a = smem_u32(bar);
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-        : "=r"(ok)
-        : "r"(a), "r"(parity)
-        : "memory");
-  }
-}
-
-// TMA bulk copy global -> shared, completion on `bar` (one arrival + bytes).
-__device__ __forceinline__ void bulk_load_async(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  const uint32_t bar_a = smem_u32(bar);
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
-  uint32_t done = 0;
-  while (done < bytes) {
-    const uint32_t chunk = min(bytes - done, 32768u);
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(reinterpret_cast<char*>(dst) + done)),
-        "l"(reinterpret_cast<const char*>(src) + done), "r"(chunk), "r"(bar_a)
-        : "memory");
-    done += chunk;
-  }
-}
-
-// Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor), K-major, no
-// swizzle: bits [0,14) start address, [16,30) leading byte offset (between the
-// two 16-byte K chunks), [32,46) stride byte offset (between 8-row groups), all
-// in 16-byte units; bits [46,48) version = 1.  Built inline in tensor_layer().
-__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                        uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-      "}\n"
-      :
-      : "r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
-      : "memory");
-}
-
-// One lane of the (converged) warp; lets the compiler move the MMA operands to
-// uniform registers without a per-lane waterfall loop.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 __device__ __forceinline__ int word_bit(const uint64_t* words, int site) {
@@ -248,7 +175,7 @@ struct Engine {
     for (int e = threadIdx.x; e < taps; e += kThreads) tap_shift[e] = (e / d.ky) * d.GW + (e % d.ky) * d.ystep;
     // the planes are read beyond the written rows by junk output rows: keep
     // the bit patterns finite
-    for (int e = threadIdx.x; e < 3 * CH * plane_halfs / 2; e += kThreads)
+    for (int e = threadIdx.x; e < kActSplits * CH * plane_halfs / 2; e += kThreads)
       reinterpret_cast<uint32_t*>(act)[e] = 0u;
     if (threadIdx.x == 0) {
       mbar_init(mma_bar, 1);
@@ -305,7 +232,7 @@ struct Engine {
         h[2][e] = __float2half_rn(r2);
       }
 #pragma unroll
-      for (int sp = 0; sp < 3; ++sp) q[sp][c / 2] = __halves2half2(h[sp][0], h[sp][1]);
+      for (int sp = 0; sp < kActSplits; ++sp) q[sp][c / 2] = __halves2half2(h[sp][0], h[sp][1]);
     }
     const int x0 = x + d.pad_x, y0 = y + d.pad_y;
 #pragma unroll
@@ -319,7 +246,7 @@ struct Engine {
         const int R = xx * d.GW + (d.il ? yy * d.G + g : g * d.PW + yy);
         __half* base = act + R * 8;
 #pragma unroll
-        for (int sp = 0; sp < 3; ++sp)
+        for (int sp = 0; sp < kActSplits; ++sp)
 #pragma unroll
           for (int ch = 0; ch < CC / 8; ++ch) {
             uint4 pk;
@@ -430,7 +357,7 @@ struct Engine {
               if (elect_one()) {
                 mma_f16(d_tmem, a1, b, idesc3, (tap | ks) ? 1u : 0u);   // [P0 P1 P2] += A1 [b1 b2 b3]
                 mma_f16(d_tmem + CC, a2, b, idesc2, 1u);                 // [P1 P2]    += A2 [b1 b2]
-                mma_f16(d_tmem + 2 * CC, a3, b, idesc1, 1u);             // [P2]       += A3 [b1]
+                if (kActSplits == 3) mma_f16(d_tmem + 2 * CC, a3, b, idesc1, 1u);   // [P2] += A3 [b1]
               }
             }
           }

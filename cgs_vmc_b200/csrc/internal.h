@@ -144,6 +144,16 @@ int conv_tc_local_energy(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* 
                          float* e_loc, float* log_amp_out, float* diag_out, float* off_out,
                          cudaStream_t s);
 
+// ---- fully_connected forward on the tensor cores (fc_tc.cu): tcgen05 + TMEM ----
+bool fc_tc_supported(const cgsvmc_ansatz* a, const cgsvmc_ham* h);
+int fc_tc_log_amp(cgsvmc_ansatz* a, const uint64_t* packed, int64_t B, float* out, cudaStream_t s);
+int fc_tc_mc_steps(cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int n_steps, uint64_t seed,
+                   uint64_t walker0, uint64_t step0, unsigned long long* accept_count,
+                   float* log_amp_out, cudaStream_t s);
+int fc_tc_local_energy(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, int64_t B,
+                       float* e_loc, float* log_amp_out, float* diag_out, float* off_out,
+                       cudaStream_t s);
+
 // ---- generic tile networks: fc, rbm with hidden layers, conv (net.cu) ----
 int net_log_amp(const cgsvmc_ansatz* a, const uint64_t* packed, int64_t B, float* out,
                 cudaStream_t s);

@@ -1,0 +1,182 @@
+"""-m gpu parity tests of the tensor-core (tcgen05) fully-connected forward
+path (fc_tc.cu) against the float64 oracle, the golden vectors recorded from
+the reference and the SIMT float32 path of net.cu (CGSVMC_FC_TC=0).
+
+Stated tolerance: three-way fp16 split of activations and weights (33 mantissa
+bits, exact float32 products) with the tensor core's fp32 accumulation:
+|dz| <= 2e-5 * (sum of |terms| of the forward pass), the bound the SIMT path
+is held to as well."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import ansatz as oansatz
+from oracle import bits, hamiltonian, lattices, philox
+
+pytestmark = pytest.mark.gpu
+F64 = torch.float64
+
+FC_SHAPES = [
+    oansatz.AnsatzSpec('fully_connected', 20, num_layers=3, layer_size=80),          # C1
+    oansatz.AnsatzSpec('fully_connected', 36, num_layers=1, layer_size=64),
+    oansatz.AnsatzSpec('fully_connected', 70, num_layers=2, layer_size=32, nonlinearity='tanh'),
+    oansatz.AnsatzSpec('fully_connected', 100, num_layers=4, layer_size=48),
+    oansatz.AnsatzSpec('fully_connected', 12, num_layers=2, layer_size=16, nonlinearity='sigmoid'),
+    oansatz.AnsatzSpec('fully_connected', 256, num_layers=2, layer_size=80),
+]
+
+
+def _id(s):
+  return 'N%d_L%d_H%d_%s' % (s.n_sites, s.num_layers, s.layer_size, s.nonlinearity)
+
+
+@pytest.fixture(scope='module')
+def native():
+  from cgs_vmc_b200 import _native
+  _native.load()
+  return _native
+
+
+@pytest.fixture(autouse=True)
+def _tc_on():
+  os.environ['CGSVMC_FC_TC'] = '1'
+  yield
+  os.environ.pop('CGSVMC_FC_TC', None)
+
+
+def _setup(spec, seed, batch, bias=0.1):
+  from gpu_util import make_native
+  params = oansatz.init_params(spec, seed=seed, bias_scale=bias, dtype=F64)
+  cfg = bits.random_sz0_configs(spec.n_sites, batch, np.random.default_rng(seed))
+  return make_native(spec, oansatz.flatten(params).numpy()), params, cfg
+
+
+@pytest.mark.parametrize('spec', FC_SHAPES, ids=_id)
+@pytest.mark.parametrize('batch', [1, 127, 129, 700, 40000])
+def test_fc_tc_log_amp_vs_oracle_and_simt(native, spec, batch):
+  """Ragged batches around the 128-row tile and the two-tile pipeline
+  (40000 > 128 x 148: two tiles in flight per CTA)."""
+  from gpu_util import packed_cuda, amp_scale
+  a, params, cfg = _setup(spec, seed=spec.n_sites + batch, batch=batch)
+  packed = packed_cuda(cfg)
+  z_tc = a.log_amp(packed).cpu().numpy()
+  os.environ['CGSVMC_FC_TC'] = '0'
+  z_simt = a.log_amp(packed).cpu().numpy()
+  os.environ['CGSVMC_FC_TC'] = '1'
+  sub = slice(0, min(batch, 2000))
+  cfg64 = torch.from_numpy(cfg[sub]).to(F64)
+  zo = oansatz.log_amp(spec, params, cfg64).numpy()
+  scale = amp_scale(spec, params, cfg64) if spec.nonlinearity == 'relu' else np.abs(zo) + spec.n_sites
+  assert np.all(np.abs(z_tc[sub] - zo) <= 2e-5 * scale), (np.abs(z_tc[sub] - zo).max(), scale.min())
+  assert np.all(np.isfinite(z_tc))
+  assert np.abs(z_tc - z_simt).max() <= 2e-5 * (np.abs(z_simt).max() + spec.n_sites)
+
+
+def test_fc_tc_golden_amplitudes(native):
+  """psi of the reference's own FullyConnectedNetwork on the C1 shape."""
+  from gpu_util import make_native, packed_cuda
+  spec, g = load_golden('fc_chain20')
+  a = make_native(spec, g['params_flat'])
+  z = a.log_amp(packed_cuda(g['configs'])).double().cpu().numpy()
+  np.testing.assert_allclose(np.exp(z - float(g['shift'])), g['psi'], rtol=3e-5)
+
+
+@pytest.mark.parametrize('spec', FC_SHAPES[:4], ids=_id)
+@pytest.mark.parametrize('batch', [19, 1024])
+def test_fc_tc_local_energy_vs_oracle(native, spec, batch):
+  from gpu_util import packed_cuda
+  a, params, cfg = _setup(spec, seed=7, batch=batch)
+  n = spec.n_sites
+  if n == 36:
+    ij, jx, jz = lattices.j1j2_couplings(6, 0.5)
+  elif n == 100:
+    ij, jx, jz = lattices.j1j2_couplings(10, 0.5)
+  else:
+    ij, jx, jz = lattices.heisenberg_couplings(lattices.chain_bonds(n), -1.0, 1.0)
+  ham = native.Hamiltonian(ij, jx, jz, n)
+  e, z, diag, off = a.local_energy(ham, packed_cuda(cfg), want_parts=True)
+  os.environ['CGSVMC_FC_TC'] = '0'
+  e_simt, z_simt = a.local_energy(ham, packed_cuda(cfg))
+  os.environ['CGSVMC_FC_TC'] = '1'
+  sub = slice(0, min(batch, 64))
+  cfg64 = torch.from_numpy(cfg[sub]).to(F64)
+  fn = lambda c: oansatz.log_amp(spec, params, c)
+  eo = hamiltonian.local_energy(cfg64, ij, jx, jz, fn).numpy()
+  eabs = hamiltonian.local_energy(cfg64, ij, np.abs(jx), np.abs(jz), fn).numpy()
+  got = e.cpu().numpy()
+  assert np.all(np.abs(got[sub] - eo) <= 3e-4 * (np.abs(eabs) + 1.0)), np.abs(got[sub] - eo).max()
+  assert np.abs(got - e_simt.cpu().numpy()).max() <= 3e-4 * (np.abs(e_simt.cpu().numpy()).max() + 1.0)
+  np.testing.assert_allclose(z.cpu().numpy(), z_simt.cpu().numpy(), atol=2e-5 * (np.abs(z_simt.cpu().numpy()).max() + n))
+  d_o, _ = hamiltonian.build(cfg64, ij, jx, jz, lambda c: torch.ones(c.shape[0], dtype=F64))
+  np.testing.assert_allclose(diag.cpu().numpy()[sub], d_o.numpy(), atol=1e-5)
+  np.testing.assert_allclose((diag + off).cpu().numpy(), got, atol=1e-5, rtol=1e-6)
+
+
+def test_fc_tc_golden_local_energy(native):
+  from gpu_util import make_native, packed_cuda
+  spec, g = load_golden('fc_chain20')
+  a = make_native(spec, g['params_flat'])
+  ham = native.Hamiltonian(g['bonds_ij'], g['bonds_jx'], g['bonds_jz'], spec.n_sites)
+  e, _ = a.local_energy(ham, packed_cuda(g['configs']))
+  np.testing.assert_allclose(e.cpu().numpy(), g['local_energy'], rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize('spec', [FC_SHAPES[0], FC_SHAPES[2]], ids=_id)
+def test_fc_tc_sampler_matches_oracle_philox(native, spec):
+  """Every proposal identical to the Philox restatement, accept decisions
+  identical away from near-ties, Sz conserved, multi-step == single steps,
+  independent of how the walkers are grouped into CTAs."""
+  from gpu_util import packed_cuda, unpack_np
+  a, params, cfg = _setup(spec, seed=9, batch=300)
+  seed, w0 = 0xC65, 500
+  fn = lambda c: oansatz.log_amp(spec, params, c)
+  cur = cfg.copy()
+  walker_ids = np.arange(cfg.shape[0], dtype=np.uint64) + np.uint64(w0)
+  for step in range(5):
+    packed = packed_cuda(cur)
+    count = torch.zeros(1, dtype=torch.int64, device='cuda')
+    a.mc_steps(packed, 1, seed, walker_id0=w0, step0=step, accept_count=count)
+    got = unpack_np(packed, spec.n_sites)
+    down, up, u = philox.fast_proposal(cur, seed, walker_ids, step)
+    prop = cur.copy()
+    rows = np.arange(cur.shape[0])
+    prop[rows, down] += 2
+    prop[rows, up] -= 2
+    t = torch.from_numpy
+    dl = (fn(t(prop).to(F64)) - fn(t(cur).to(F64))).numpy()
+    acc = np.exp(2 * dl) > u
+    exp = np.where(acc[:, None], prop, cur)
+    near = np.abs(np.exp(2 * dl) - u) < 2e-3 * np.exp(2 * dl)
+    row_same = np.all(got == exp, axis=1)
+    assert np.all(row_same | near)
+    other = np.where(acc[:, None], cur, prop)
+    assert np.all(row_same | np.all(got == other, axis=1))
+    assert int(count.item()) == int(np.all(got == prop, axis=1).sum() - np.all(prop == cur, axis=1).sum())
+    cur = got
+  assert np.all(cur.sum(axis=1) == 0)
+  p_all = packed_cuda(cfg)
+  z_all = torch.empty(cfg.shape[0], device='cuda')
+  a.mc_steps(p_all, 6, 11, walker_id0=3, step0=0, log_amp_out=z_all)
+  p_steps = packed_cuda(cfg)
+  for s in range(0, 6, 2):
+    a.mc_steps(p_steps, 2, 11, walker_id0=3, step0=s)
+  assert torch.equal(p_all, p_steps)
+  torch.testing.assert_close(z_all, a.log_amp(p_all), rtol=0, atol=1e-4)
+
+
+def test_fc_tc_sampler_large_batch_two_tiles(native):
+  """More than 128 x 148 walkers: two tiles in flight per CTA; trajectories
+  equal those of the same walkers sampled in small groups."""
+  from gpu_util import packed_cuda
+  spec = FC_SHAPES[0]
+  a, params, cfg = _setup(spec, seed=3, batch=20000)
+  p_big = packed_cuda(cfg)
+  a.mc_steps(p_big, 4, 77, walker_id0=0, step0=0)
+  p_small = packed_cuda(cfg[:500])
+  a.mc_steps(p_small, 4, 77, walker_id0=0, step0=0)
+  same = (p_big[:500] == p_small).all(dim=1)
+  assert same.float().mean().item() > 0.99      # near-ties may differ between tile placements? no: same arithmetic
+  assert torch.equal(p_big[:500], p_small)
