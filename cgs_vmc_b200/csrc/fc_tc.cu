@@ -38,6 +38,18 @@ namespace {
 
 using namespace tc;
 
+// Development aid (-DCGSVMC_RBM2_TIMING build, profiles/run_fc_tc_phases.py):
+// thread 0 of every CTA accumulates the cycles it waits for the MMAs of a layer,
+// spends in the epilogue, and in whole forward passes.
+#ifdef CGSVMC_RBM2_TIMING
+__device__ unsigned long long g_fc_phase[6];   // wait cycles, epilogue cycles, epilogues, forward cycles, forwards, issue cycles
+#define FC_CLOCK(NAME) const long long NAME = clock64()
+#define FC_ADD(IDX, VAL) do { if (threadIdx.x == 0) atomicAdd(&g_fc_phase[IDX], (unsigned long long)(VAL)); } while (0)
+#else
+#define FC_CLOCK(NAME) do {} while (0)
+#define FC_ADD(IDX, VAL) do {} while (0)
+#endif
+
 constexpr int kThreads = 256;
 constexpr int kWarps = 8;
 constexpr int kTile = 128;          // configurations per tile (UMMA M)
@@ -79,6 +91,13 @@ __host__ __device__ inline FcSmem fc_plan(const FcDesc& d) {
 __device__ __forceinline__ int word_bit(const uint64_t* words, int site) {
   return (int)((words[site >> 6] >> (site & 63)) & 1ull);
 }
+
+// The nonlinearities other than relu as ONE out-of-line function: inlined into
+// the unrolled epilogue they multiplied its code size by the number of
+// activation kinds times the elements per thread (336 KB of SASS for H = 80),
+// and the relu path crawled through instruction-cache misses (measured: 10.6 k
+// cycles per epilogue).
+__device__ __noinline__ float activate_slow(int act, float x) { return tc_activate(act, x); }
 
 // ---------------------------------------------------------------------------
 // The forward engine.  All 256 threads of the CTA call every method.
@@ -171,6 +190,7 @@ struct FcEngine {
   // elected lane of warp 0; completion arrives on mma_bar[buf].
   __device__ void issue(int buf, int layer) {
     if ((threadIdx.x >> 5) != 0) return;
+    FC_CLOCK(t_i0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // instruction descriptor: D = F32, A = B = F16, K-major, M = 128; N per MMA
     const uint32_t idesc0 = (1u << 4) | (8u << 24);
@@ -212,6 +232,8 @@ struct FcEngine {
                        smem_u32(mma_bar + buf))
                    : "memory");
     __syncwarp();
+    FC_CLOCK(t_i1);
+    FC_ADD(5, t_i1 - t_i0);
   }
 
   // Epilogue of layer `layer` on tile `buf`: TMEM -> bias -> nonlinearity ->
@@ -219,18 +241,29 @@ struct FcEngine {
   // w_out.  Ends with a CTA barrier: afterwards the next layer may be issued /
   // z_of(buf) may be read.
   __device__ void epilogue(int buf, int layer) {
+    if (d.act == CGSVMC_ACT_RELU) epilogue_impl<true>(buf, layer);
+    else epilogue_impl<false>(buf, layer);
+  }
+
+  template <bool RELU>
+  __device__ __forceinline__ void epilogue_impl(int buf, int layer) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    FC_CLOCK(t_in);
     mbar_wait(mma_bar + buf, phase[buf]);
+    FC_CLOCK(t_go);
+    FC_ADD(0, t_go - t_in);
     phase[buf] ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3, half = warp >> 2;
     const int r = 32 * q + lane;
     const bool last = layer == d.L - 1;
     const float* bj = bias_s + layer * H + half * HH;
+    const float* wo = wout_s + half * HH;
     const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 3 * H + half * HH);
     char* abuf = act_buf(buf);
+    const int act = d.act;
     float zacc = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int c8 = 0; c8 < HH / 8; ++c8) {
       uint32_t p0[8], p1[8], p2[8];
       tmem_ld8_nowait(trow + (uint32_t)(8 * c8), p0);
@@ -242,11 +275,11 @@ struct FcEngine {
       for (int k = 0; k < 8; ++k) {
         const float pre = fmaf(fmaf(__uint_as_float(p2[k]), 1.f / kSplitScale, __uint_as_float(p1[k])),
                                1.f / kSplitScale, __uint_as_float(p0[k])) + bj[8 * c8 + k];
-        v[k] = d.act == CGSVMC_ACT_RELU ? fmaxf(pre, 0.f) : tc_activate(d.act, pre);
+        v[k] = RELU ? fmaxf(pre, 0.f) : activate_slow(act, pre);
       }
       if (last) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) zacc = fmaf(v[k], wout_s[half * HH + 8 * c8 + k], zacc);
+        for (int k = 0; k < 8; ++k) zacc = fmaf(v[k], wo[8 * c8 + k], zacc);
       } else {
         __half hs[3][8];
 #pragma unroll
@@ -267,6 +300,9 @@ struct FcEngine {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    FC_CLOCK(t_out);
+    FC_ADD(1, t_out - t_go);
+    FC_ADD(2, 1);
     if (last) {
       if (threadIdx.x < kTile)
         z_s[buf * kTile + threadIdx.x] = (zpart_s[(buf * 2) * kTile + threadIdx.x] +
@@ -278,7 +314,8 @@ struct FcEngine {
   // Forward pass of the tiles whose input planes have been written
   // (write_input; n_tiles = 1 or 2): z_of(buf)[r] for every row.  With two
   // tiles the MMAs of one overlap the epilogue of the other.
-  __device__ void forward(int n_tiles) {
+  __device__ __noinline__ void forward(int n_tiles) {
+    FC_CLOCK(t_f0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     issue(0, 0);
@@ -288,6 +325,9 @@ struct FcEngine {
       if (layer + 1 < d.L) issue(0, layer + 1);
       if (n_tiles > 1) epilogue(1, layer);
     }
+    FC_CLOCK(t_f1);
+    FC_ADD(3, t_f1 - t_f0);
+    FC_ADD(4, 1);
   }
 };
 
@@ -713,3 +753,14 @@ int fc_tc_local_energy(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* pa
 }
 
 }  // namespace cgsvmc
+
+#ifdef CGSVMC_RBM2_TIMING
+// Development build only: reads (and clears) the fc_tc phase counters.
+extern "C" int cgsvmc_debug_fc_tc_phases(unsigned long long* host_out) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(host_out, cgsvmc::g_fc_phase, 6 * sizeof(unsigned long long));
+  unsigned long long zero[6] = {0, 0, 0, 0, 0, 0};
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(cgsvmc::g_fc_phase, zero, sizeof(zero));
+  return e == cudaSuccess ? 0 : -2;
+}
+#endif
