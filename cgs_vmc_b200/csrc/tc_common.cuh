@@ -114,6 +114,19 @@ __device__ __forceinline__ void split3(float v, __half& h1, __half& h2, __half& 
   h3 = __float2half_rn(r2);
 }
 
+// The same for two values at once (packed conversions; identical roundings):
+// h_k = (part k of a, part k of b).
+__device__ __forceinline__ void split3_pair(float a, float b, __half2& h1, __half2& h2, __half2& h3) {
+  h1 = __floats2half2_rn(a, b);
+  const float2 f1 = __half22float2(h1);
+  float ra = (a - f1.x) * kSplitScale, rb = (b - f1.y) * kSplitScale;
+  h2 = __floats2half2_rn(ra, rb);
+  const float2 f2 = __half22float2(h2);
+  ra = (ra - f2.x) * kSplitScale;
+  rb = (rb - f2.y) * kSplitScale;
+  h3 = __floats2half2_rn(ra, rb);
+}
+
 // 8-column TMEM load (32 lanes x 32 bit x 8 columns) WITHOUT the wait: issue
 // several, then tmem_ld_wait() once.
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
