@@ -178,7 +178,7 @@ struct Engine {
     for (int e = threadIdx.x; e < kActSplits * CH * plane_halfs / 2; e += kThreads)
       reinterpret_cast<uint32_t*>(act)[e] = 0u;
     if (threadIdx.x == 0) {
-      mbar_init(mma_bar, 1);
+      mbar_init(mma_bar, (uint32_t)min(kWarps, d.n_tiles));   // one commit per issuing warp
       mbar_init(wbar, 1);
       mbar_init(wbar + 1, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -296,14 +296,20 @@ struct Engine {
     const bool first = layer == 0;
     TC_PHASE_T0();
     const uint32_t buf = (!first && d.n_wbuf == 2) ? (use_count & 1u) : 0u;
-    if (warp == 0) {
+    // MMA issue: tile t is issued by warp t mod n_iss (one elected lane each).
+    // A single issuing thread needs ~30 uniform-datapath instructions per tap
+    // (descriptors, UMOV / R2UR, elect) and was the bottleneck of the MMA phase
+    // (181 cycles per tap of three MMAs whose tensor-pipe floor is 48); up to
+    // eight warps issue in parallel, each into its own tiles' accumulators.
+    const int n_iss = min(kWarps, d.n_tiles);
+    if (warp < n_iss) {
       char* wb = wbuf + (size_t)buf * d.wbuf_bytes;
       if (!first) {
         uint64_t* bar = wbar + buf;
         const uint32_t ph = buf ? wphase1 : wphase0;
         const int j = layer - 1;
         mbar_wait(bar, ph);
-        if (d.n_wbuf == 2 && lane == 0) {   // prefetch the next layer's weights (wraps to the next forward)
+        if (d.n_wbuf == 2 && warp == 0 && lane == 0) {   // prefetch the next layer's weights (wraps to the next forward)
           const int jn = (j + 1) % d.n_tensor;
           bulk_load_async(wbuf + (size_t)(buf ^ 1u) * d.wbuf_bytes,
                           reinterpret_cast<const char*>(d.wimg) + (size_t)jn * d.wbuf_bytes,
@@ -324,7 +330,7 @@ struct Engine {
         // A: spin plane, second K chunk = the same plane one kernel row (GW rows) further
         const uint32_t b_units = smem_u32(w1s) >> 4;
         const uint32_t a_lbo = (uint32_t)d.GW << 16, b_lbo = (uint32_t)(3 * CC) << 16;
-        for (int t = 0; t < d.n_tiles; ++t) {
+        for (int t = warp; t < d.n_tiles; t += n_iss) {
           const uint32_t d_tmem = tmem + (uint32_t)(t * 3 * CC);
           for (int pr = 0; pr < d.n_pairs; ++pr) {
             const uint32_t a_lo = (a_units + (uint32_t)(t * 128 + 2 * pr * d.GW)) | a_lbo;
@@ -338,7 +344,7 @@ struct Engine {
         const uint32_t b_units = smem_u32(wb) >> 4;
         const uint32_t a_lbo = plane_units << 16, b_lbo = (uint32_t)(3 * CC) << 16;
         const uint32_t b_tap_units = (uint32_t)(CC / 8) * 3 * CC;     // per tap: [CH][3C] rows of 16 B
-        for (int t = 0; t < d.n_tiles; ++t) {
+        for (int t = warp; t < d.n_tiles; t += n_iss) {
           const uint32_t d_tmem = tmem + (uint32_t)(t * 3 * CC);
           const uint32_t a_tile = a_units + (uint32_t)(t * 128);
           for (int dx = 0; dx < d.kx; ++dx)
@@ -760,12 +766,13 @@ void size_plan(TcDesc* t, int G) {
 bool make_desc_plan(const cgsvmc_ansatz* a, size_t extra_bytes_per_cfg, size_t extra_fixed, int ctas, int il,
                     TcDesc* out);
 
-// Plans in order of measured throughput: interleaved configurations (aligned
-// tap shifts) with two CTAs per SM, with one, then the side-by-side layout.
+// Plans in order of measured throughput (C3 / C4 / 16x16, profiles/r02g_*): two
+// CTAs per SM before one (the tensor pipe of one works under the epilogue of the
+// other), and within that the interleaved layout before the side-by-side one.
 bool make_desc_host(const cgsvmc_ansatz* a, size_t extra_bytes_per_cfg, size_t extra_fixed, TcDesc* out) {
   const int max_ctas = tc_ctas_wanted();
-  for (int il = tc_interleave_wanted() ? 1 : 0; il >= 0; --il)
-    for (int ctas = max_ctas; ctas >= 1; --ctas)
+  for (int ctas = max_ctas; ctas >= 1; --ctas)
+    for (int il = tc_interleave_wanted() ? 1 : 0; il >= 0; --il)
       if (make_desc_plan(a, extra_bytes_per_cfg, extra_fixed, ctas, il, out)) return true;
   return false;
 }
