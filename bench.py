@@ -467,20 +467,29 @@ def roofline_for(w, t_step, n_act, pk):
     flop = B * (steps * f_inc + f_fwd + n_act * f_inc + 4 * f_fwd)
     what = ('B x (N sampler ratios x F_inc + E_loc (F_fwd + n_active x F_inc) + gradient of two weight '
             'columns (4 F_fwd)); F_inc = F_fwd for conv (no incremental credit)')
-  if kind == 'fully_connected':
-    return {'kernel': 'net.cu tile kernels (mlp sampler / local energy / gradient), FP32 SIMT',
-            'bound': 'fp32', 'achieved': flop / t_step / 1e12, 'peak': fp32_peak, 'unit': 'TFLOP/s',
-            'frac': flop / t_step / 1e12 / fp32_peak, 'traffic': None,
-            'peak_source': 'derived: 148 SM x 128 FP32 lanes x 2 x sm_max_mhz', 'what': what,
-            'kernel_ms': t_step * 1e3, 'n_active_bonds_mean': n_act}
   peak = pk['bf16_tflops_sustained']
-  return {'kernel': 'conv_tc.cu tcgen05 kernels (sampler, local energy) + conv gradient',
+  if kind == 'fully_connected':
+    return {'kernel': 'fc_tc.cu tcgen05 kernels (sampler, local energy) + net.cu mlp_grad_kernel (FP32 SIMT)',
+            'bound': 'tensor', 'achieved': flop / t_step / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
+            'frac': flop / t_step / 1e12 / peak, 'traffic': None,
+            'peak_source': '%s bf16 cuBLAS, sustained' % pk['source'],
+            'frac_of_split_peak': flop / t_step / 1e12 / (peak / 6.0),
+            'split': 'float32-grade products from fp16 MMAs: 6 tensor-core products per algorithmic product '
+                     '(three-way split of activations and weights), so the useful ceiling is peak / 6',
+            'fp32': {'achieved': flop / t_step / 1e12, 'peak': fp32_peak, 'unit': 'TFLOP/s',
+                     'frac': flop / t_step / 1e12 / fp32_peak,
+                     'peak_source': 'derived: 148 SM x 128 FP32 lanes x 2 x sm_max_mhz'},
+            'what': what, 'kernel_ms': t_step * 1e3, 'n_active_bonds_mean': n_act,
+            'note': 'at 1024 walkers (8 tiles of 128 for the sampler) the step is launch- and latency-bound; '
+                    'profiles/ holds the 65536-walker numbers where the tensor path is 2.5-3.4x the SIMT path'}
+  return {'kernel': 'conv_tc.cu tcgen05 kernels (sampler, local energy) + net.cu conv_grad_kernel (FP32 SIMT)',
           'bound': 'tensor', 'achieved': flop / t_step / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
           'frac': flop / t_step / 1e12 / peak, 'traffic': None,
           'peak_source': '%s bf16 cuBLAS, sustained' % pk['source'],
-          'frac_of_split_peak': flop / t_step / 1e12 / (peak / 6.0),
-          'split': 'float32-grade products from fp16 MMAs: 6 tensor-core products per algorithmic product, '
-                   'so the useful ceiling is peak / 6',
+          'frac_of_split_peak': flop / t_step / 1e12 / (peak / 5.0),
+          'split': 'float32-grade products from fp16 MMAs: 5 tensor-core products per algorithmic product '
+                   '(two activation planes x three weight planes), so the useful ceiling is peak / 5; with 16 '
+                   'filters an MMA has N <= 48 and the layer is bound by MMA issue / operand fetch, not the pipe',
           'what': what, 'kernel_ms': t_step * 1e3, 'n_active_bonds_mean': n_act}
 
 

@@ -1056,7 +1056,85 @@ conv_grad_kernel(NetDesc d, int T, const uint64_t* __restrict__ packed,
       __syncthreads();
     }
     }
-    // accumulate
+    // accumulate the weight gradients: dW_l[tap][ci][co] = sum_t w_k[t] sum_pos
+    // h_l[t][ci][pos + tap] delta_l[t][co][pos].  Register tiles of 4 input x 4
+    // output channels per (layer, tap): 8 shared-memory loads feed 16 FMAs
+    // (one entry per thread needed 2 loads + 2 table look-ups per FMA and left
+    // the kernel LSU-bound: ncu r01z, FMA pipe 11.6 %).
+    if ((C & 3) == 0) {
+      const int taps = d.kx * d.ky, cb = C / 4;
+      const int items0 = taps * cb;                 // layer 0: one input channel
+      const int items1 = taps * cb * cb;            // layers >= 1
+      const int n_items = items0 + (L - 1) * items1;
+#pragma unroll 1
+      for (int it = threadIdx.x; it < n_items; it += kThreads) {
+        int l = 0, r = it;
+        if (it >= items0) { l = 1 + (it - items0) / items1; r = (it - items0) % items1; }
+        const int cl = l == 0 ? 1 : C;
+        const int cob = r % cb;
+        const int cib = l == 0 ? 0 : (r / cb) % cb;
+        const int tap = l == 0 ? r / cb : r / (cb * cb);
+        const int dx = tap / d.ky, dy = tap - dx * d.ky;
+        const float* hl = H(l);
+        const float* dl = DL + (size_t)l * szC;
+        float acc[K][4][4];
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[k][a][b] = 0.f;
+        for (int t = 0; t < T; ++t) {
+          const float* hp = hl + ((size_t)t * cl + (l == 0 ? 0 : 4 * cib)) * N;
+          const float* dp = dl + ((size_t)t * C + 4 * cob) * N;
+          float g[4][4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) g[a][b] = 0.f;
+          for (int x = 0; x < d.X; ++x) {
+            const int sx = xi[x * d.kx + dx];
+            for (int y = 0; y < d.Y; ++y) {
+              const int hidx = sx + yi[y * d.ky + dy], pos = x * d.Y + y;
+              float hv[4], dv[4];
+#pragma unroll
+              for (int a = 0; a < 4; ++a) hv[a] = (l == 0 && a > 0) ? 0.f : hp[(size_t)a * N + hidx];
+#pragma unroll
+              for (int b = 0; b < 4; ++b) dv[b] = dp[(size_t)b * N + pos];
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) g[a][b] = fmaf(hv[a], dv[b], g[a][b]);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const float wkt = wk[k * T + t];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 4; ++b) acc[k][a][b] = fmaf(wkt, g[a][b], acc[k][a][b]);
+          }
+        }
+        // flat layout of a conv weight tensor: [tap][ci][co]
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          if (l == 0 && a > 0) continue;
+          const int ci = l == 0 ? 0 : 4 * cib + a;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int64_t e = d.w_off[l] + ((int64_t)tap * cl + ci) * C + 4 * cob + b;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+              float* dst = part + (int64_t)k * P + e;
+              *dst = first_tile ? acc[k][a][b] : *dst + acc[k][a][b];
+            }
+          }
+        }
+      }
+    }
+    // bias gradients (and, for channel counts that are not a multiple of 4, the
+    // weight gradients entry by entry)
 #pragma unroll 1
     for (int64_t e = threadIdx.x; e < P; e += kThreads) {
       float acc[K];
@@ -1066,6 +1144,7 @@ conv_grad_kernel(NetDesc d, int T, const uint64_t* __restrict__ packed,
       while (l + 1 < L && e >= d.w_off[l + 1]) ++l;
       const int cl = l == 0 ? 1 : C;
       const bool is_bias = e >= d.b_off[l];
+      if (!is_bias && (C & 3) == 0) continue;       // done above
       const float* dl = DL + (size_t)l * szC;
       if (is_bias) {
         const int co = (int)(e - d.b_off[l]);

@@ -24,7 +24,12 @@ METRICS = [
     'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
     'dram__bytes_read.sum', 'dram__bytes_write.sum',
     'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
-    'lts__t_bytes.sum',
+    'lts__t_bytes.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+    'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+    'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+    'sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active',
+    'smsp__inst_executed_pipe_tmem.sum',
     'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
     'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
     'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
