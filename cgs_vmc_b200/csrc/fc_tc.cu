@@ -726,6 +726,17 @@ int eloc_chunk(const cgsvmc_ansatz* a, const cgsvmc_ham* h, int64_t B) {
 
 }  // namespace
 
+// The split weight image and constants of a supported network (built when the
+// parameters changed), for the gradient kernel of fc_tc_grad.cu.
+int fc_tc_image(cgsvmc_ansatz* a, const void** wimg, const float** consts, cudaStream_t st) {
+  FcDesc d;
+  if (!make_fc_desc(a, mc_extra, &d)) { set_error("fc_tc: unsupported network"); return CGSVMC_ERR_UNSUPPORTED; }
+  if (int rc = build_fc_image(a, &d, st)) return rc;
+  *wimg = d.wimg;
+  *consts = d.consts;
+  return CGSVMC_OK;
+}
+
 bool fc_tc_supported(const cgsvmc_ansatz* a, const cgsvmc_ham* h) {
   if (!fc_tc_enabled()) return false;
   FcDesc d;

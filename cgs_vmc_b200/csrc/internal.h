@@ -154,6 +154,13 @@ int fc_tc_local_energy(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* pa
                        float* e_loc, float* log_amp_out, float* diag_out, float* off_out,
                        cudaStream_t s);
 
+// weighted gradient sums of the fully connected ansatz on tcgen05 (fc_tc_grad.cu):
+// forward, backward-data and the weight-gradient GEMMs dW_l = h_{l-1}^T (w delta_l)
+int fc_tc_image(cgsvmc_ansatz* a, const void** wimg, const float** consts, cudaStream_t s);
+bool fc_tc_grad_supported(const cgsvmc_ansatz* a);
+int fc_tc_grad(cgsvmc_ansatz* a, const uint64_t* packed, const float* weights, int64_t B, int K,
+               float* out, cudaStream_t s);
+
 // ---- generic tile networks: fc, rbm with hidden layers, conv (net.cu) ----
 int net_log_amp(const cgsvmc_ansatz* a, const uint64_t* packed, int64_t B, float* out,
                 cudaStream_t s);

@@ -180,3 +180,63 @@ def test_fc_tc_sampler_large_batch_two_tiles(native):
   same = (p_big[:500] == p_small).all(dim=1)
   assert same.float().mean().item() > 0.99      # near-ties may differ between tile placements? no: same arithmetic
   assert torch.equal(p_big[:500], p_small)
+
+
+# ---------------------------------------------------------------------------
+# gradient on the tensor cores (fc_tc_grad.cu)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('spec', FC_SHAPES[:5], ids=_id)
+@pytest.mark.parametrize('batch', [1, 127, 300, 20000])
+def test_fc_tc_weighted_grad_sum_vs_oracle_and_simt(native, spec, batch):
+  """S_k = sum_b w_kb O_b (training.py:545-548, 169-175) from the tcgen05
+  forward / backward / weight-gradient GEMMs against float64 autograd and
+  against the SIMT kernel of net.cu; gradient tolerance of the suite: 1e-4 of
+  the largest entry per entry, 3e-5 in norm."""
+  from oracle import estimators
+  from gpu_util import packed_cuda
+  a, params, cfg = _setup(spec, seed=17 + batch, batch=batch)
+  rng = np.random.default_rng(3)
+  w = rng.normal(size=(2, batch)).astype(np.float32)
+  w[0] = 1.0
+  packed = packed_cuda(cfg)
+  wt = torch.from_numpy(w).cuda()
+  out = a.weighted_grad_sum(packed, wt).cpu().numpy()
+  os.environ['CGSVMC_FC_TC_GRAD'] = '0'
+  try:
+    simt = a.weighted_grad_sum(packed, wt).cpu().numpy()
+  finally:
+    os.environ.pop('CGSVMC_FC_TC_GRAD', None)
+  for k in range(2):
+    scale = np.abs(simt[k]).max() + 1e-3
+    assert np.abs(out[k] - simt[k]).max() <= 1e-4 * scale + 1e-4, (k, np.abs(out[k] - simt[k]).max(), scale)
+  if batch <= 300:
+    cfg64 = torch.from_numpy(cfg).to(F64)
+    ref = estimators.weighted_grad_sum(spec, params, cfg64, torch.from_numpy(w).to(F64)).numpy()
+    for k in range(2):
+      scale = np.abs(ref[k]).max() + 1e-3
+      assert np.abs(out[k] - ref[k]).max() <= 1e-4 * scale + 1e-4, (k, np.abs(out[k] - ref[k]).max(), scale)
+      assert np.linalg.norm(out[k] - ref[k]) <= 3e-5 * np.linalg.norm(ref[k]) + 1e-4
+  # single column and accumulate-into semantics
+  one = a.weighted_grad_sum(packed, torch.from_numpy(w[1:2].copy()).cuda())
+  np.testing.assert_allclose(one[0].cpu().numpy(), out[1], rtol=1e-5, atol=1e-5 * (np.abs(out[1]).max() + 1))
+  twice = a.weighted_grad_sum(packed, torch.from_numpy(w[1:2].copy()).cuda(), out=one.clone())
+  np.testing.assert_allclose(twice[0].cpu().numpy(), 2 * out[1], rtol=1e-5, atol=1e-5 * (np.abs(out[1]).max() + 1))
+
+
+def test_fc_tc_energy_gradient_golden(native):
+  """The energy gradient the reference's EnergyGradientOptimizer graph produced
+  for the C1 network (training.py:539-564), through fc_tc local energy + fc_tc
+  gradient."""
+  from gpu_util import make_native, packed_cuda
+  spec, g = load_golden('fc_chain20')
+  a = make_native(spec, g['params_flat'])
+  ham = native.Hamiltonian(g['bonds_ij'], g['bonds_jx'], g['bonds_jz'], spec.n_sites)
+  packed = packed_cuda(g['eg_configs'])
+  e, _ = a.local_energy(ham, packed)
+  s = a.weighted_grad_sum(packed, torch.stack([torch.ones_like(e), e]))
+  stats = native.energy_stats(e).cpu().numpy()
+  mean_e = stats[0] / stats[2]
+  assert abs(mean_e - float(g['eg_mean_energy'])) < 5e-5 * (1 + abs(mean_e))
+  grad = (s[1] - mean_e * s[0]).cpu().numpy()
+  ref = g['eg_gradient']
+  assert np.linalg.norm(grad - ref) <= 5e-4 * np.linalg.norm(ref) + 1e-4
