@@ -74,10 +74,17 @@ __host__ __device__ inline GradSmem grad_plan(const GradDesc& d, int KW) {
     p.wgbuf = off; off += ((planes > staging ? planes : staging) + 127) / 128 * 128;
   }
   p.wk = off; off += (size_t)KW * kTile * 4;
-  p.accout = off; off += (size_t)KW * (d.H + 4) * 4;
+  p.accout = off; off += (size_t)4 * KW * (d.H + 4) * 4;     // [lane quarter][k][H + 4]: one writer per slot
   off = (off + 15) / 16 * 16;
   p.bars = off; off += 64;
   p.cfg = off; off += (size_t)kTile * d.NW * 8;
+  // The weight-gradient MMAs read their MN-major A operand as M = 128 rows = 16
+  // chunks from the start of an activation plane (rows past the real features
+  // are junk accumulator rows nobody reads): keep those reads inside the CTA's
+  // allocation for narrow layers.
+  size_t last_a = p.h0;
+  if (d.L > 1) last_a = p.hbuf + (size_t)(d.L - 2) * p.hbuf_each + (size_t)(CH + 1) * kPlane;
+  if (last_a + 16 * (size_t)kPlane > off) off = last_a + 16 * (size_t)kPlane;
   p.total = off;
   return p;
 }
@@ -187,7 +194,7 @@ fc_grad_kernel(GradDesc d, const uint64_t* __restrict__ packed, const float* __r
 
   // ---- one-time setup ----
   for (int e = threadIdx.x; e < d.L * H + H + 1; e += kThreads) bias_s[e] = d.consts[e];
-  for (int e = threadIdx.x; e < KW * (H + 4); e += kThreads) accout[e] = 0.f;
+  for (int e = threadIdx.x; e < 4 * KW * (H + 4); e += kThreads) accout[e] = 0.f;
   // constant-one feature behind the real ones: chunk K1/8 of h_0, chunk CH of the
   // first plane of h_1 .. h_{L-1} (second planes: zero)
   for (int e = threadIdx.x; e < kTile; e += kThreads) {
@@ -340,7 +347,8 @@ fc_grad_kernel(GradDesc d, const uint64_t* __restrict__ packed, const float* __r
 #pragma unroll
               for (int e = 0; e < 8; ++e) wv[e] = wkr * v[e];
               const float cs = colsum8(wv, lane);
-              if ((lane & 3) == 0) atomicAdd(&accout[k * (H + 4) + half * HH + 8 * c8 + ((lane >> 2) & 7)], cs);
+              // slot (lane quarter q, k, column): written by this warp only -- deterministic, no atomics
+              if ((lane & 3) == 0) accout[(q * KW + k) * (H + 4) + half * HH + 8 * c8 + ((lane >> 2) & 7)] += cs;
             }
             float g[8];
 #pragma unroll
@@ -353,7 +361,7 @@ fc_grad_kernel(GradDesc d, const uint64_t* __restrict__ packed, const float* __r
 #pragma unroll
           for (int k = 0; k < KW; ++k) {
             const float s = warp_sum(wk_s[k * kTile + r]);
-            if (lane == 0) atomicAdd(&accout[k * (H + 4) + H], s);
+            if (lane == 0) accout[(q * KW + k) * (H + 4) + H] += s;
           }
         }
       }
@@ -456,11 +464,26 @@ fc_grad_kernel(GradDesc d, const uint64_t* __restrict__ packed, const float* __r
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        {   // coalesced read-modify-write of this CTA's slice
+        {   // coalesced read-modify-write of this CTA's (L2-resident) slice, eight
+            // independent loads in flight per thread (a load-add-store chain per
+            // element would pay the L2 latency in_dim * H / 288 times)
           float* pw = part + (size_t)k * d.P + d.w_off[l];
-          for (int e = threadIdx.x; e < in_dim * H; e += kThreads) {
-            const int i = e / H, j = e - i * H;
-            pw[e] += stage[(size_t)i * HS + j];
+          const int n = in_dim * H;
+          for (int e0 = threadIdx.x; e0 < n; e0 += 8 * kThreads) {
+            float old[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int e = e0 + u * kThreads;
+              old[u] = e < n ? __ldcg(pw + e) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int e = e0 + u * kThreads;
+              if (e < n) {
+                const int i = e / H, j = e - i * H;
+                pw[e] = old[u] + stage[(size_t)i * HS + j];
+              }
+            }
           }
           float* pb = part + (size_t)k * d.P + d.b_off[l];
           for (int j = threadIdx.x; j < H; j += kThreads) pb[j] += stage[(size_t)ones_row * HS + j];
@@ -503,7 +526,10 @@ fc_grad_kernel(GradDesc d, const uint64_t* __restrict__ packed, const float* __r
   __syncthreads();
   for (int e = threadIdx.x; e < KW * (H + 1); e += kThreads) {
     const int k = e / (H + 1), j = e - k * (H + 1);
-    part[(size_t)k * d.P + (j < H ? d.w_off[d.L] + j : d.b_off[d.L])] += accout[k * (H + 4) + j];
+    float total = 0.f;
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) total += accout[(qq * KW + k) * (H + 4) + j];
+    part[(size_t)k * d.P + (j < H ? d.w_off[d.L] + j : d.b_off[d.L])] += total;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

@@ -185,8 +185,16 @@ def test_fc_tc_sampler_large_batch_two_tiles(native):
 # ---------------------------------------------------------------------------
 # gradient on the tensor cores (fc_tc_grad.cu)
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize('spec', FC_SHAPES[:5], ids=_id)
-@pytest.mark.parametrize('batch', [1, 127, 300, 20000])
+# 20000 walkers = two tiles per CTA.  Smooth nonlinearities there: with relu one
+# pre-activation out of millions lands within float32 rounding of the kink and
+# its derivative (0 or 1) legitimately differs between two float32 evaluations.
+GRAD_CASES = [(s, b) for b in (1, 127, 300) for s in FC_SHAPES[:5]] + [
+    (oansatz.AnsatzSpec('fully_connected', 20, num_layers=3, layer_size=80, nonlinearity='tanh'), 20000),
+    (oansatz.AnsatzSpec('fully_connected', 100, num_layers=4, layer_size=48, nonlinearity='tanh'), 20000),
+    (FC_SHAPES[2], 20000), (FC_SHAPES[4], 20000)]
+
+
+@pytest.mark.parametrize('spec,batch', GRAD_CASES, ids=lambda v: _id(v) if hasattr(v, 'kind') else str(v))
 def test_fc_tc_weighted_grad_sum_vs_oracle_and_simt(native, spec, batch):
   """S_k = sum_b w_kb O_b (training.py:545-548, 169-175) from the tcgen05
   forward / backward / weight-gradient GEMMs against float64 autograd and
@@ -206,21 +214,25 @@ def test_fc_tc_weighted_grad_sum_vs_oracle_and_simt(native, spec, batch):
     simt = a.weighted_grad_sum(packed, wt).cpu().numpy()
   finally:
     os.environ.pop('CGSVMC_FC_TC_GRAD', None)
+  cfg64 = torch.from_numpy(cfg).to(F64)
+  ref = estimators.weighted_grad_sum(spec, params, cfg64, torch.from_numpy(w).to(F64)).numpy()
   for k in range(2):
-    scale = np.abs(simt[k]).max() + 1e-3
-    assert np.abs(out[k] - simt[k]).max() <= 1e-4 * scale + 1e-4, (k, np.abs(out[k] - simt[k]).max(), scale)
-  if batch <= 300:
-    cfg64 = torch.from_numpy(cfg).to(F64)
-    ref = estimators.weighted_grad_sum(spec, params, cfg64, torch.from_numpy(w).to(F64)).numpy()
-    for k in range(2):
-      scale = np.abs(ref[k]).max() + 1e-3
-      assert np.abs(out[k] - ref[k]).max() <= 1e-4 * scale + 1e-4, (k, np.abs(out[k] - ref[k]).max(), scale)
+    scale = np.abs(ref[k]).max() + 1e-3
+    err = np.abs(out[k] - ref[k]).max()
+    err_simt = np.abs(simt[k] - ref[k]).max()
+    # float32 sums over the batch: hold the tensor-core path to the suite's
+    # tolerance, or -- for the 20000-walker sums, where float32 summation noise
+    # dominates -- to the error of the SIMT kernel
+    assert err <= max(1e-4 * scale + 1e-4, 2.0 * err_simt), (k, err, err_simt, scale)
+    if batch <= 300:
       assert np.linalg.norm(out[k] - ref[k]) <= 3e-5 * np.linalg.norm(ref[k]) + 1e-4
   # single column and accumulate-into semantics
   one = a.weighted_grad_sum(packed, torch.from_numpy(w[1:2].copy()).cuda())
   np.testing.assert_allclose(one[0].cpu().numpy(), out[1], rtol=1e-5, atol=1e-5 * (np.abs(out[1]).max() + 1))
   twice = a.weighted_grad_sum(packed, torch.from_numpy(w[1:2].copy()).cuda(), out=one.clone())
   np.testing.assert_allclose(twice[0].cpu().numpy(), 2 * out[1], rtol=1e-5, atol=1e-5 * (np.abs(out[1]).max() + 1))
+  # deterministic: fixed summation order everywhere
+  assert np.array_equal(a.weighted_grad_sum(packed, wt).cpu().numpy(), out)
 
 
 def test_fc_tc_energy_gradient_golden(native):
