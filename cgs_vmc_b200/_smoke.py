@@ -45,5 +45,22 @@ def run():
   assert np.allclose(e.cpu().numpy(), eo, atol=2e-3, rtol=1e-4), 'local energy mismatch'
   assert abs(stats[0].item() - eo.sum()) < 1e-2 * (1 + abs(eo.sum()))
   assert torch.isfinite(s).all()
+  # the tensor-core ansaetze: fully connected (fc_tc.cu, gradient fc_tc_grad.cu)
+  # and periodic convolution (conv_tc.cu), amplitudes against the oracle
+  for tc_spec in (oansatz.AnsatzSpec('fully_connected', 20, num_layers=3, layer_size=80),
+                  oansatz.AnsatzSpec('conv_2d', 36, num_layers=3, num_filters=16, kernel_size=3,
+                                     size_x=6, size_y=6)):
+    tc_params = oansatz.init_params(tc_spec, seed=7, bias_scale=0.1, dtype=torch.float64)
+    t = _native.Ansatz(tc_spec.kind, tc_spec.n_sites, num_layers=tc_spec.num_layers,
+                       layer_size=tc_spec.layer_size, num_filters=tc_spec.num_filters,
+                       kernel_size=tc_spec.kernel_size, size_x=tc_spec.size_x, size_y=tc_spec.size_y)
+    t.set_params(oansatz.flatten(tc_params).float())
+    tc_cfg = bits.random_sz0_configs(tc_spec.n_sites, 64, np.random.default_rng(5))
+    tc_packed = torch.from_numpy(bits.pack(tc_cfg).view(np.int64)).cuda()
+    z_tc = t.log_amp(tc_packed).cpu().numpy()
+    z_ref = oansatz.log_amp(tc_spec, tc_params, torch.from_numpy(tc_cfg).to(torch.float64)).numpy()
+    assert np.allclose(z_tc, z_ref, atol=3e-4, rtol=3e-5), '%s: log-amplitude mismatch' % tc_spec.kind
+    g_tc = t.weighted_grad_sum(tc_packed, torch.ones(1, 64, device='cuda'))
+    assert torch.isfinite(g_tc).all(), '%s: gradient not finite' % tc_spec.kind
   print('smoke ok: accept=%d/%d  <E>/N=%.5f  |G1|=%.3f' % (
       int(count.item()), 256 * 36, eo.mean() / 36, float(s[0].norm())))

@@ -287,7 +287,10 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
   static const bool pt_off = getenv("CGSVMC_RBM2_NO_PAIR_TABLE") != nullptr;
   pl.pt = !pt_off && do_eloc && pl.ws && pl.lpw == 8 && nb >= 1 && nb < 16384 &&
           walker_smem_bytes(pl.im, slots, true, do_eloc, nb, do_grad, mc, true) <= (size_t)a->max_smem_optin;
-  cgsvmc_ansatz::PairTable* slot = pl.pt ? pair_slot(a, h, (size_t)2 * nb * pl.im.HP * 4) : nullptr;
+  // tables in global memory: the pair table too (read through L1 / L2)
+  const bool pt_global = !pt_off && do_eloc && !pl.ws && nb >= 1 && nb < 16384;
+  cgsvmc_ansatz::PairTable* slot =
+      (pl.pt || pt_global) ? pair_slot(a, h, (size_t)2 * nb * pl.im.HP * 4) : nullptr;
   if (slot == nullptr) pl.pt = false;
   pl.walker_smem = walker_smem_bytes(pl.im, slots, pl.ws, do_eloc, nb, do_grad, mc, pl.pt);
   if (pl.walker_smem > (size_t)a->max_smem_optin) {
@@ -295,12 +298,12 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
     return CGSVMC_ERR_UNSUPPORTED;
   }
   if (int rc = build_image(a, pl, st)) return rc;
-  if (pl.pt)
+  if (slot != nullptr)
     if (int rc = build_pair_table(a, h, pl, slot, st)) return rc;
   const int64_t P = a->n_params;
   WalkerArgs A;
   memset(&A, 0, sizeof(A));
-  A.pair_table = pl.pt ? slot->buf : nullptr;
+  A.pair_table = slot != nullptr ? slot->buf : nullptr;
   A.packed = packed; A.B = B; A.wpc = pl.wpc; A.n_batches = pl.n_batches;
   A.do_eloc = do_eloc ? 1 : 0;
   if (do_eloc) { A.bonds_ij = h->ij; A.bonds_jx = h->jx; A.bonds_jz = h->jz; A.n_bonds = h->n_bonds; }

@@ -353,7 +353,7 @@ __device__ __forceinline__ void transpose_reduce(float (&part)[LPW], int sub) {
 // bond-pair table (T_j = F[d][j] G[u][j], formed by pair_prep_kernel with the
 // same multiply as exchange_log2_partial: identical values, half the
 // shared-memory traffic and no FMUL2 per pair of hidden units).
-template <int LPW, int KJV>
+template <int LPW, int KJV, bool WS = true>
 __device__ __forceinline__ float pair_log2_partial(const float* __restrict__ row, int sub,
                                                    const float (&p)[32 / LPW * KJV],
                                                    const float (&m)[32 / LPW * KJV]) {
@@ -362,7 +362,7 @@ __device__ __forceinline__ float pair_log2_partial(const float* __restrict__ row
 #pragma unroll
   for (int q = 0; q < KJV; ++q) {
     float tv[VW];
-    ldv<VW, true>(row + VW * sub + 32 * q, tv);
+    ldv<VW, WS>(row + VW * sub + 32 * q, tv);
 #pragma unroll
     for (int c = 0; c < VW; c += 2) {
       const int k = VW * q + c;
@@ -404,7 +404,7 @@ __device__ __forceinline__ float ratio_round(const Tables& t, const uint32_t* li
     for (int i = 0; i < R; ++i) {
       const uint32_t ent = it0 + i < cnt ? list[it0 + i] : 0u;
       const int row = (int)(((ent >> 16) & 0x7fffu) * 2u + (ent >> 31));
-      part[i] = pair_log2_partial<LPW, KJV>(pair_s + (size_t)row * HP, sub, p, m);
+      part[i] = pair_log2_partial<LPW, KJV, WS>(pair_s + (size_t)row * HP, sub, p, m);
     }
   } else {
 #pragma unroll
@@ -913,7 +913,10 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
   float* e_s = reinterpret_cast<float*>(cur); cur += (size_t)SLOTS * 4;
   // select table: inside the image when it is in shared memory, else 2048 bytes here (MC only)
   uint8_t* lut = WS ? reinterpret_cast<uint8_t*>(img_s + im.off_lut) : reinterpret_cast<uint8_t*>(cur);
-  float* pair_s = PT ? reinterpret_cast<float*>(cur) : nullptr;      // [2 n_bonds][HP]
+  // [2 n_bonds][HP]: in shared memory (PT), or -- tables too large for shared
+  // memory (16x16, H = 256) -- read through L1 / L2 like the site tables: still
+  // one row per amplitude ratio instead of two and no multiply per hidden unit
+  const float* pair_s = PT ? reinterpret_cast<const float*>(cur) : (!WS ? A.pair_table : nullptr);
   int* tile_next_s = reinterpret_cast<int*>(bar) + 2;                // behind the 8-byte mbarrier
 
   RBM2_MARK(1, 0);
@@ -930,7 +933,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
     load_walker<NW, LPW>(A, im, bb, sub, grp, s_first);
   }
   if (PT) bulk_load(smem, img_g + img_skip, (uint32_t)(im.total - img_skip) * 4u, bar,
-                    pair_s, A.pair_table, (uint32_t)(2 * A.n_bonds * HP) * 4u,
+                    const_cast<float*>(pair_s), A.pair_table, (uint32_t)(2 * A.n_bonds * HP) * 4u,
                     T_s, img_g + im.off_w2, (uint32_t)(im.N * HP) * 4u);
   else if (WS) bulk_load(img_s, img_g, (uint32_t)im.total * 4u, bar);
   else if (MC) build_lut(lut);
