@@ -398,6 +398,7 @@ int cgsvmc_weighted_grad_sum(const cgsvmc_ansatz* a, const uint64_t* packed, con
   }
   if (rbm_fast_supported(a)) return rbm_grad(am, packed, weights, B, K, out, (cudaStream_t)stream);
   if (fc_tc_grad_supported(a)) return fc_tc_grad(am, packed, weights, B, K, out, (cudaStream_t)stream);
+  if (conv_tc_grad_supported(a)) return conv_tc_grad(am, packed, weights, B, K, out, (cudaStream_t)stream);
   return net_grad(am, packed, weights, B, K, out, (cudaStream_t)stream);
 }
 

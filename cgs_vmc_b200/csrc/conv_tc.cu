@@ -107,6 +107,7 @@ struct TcDesc {
   int ystep;                // rows per step in y: G (interleaved) or 1
   const __half* w1img;      // [n_pairs][2][3C][8]   layer 1 B operand
   const __half* wimg;       // [n_tensor][taps][C/8][3C][8]
+  const __half* wimg_b;     // the same layers for backward-data: taps mirrored, [co chunk][3C: split, ci][8 co]
   const float* bias;        // [L - 1][C]  layers 1 .. L-1
   const float* wsum;        // [C] last-layer column sums, then z0 = N sum_c b_L[c]
 };
@@ -679,8 +680,8 @@ __device__ __forceinline__ __half split_part(float w, int split) {
 __global__ void tc_prep_kernel(int kx, int ky, int C, int L, int N, int n_pairs,
                                const float* __restrict__ params, const int64_t* __restrict__ w_off,
                                const int64_t* __restrict__ b_off, __half* __restrict__ w1img,
-                               __half* __restrict__ wimg, int64_t wimg_halfs, float* __restrict__ bias,
-                               float* __restrict__ wsum, int n_tensor) {
+                               __half* __restrict__ wimg, __half* __restrict__ wimg_b, int64_t wimg_halfs,
+                               float* __restrict__ bias, float* __restrict__ wsum, int n_tensor) {
   const int taps = kx * ky;
   const int64_t per_layer = (int64_t)taps * 3 * C * C;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < wimg_halfs;
@@ -695,6 +696,12 @@ __global__ void tc_prep_kernel(int kx, int ky, int C, int L, int N, int n_pairs,
     const int ci = chunk * 8 + el;
     const float w = params[w_off[j + 1] + ((int64_t)tap * C + ci) * C + co];   // layer j + 2, [tap][ci][co]
     wimg[e] = split_part(w, split);
+    // backward-data image (conv_tc_grad.cu): the transposed convolution is the
+    // same implicit GEMM with the taps mirrored and the channel matrices
+    // transposed; in this element's indices: K chunk / el = output channel, n = input channel
+    const int tap_m = (kx - 1 - tap / ky) * ky + (ky - 1 - tap % ky);
+    const float wb = params[w_off[j + 1] + ((int64_t)tap_m * C + co) * C + ci];
+    wimg_b[e] = split_part(wb, split);
   }
   if (blockIdx.x == 0) {
     // layer 1: [pair][dx_local][n = split * C + co][slot e = dy]; zero beyond the kernel
@@ -835,7 +842,8 @@ int build_tc_image(cgsvmc_ansatz* a, TcDesc* d, cudaStream_t st) {
   const size_t off_pad = (off_bytes + 255) / 256 * 256;
   const size_t small_bytes = (((size_t)(d->L - 1) * d->C + d->C + 4) * 4 + 255) / 256 * 256;
   const size_t w1_bytes = ((size_t)d->n_pairs * 2 * 3 * d->C * 16 + 255) / 256 * 256;
-  const size_t bytes = off_pad + small_bytes + w1_bytes + (size_t)wimg_halfs * 2;
+  const size_t wimg_bytes = ((size_t)wimg_halfs * 2 + 255) / 256 * 256;
+  const size_t bytes = off_pad + small_bytes + w1_bytes + 2 * wimg_bytes;
   if (a->tables_bytes < bytes) {
     if (a->tables != nullptr) {
       if (int rc = cuda_fail(cudaDeviceSynchronize(), "tables sync")) return rc;
@@ -860,14 +868,16 @@ int build_tc_image(cgsvmc_ansatz* a, TcDesc* d, cudaStream_t st) {
   float* wsum = bias + (int64_t)(d->L - 1) * d->C;
   __half* w1img = reinterpret_cast<__half*>(base + off_pad + small_bytes);
   __half* wimg = reinterpret_cast<__half*>(base + off_pad + small_bytes + w1_bytes);
+  __half* wimg_b = reinterpret_cast<__half*>(base + off_pad + small_bytes + w1_bytes + wimg_bytes);
   d->w1img = w1img;
   d->wimg = wimg;
+  d->wimg_b = wimg_b;
   d->bias = bias;
   d->wsum = wsum;
   if (a->track_params && a->tables_valid) return CGSVMC_OK;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((wimg_halfs + 255) / 256, 592));
   tc_prep_kernel<<<blocks, 256, 0, st>>>(d->kx, d->ky, d->C, d->L, d->N, d->n_pairs, a->params, w_off, b_off,
-                                         w1img, wimg, wimg_halfs, bias, wsum, d->n_tensor);
+                                         w1img, wimg, wimg_b, wimg_halfs, bias, wsum, d->n_tensor);
   a->tables_valid = true;
   return cuda_fail(cudaGetLastError(), "conv_tc prep launch");
 }
@@ -906,6 +916,15 @@ bool conv_tc_supported(const cgsvmc_ansatz* a, const cgsvmc_ham* h) {
       KERNEL<32, 1><<<grid, kThreads, smem, st>>>(__VA_ARGS__);                                 \
     }                                                                                           \
   } while (0)
+
+// The parameter image for conv_tc_grad.cu (same buffers the forward kernels read).
+int conv_tc_image(cgsvmc_ansatz* a, ConvTcImage* img, cudaStream_t st) {
+  TcDesc d;
+  if (!make_desc_host(a, 0, 0, &d)) { set_error("conv_tc: unsupported network"); return CGSVMC_ERR_UNSUPPORTED; }
+  if (int rc = build_tc_image(a, &d, st)) return rc;
+  img->w1img = d.w1img; img->wimg = d.wimg; img->wimg_b = d.wimg_b; img->bias = d.bias; img->wsum = d.wsum;
+  return CGSVMC_OK;
+}
 
 int conv_tc_log_amp(cgsvmc_ansatz* a, const uint64_t* packed, int64_t B, float* out, cudaStream_t st) {
   TcDesc d;

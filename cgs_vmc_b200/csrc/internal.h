@@ -144,6 +144,18 @@ int conv_tc_local_energy(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* 
                          float* e_loc, float* log_amp_out, float* diag_out, float* off_out,
                          cudaStream_t s);
 
+// weighted gradient sums of conv_1d / conv_2d on tcgen05 (conv_tc_grad.cu): forward,
+// backward-data as the mirrored implicit GEMM, weight gradients as GEMMs over the
+// rows (sites x configurations) of a batch with MN-major operands
+struct ConvTcImage {
+  const void *w1img, *wimg, *wimg_b;   // layer-1 B operand; forward / backward-data images of the tensor layers
+  const float *bias, *wsum;            // [L-1][C]; [C] last-layer column sums, then N sum_c b_L[c]
+};
+int conv_tc_image(cgsvmc_ansatz* a, ConvTcImage* img, cudaStream_t s);
+bool conv_tc_grad_supported(const cgsvmc_ansatz* a);
+int conv_tc_grad(cgsvmc_ansatz* a, const uint64_t* packed, const float* weights, int64_t B, int K,
+                 float* out, cudaStream_t s);
+
 // ---- fully_connected forward on the tensor cores (fc_tc.cu): tcgen05 + TMEM ----
 bool fc_tc_supported(const cgsvmc_ansatz* a, const cgsvmc_ham* h);
 int fc_tc_log_amp(cgsvmc_ansatz* a, const uint64_t* packed, int64_t B, float* out, cudaStream_t s);

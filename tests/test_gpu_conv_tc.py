@@ -136,3 +136,112 @@ def test_tc_sampler_matches_oracle_philox(native, spec):
   for s in range(0, 6, 2):
     a.mc_steps(p_steps, 2, 11, walker_id0=3, step0=s)
   assert torch.equal(p_all, p_steps)
+
+
+# ---------------------------------------------------------------------------
+# weighted gradient sums on the tensor cores (conv_tc_grad.cu)
+# ---------------------------------------------------------------------------
+GRAD_SHAPES = [
+    oansatz.AnsatzSpec('conv_2d', 100, num_layers=5, num_filters=16, kernel_size=5, size_x=10, size_y=10),  # C3
+    oansatz.AnsatzSpec('conv_2d', 36, num_layers=3, num_filters=16, kernel_size=3, size_x=6, size_y=6),
+    oansatz.AnsatzSpec('conv_2d', 36, num_layers=5, num_filters=16, kernel_size=5, size_x=6, size_y=6,
+                       nonlinearity='tanh'),                                                                # C4 shape
+    oansatz.AnsatzSpec('conv_2d', 64, num_layers=4, num_filters=16, kernel_size=4, size_x=8, size_y=8,
+                       nonlinearity='sigmoid'),                                # even kernel: pad != k - 1 - pad
+    oansatz.AnsatzSpec('conv_2d', 24, num_layers=4, num_filters=16, kernel_size=3, size_x=4, size_y=6),
+    oansatz.AnsatzSpec('conv_1d', 20, num_layers=3, num_filters=16, kernel_size=5, nonlinearity='tanh'),
+    oansatz.AnsatzSpec('conv_1d', 70, num_layers=4, num_filters=16, kernel_size=6),
+]
+
+
+def _grad_both(a, packed, w, **kw):
+  """(tensor-core path, SIMT tile path) of cgsvmc_weighted_grad_sum."""
+  os.environ['CGSVMC_CONV_TC_GRAD'] = '1'
+  tc_out = a.weighted_grad_sum(packed, w, **kw).cpu().numpy()
+  os.environ['CGSVMC_CONV_TC_GRAD'] = '0'
+  try:
+    simt = a.weighted_grad_sum(packed, w).cpu().numpy()
+  finally:
+    os.environ.pop('CGSVMC_CONV_TC_GRAD', None)
+  return tc_out, simt
+
+
+@pytest.mark.parametrize('spec', GRAD_SHAPES, ids=_id)
+@pytest.mark.parametrize('batch', [1, 5, 301])
+def test_tc_weighted_grad_sum_vs_oracle_and_simt(native, spec, batch):
+  """S_k = sum_b w_kb d z_b / d params (training.py:545-548) from the tcgen05
+  kernel against float64 autograd and against the float32 SIMT kernel.  Stated
+  tolerance (the suite's gradient tolerance): 1e-4 of the largest entry per
+  entry, 3e-5 of the norm overall; ragged batches (the last batch of a CTA is
+  partial), one and two weight columns, a third column through the pair loop."""
+  from gpu_util import packed_cuda
+  from oracle import estimators
+  a, params, cfg = _setup(spec, seed=31 + batch, batch=batch)
+  packed = packed_cuda(cfg)
+  rng = np.random.default_rng(5)
+  w = rng.normal(size=(3, batch)).astype(np.float32)
+  w[0] = 1.0
+  wt = torch.from_numpy(w).cuda()
+  out, simt = _grad_both(a, packed, wt)
+  cfg64 = torch.from_numpy(cfg).to(F64)
+  ref = estimators.weighted_grad_sum(spec, params, cfg64, torch.from_numpy(w).to(F64)).numpy()
+  for k in range(3):
+    scale = np.abs(ref[k]).max() + 1e-3
+    err = np.abs(out[k] - ref[k])
+    assert err.max() <= 1e-4 * scale + 1e-4, (k, err.max(), scale, int(err.argmax()))
+    assert np.linalg.norm(out[k] - ref[k]) <= 3e-5 * np.linalg.norm(ref[k]) + 1e-4
+    assert np.abs(out[k] - simt[k]).max() <= 1e-4 * scale + 1e-4
+  one = a.weighted_grad_sum(packed, wt[1:2].contiguous())
+  np.testing.assert_allclose(one[0].cpu().numpy(), out[1], rtol=1e-5, atol=1e-5)
+  twice = a.weighted_grad_sum(packed, wt[1:2].contiguous(), out=one.clone())
+  np.testing.assert_allclose(twice[0].cpu().numpy(), 2 * out[1], rtol=1e-5, atol=1e-5)
+
+
+def test_tc_weighted_grad_sum_large_batches(native):
+  """Many configurations per CTA batch (the plan grows G with the walker
+  count), deterministic from run to run, linear in the weights."""
+  from gpu_util import packed_cuda
+  from oracle import estimators
+  spec = GRAD_SHAPES[1]
+  batch = 2100
+  a, params, cfg = _setup(spec, seed=77, batch=batch)
+  packed = packed_cuda(cfg)
+  rng = np.random.default_rng(8)
+  w = rng.normal(size=(2, batch)).astype(np.float32)
+  wt = torch.from_numpy(w).cuda()
+  out = a.weighted_grad_sum(packed, wt)
+  again = a.weighted_grad_sum(packed, wt)
+  assert torch.equal(out, again)
+  cfg64 = torch.from_numpy(cfg).to(F64)
+  ref = estimators.weighted_grad_sum(spec, params, cfg64, torch.from_numpy(w).to(F64)).numpy()
+  for k in range(2):
+    scale = np.abs(ref[k]).max() + 1e-3
+    assert np.abs(out[k].cpu().numpy() - ref[k]).max() <= 1e-4 * scale + 1e-4
+  both = a.weighted_grad_sum(packed, (wt[0] + 2 * wt[1]).reshape(1, -1).contiguous())[0]
+  scale = float(both.abs().max()) + 1e-3
+  assert float((both - (out[0] + 2 * out[1])).abs().max()) <= 1e-4 * scale
+
+
+def test_tc_accumulate_c3_full_size(native):
+  """BASELINE C3 at 8192 walkers: accumulate (K3 + K4 + K5) with the
+  tensor-core gradient equals the SIMT gradient path within the gradient
+  tolerance (size-independent check; the oracle needs minutes at this size)."""
+  from gpu_util import packed_cuda
+  spec = GRAD_SHAPES[0]
+  batch = 8192
+  a, params, cfg = _setup(spec, seed=3, batch=batch)
+  packed = packed_cuda(cfg)
+  ij, jx, jz = _bonds(spec)
+  ham = native.Hamiltonian(ij, jx, jz, spec.n_sites)
+  res = []
+  for flag in ('1', '0'):
+    os.environ['CGSVMC_CONV_TC_GRAD'] = flag
+    sums = torch.zeros(2, a.num_params, dtype=torch.float32, device='cuda')
+    stats = torch.zeros(4, dtype=torch.float64, device='cuda')
+    a.accumulate(ham, packed, sums, stats)
+    res.append((sums.cpu().numpy(), stats.cpu().numpy()))
+  os.environ.pop('CGSVMC_CONV_TC_GRAD', None)
+  np.testing.assert_array_equal(res[0][1], res[1][1])
+  for k in range(2):
+    scale = np.abs(res[1][0][k]).max()
+    assert np.abs(res[0][0][k] - res[1][0][k]).max() <= 1e-4 * scale
