@@ -274,6 +274,7 @@ class EnergyGradientWorkload:
     self.state.mc_steps(self.ansatz, 20 * self.n if name in ('C1', 'C2') else self.n)   # equilibrate a little
     self.graphed = engine.GraphedBatchStep(self.state, self.ansatz, self.ham, self.sums, self.sweep_steps)
     self.fused = self.ansatz.kind == 'rbm' and hp.num_fc_layers == 0
+    self.epochs = {}
     self.launches = 0
     self.allreduce_ms = []
     self.energies = []
@@ -287,6 +288,24 @@ class EnergyGradientWorkload:
     # build and bond-pair table after a parameter update); tile networks: fill,
     # local energy, copy, gradient, reduction, statistics, sampler, counter
     self.launches += (1 + (2 if rebuilt else 0)) if self.fused else 8
+
+  def prepare_epoch(self, n_batches):
+    """Pure RBM: the n_batches batch iterations of an epoch as ONE persistent
+    kernel (cgsvmc_batch_steps, engine.GraphedEpoch)."""
+    from cgs_vmc_b200 import engine
+    if not self.fused or n_batches < 2 or os.environ.get('CGSVMC_BENCH_PER_STEP') == '1':
+      return False
+    if n_batches not in self.epochs:
+      self.epochs[n_batches] = engine.GraphedEpoch(self.state, self.ansatz, self.ham, self.sums,
+                                                   self.sweep_steps, n_batches)
+    return True
+
+  def run_epoch(self, n_batches):
+    version = self.ansatz.params._version
+    rebuilt = getattr(self, '_seen_version', None) != version
+    self._seen_version = version
+    self.epochs[n_batches].replay()
+    self.launches += 1 + (2 if rebuilt else 0)
 
   def epoch_end(self):
     """training.py:618-622: apply_gradients (all-reduce over the walker shards,
@@ -365,12 +384,15 @@ class SupervisedWorkload:
     return 0.0
 
 
-def time_workload(w, steps, warmup, flush, world, dev, clock_index=None):
+def time_workload(w, steps, warmup, flush, world, dev, clock_index=None, force_per_step=False):
   """W warm-up steps (with one epoch end), then K steps in epochs of
   min(EPOCH_BATCHES, K) with the epoch end inside the timed region.  Returns
-  device times (max over ranks)."""
+  device times (max over ranks).  Pure RBM: the batch iterations of an epoch
+  are ONE launch (persistent kernel, cgsvmc_batch_steps); the event pairs then
+  bracket whole epochs and the L2 flush sits between launches."""
   import torch.distributed as dist
   epoch_len = max(1, min(EPOCH_BATCHES, steps))
+  per_epoch = not force_per_step and hasattr(w, 'prepare_epoch') and w.prepare_epoch(epoch_len)
   for _ in range(max(warmup, 3)):
     w.step()
     flush.zero_()
@@ -378,28 +400,46 @@ def time_workload(w, steps, warmup, flush, world, dev, clock_index=None):
   w.step()                                 # the rebuilding variant of the step, once
   flush.zero_()
   w.epoch_end()
+  if per_epoch:
+    for _ in range(2):                     # and of the epoch launch
+      w.run_epoch(epoch_len)
+      flush.zero_()
+      w.epoch_end()
   w.launches = 0
   w.allreduce_ms = []
   w.energies = []
   clock = ClockSampler(clock_index) if clock_index is not None else None
-  marks = [[ev(), ev()] for _ in range(steps)]
+  marks = []
   ends = []
   torch.cuda.synchronize()
   if world > 1:
     dist.barrier()
   torch.cuda.synchronize()
   wall0 = time.perf_counter()
-  for k in range(steps):
-    marks[k][0].record()
-    w.step()
-    marks[k][1].record()
-    flush.zero_()                          # L2 flush, outside the event pairs
-    if (k + 1) % epoch_len == 0 or k + 1 == steps:
-      e0, e1 = ev(), ev()
-      e0.record()
-      w.epoch_end()
-      e1.record()
-      ends.append((e0, e1))
+  k = 0
+  while k < steps:
+    n = min(epoch_len, steps - k)
+    if per_epoch and n == epoch_len:
+      m0, m1 = ev(), ev()
+      m0.record()
+      w.run_epoch(n)
+      m1.record()
+      marks.append((m0, m1))
+      flush.zero_()                        # L2 flush, outside the event pairs
+    else:
+      for _ in range(n):
+        m0, m1 = ev(), ev()
+        m0.record()
+        w.step()
+        m1.record()
+        marks.append((m0, m1))
+        flush.zero_()
+    k += n
+    e0, e1 = ev(), ev()
+    e0.record()
+    w.epoch_end()
+    e1.record()
+    ends.append((e0, e1))
   torch.cuda.synchronize()
   wall = time.perf_counter() - wall0
   if world > 1:
@@ -413,7 +453,7 @@ def time_workload(w, steps, warmup, flush, world, dev, clock_index=None):
              epoch_end_s=max_over_ranks(t_ends, dev, world),
              allreduce_s=max_over_ranks(t_ar, dev, world),
              n_epoch_ends=len(ends), epoch_len=epoch_len, wall_s=wall, clocks=clocks,
-             launches=w.launches, energies=list(w.energies))
+             launches=w.launches, energies=list(w.energies), per_epoch_launch=bool(per_epoch))
   return out
 
 
@@ -456,8 +496,9 @@ def roofline_for(w, t_step, n_act, pk):
         'hbm': {'achieved': bytes_alg / t_step / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                 'frac': bytes_alg / t_step / 1e9 / pk['hbm_gbs'], 'peak_source': pk['source']},
         'kernel_ms': t_step * 1e3, 'n_active_bonds_mean': n_act,
-        'kernel_ms_is': 'CUDA-event time of the whole captured step on the launching stream (fused kernel + '
-                        'reduction); ncu share of the fused kernel: profiles/ launch list'}
+        'kernel_ms_is': 'CUDA-event time of the captured launch on the launching stream divided by the batch '
+                        'iterations it runs (one persistent kernel per epoch for the headline; fused kernel + '
+                        'reduction per step otherwise); ncu share of the kernel: profiles/ launch list'}
   f_fwd = cfg['f_fwd']
   if w.name == 'C4':        # sweep + two amplitude passes (trainee, target) + forward/backward gradient
     flop = B * (steps * f_fwd + 2 * f_fwd + 3 * f_fwd)
@@ -582,6 +623,15 @@ def run_ours(args, rank, world, local_rank):
                          clock_index=local_rank if rank == 0 else None)
   main = result_for(w, timing, args.steps, world, pk)
   P = w.ansatz.num_params
+  # the same epochs with one launch per batch iteration (cgsvmc_batch_step), for comparison
+  per_step_launch = None
+  if timing['per_epoch_launch']:
+    tps = time_workload(w, args.steps, 3, flush, world, dev, force_per_step=True)
+    per_step_launch = {
+        'value': B * world * w.sweep_steps * args.steps / tps['total_s'], 'unit': 'walker-steps/s',
+        'ms_per_step': tps['total_s'] / args.steps * 1e3, 'step_ms': tps['steps_s'] / args.steps * 1e3,
+        'what': 'one captured graph (one cooperative kernel incl. the cross-CTA reduction) per batch '
+                'iteration, L2 flushed between iterations'}
 
   # per-phase device times of the split launches (how the fused time divides), outside the timed region
   phase = [[ev() for _ in range(3)] for _ in range(20)]
@@ -681,10 +731,18 @@ def run_ours(args, rank, world, local_rank):
       'config': config_dict(B),
       'config_detail': {
           'n_params': P,
-          'l2': 'flushed: %d MiB memset between steps, outside the per-step CUDA-event pairs' % (L2_FLUSH_BYTES >> 20),
-          'launch': 'one captured CUDA graph per step holding cgsvmc_batch_step = ONE cooperative kernel '
-                    '(estimators + sweep + deterministic cross-CTA reduction); the parameter tables are '
-                    'rebuilt in the first step after every Adam update',
+          'l2': ('flushed: %d MiB memset between launches (= epochs), outside the CUDA-event pairs; within an epoch '
+                 'the walkers and ratio tables are SM-resident by design (registers / shared memory)'
+                 if timing['per_epoch_launch'] else
+                 'flushed: %d MiB memset between steps, outside the per-step CUDA-event pairs') % (L2_FLUSH_BYTES >> 20),
+          'launch': ('one captured CUDA graph per EPOCH holding cgsvmc_batch_steps = ONE persistent cooperative '
+                     'kernel running all batch iterations of the epoch (estimators + sweep per iteration, walkers '
+                     'resident in registers, tables loaded once, one deterministic cross-CTA reduction); the '
+                     'parameter tables are rebuilt at the start of the epoch after every Adam update'
+                     if timing['per_epoch_launch'] else
+                     'one captured CUDA graph per step holding cgsvmc_batch_step = ONE cooperative kernel '
+                     '(estimators + sweep + deterministic cross-CTA reduction); the parameter tables are '
+                     'rebuilt in the first step after every Adam update'),
           'timed_region': 'whole epochs of %d steps: every step plus the epoch end (float64 all-reduce of '
                           '[2P+4], gradient + Adam kernel, mean energy to the host, reset)' % epoch_len,
           'parallelism': 'walkers sharded, params replicated' + (
@@ -696,6 +754,7 @@ def run_ours(args, rank, world, local_rank):
                     'split launch: rbm2::mc_kernel (36 Metropolis steps)': t_mc * 1e3},
       'kernel_rates': {'sampler_walker_steps_per_sec': B * SWEEP_STEPS / t_mc,
                        'accumulate_eloc_evals_per_sec': B / t_acc},
+      'per_step_launch': per_step_launch,
       'roofline': roofline,
       'e2e': {'value': walkers_total * SWEEP_STEPS * args.steps / e2e_s, 'unit': 'walker-steps/s',
               'eloc_evals_per_sec': walkers_total * args.steps / e2e_s,

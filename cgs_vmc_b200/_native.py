@@ -30,7 +30,7 @@ EXPORTS = [
     'cgsvmc_flip_enum', 'cgsvmc_local_energy', 'cgsvmc_weighted_grad_sum',
     'cgsvmc_energy_stats', 'cgsvmc_accumulate', 'cgsvmc_batch_step',
     'cgsvmc_propose_exchange', 'cgsvmc_accept_exchange', 'cgsvmc_local_energy_from_amps',
-    'cgsvmc_swo_weights', 'cgsvmc_adam_step', 'cgsvmc_batch_step_fed',
+    'cgsvmc_swo_weights', 'cgsvmc_adam_step', 'cgsvmc_batch_step_fed', 'cgsvmc_batch_steps',
 ]
 
 
@@ -86,6 +86,7 @@ def load():
   lib.cgsvmc_accept_exchange.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]
   lib.cgsvmc_local_energy_from_amps.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
   f32 = ctypes.c_float
+  lib.cgsvmc_batch_steps.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, vp, i32, u64, u64, u64, vp, vp, vp]
   lib.cgsvmc_batch_step_fed.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, u64, u64, u64, vp, vp, vp, vp]
   lib.cgsvmc_swo_weights.argtypes = [vp, vp, vp, vp, i64, f32, f32, vp, vp, vp]
   lib.cgsvmc_adam_step.argtypes = [vp, vp, vp, i64, vp, vp, vp, f32, f32, vp, f32, f32, f32, u64, vp, vp]
@@ -312,6 +313,30 @@ class Ansatz:
                                    int(seed), int(walker_id0), int(step0), _ptr(step_counter),
                                    _ptr(accept_count), _stream()))
 
+
+  def batch_steps(self, ham, packed, n_batches, sums, stats, n_steps, seed, walker_id0=0, step0=0,
+                  step_counter=None, accept_count=None, e_loc_out=None, log_amp_out=None):
+    """n_batches consecutive batch iterations (the inner loop of
+    run_optimization_epoch, training.py:614-617) in one call
+    (cgsvmc_batch_steps): one persistent kernel for the pure RBM.  e_loc_out /
+    log_amp_out: float32 [n_batches, B]."""
+    self._sync_params()
+    b = packed.shape[0]
+    _want(packed, torch.int64, (b, n_words(self.n_sites)), 'packed')
+    _want(sums, torch.float32, (2, self.num_params), 'sums')
+    _want(stats, torch.float64, (4,), 'stats')
+    if step_counter is not None:
+      _want(step_counter, torch.int64, (1,), 'step_counter')
+    if accept_count is not None:
+      _want(accept_count, torch.int64, (1,), 'accept_count')
+    if e_loc_out is not None:
+      _want(e_loc_out, torch.float32, (int(n_batches), b), 'e_loc_out')
+    if log_amp_out is not None:
+      _want(log_amp_out, torch.float32, (int(n_batches), b), 'log_amp_out')
+    check(load().cgsvmc_batch_steps(self._handle, ham._handle, _ptr(packed), b, int(n_batches),
+                                    _ptr(e_loc_out), _ptr(log_amp_out), _ptr(sums), _ptr(stats),
+                                    int(n_steps), int(seed), int(walker_id0), int(step0),
+                                    _ptr(step_counter), _ptr(accept_count), _stream()))
 
   def batch_step_fed(self, ham, configs_f32, packed_out, sums, stats, n_steps, seed, walker_id0,
                      step_counter, accept_count=None, e_loc_out=None, stats_out=None):

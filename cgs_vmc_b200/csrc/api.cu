@@ -441,7 +441,7 @@ static int batch_step_impl(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const fl
                            uint64_t* packed, int64_t B, float* e_loc_out, float* log_amp_out, float* sums,
                            double* stats, int32_t n_steps, uint64_t seed, uint64_t walker_id0, uint64_t step0,
                            uint64_t* step_counter, unsigned long long* accept_count, double* stats_out,
-                           void* stream) {
+                           void* stream, int32_t n_iters = 1) {
   if (int rc = check_ready(a)) return rc;
   if (h == nullptr) return invalid("batch_step: NULL hamiltonian");
   if (h->n_sites != a->desc.n_sites) return invalid("batch_step: hamiltonian and ansatz n_sites differ");
@@ -453,7 +453,7 @@ static int batch_step_impl(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const fl
     cgsvmc_ansatz* am = const_cast<cgsvmc_ansatz*>(a);
     Rbm2Sweep sw = {n_steps, seed, walker_id0, step_counter != nullptr ? 0 : step0, accept_count,
                     step_counter,   // the reduction advances the counter
-                    configs_f32, stats_out};
+                    configs_f32, stats_out, n_iters};
     am->step_counter_dev = step_counter;
     const int rc = rbm2_walker(am, h, packed, B, e_loc_out, log_amp_out, nullptr, nullptr, true, nullptr, 2,
                                sums, stats, st, &sw);
@@ -480,6 +480,28 @@ int cgsvmc_batch_step(const cgsvmc_ansatz* a, const cgsvmc_ham* h, uint64_t* pac
   NvtxRange range("cgsvmc:K2+K3+K4+K5 batch_step");
   return batch_step_impl(a, h, nullptr, packed, B, e_loc_out, log_amp_out, sums, stats, n_steps, seed,
                          walker_id0, step0, step_counter, accept_count, nullptr, stream);
+}
+
+int cgsvmc_batch_steps(const cgsvmc_ansatz* a, const cgsvmc_ham* h, uint64_t* packed, int64_t B, int32_t n_batches,
+                       float* e_loc_out, float* log_amp_out, float* sums, double* stats, int32_t n_steps,
+                       uint64_t seed, uint64_t walker_id0, uint64_t step0, uint64_t* step_counter,
+                       unsigned long long* accept_count, void* stream) {
+  NvtxRange range("cgsvmc:K2+K3+K4+K5 batch_steps");
+  if (n_batches < 0) return invalid("batch_steps: n_batches < 0");
+  if (n_batches == 0) return CGSVMC_OK;
+  if (int rc = check_ready(a)) return rc;
+  if (h != nullptr && rbm2_supported(a, h))
+    return batch_step_impl(a, h, nullptr, packed, B, e_loc_out, log_amp_out, sums, stats, n_steps, seed,
+                           walker_id0, step0, step_counter, accept_count, nullptr, stream, n_batches);
+  // tile networks: the launches of every iteration, one after another
+  for (int32_t i = 0; i < n_batches; ++i) {
+    if (int rc = batch_step_impl(a, h, nullptr, packed, B, e_loc_out != nullptr ? e_loc_out + (int64_t)i * B : nullptr,
+                                 log_amp_out != nullptr ? log_amp_out + (int64_t)i * B : nullptr, sums, stats,
+                                 n_steps, seed, walker_id0, step0 + (uint64_t)i * (uint64_t)n_steps, step_counter,
+                                 accept_count, nullptr, stream))
+      return rc;
+  }
+  return CGSVMC_OK;
 }
 
 int cgsvmc_batch_step_fed(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const float* configs_f32,

@@ -128,6 +128,7 @@ struct Rbm2Sweep {
   uint64_t* advance_counter;   // device step counter to advance by n_steps afterwards, or NULL
   const float* configs_f32;    // optional: the walkers as float32 [B][N] of +-1 (packed is then output only)
   double* stats_snapshot;      // optional: copy of the updated statistics (may be mapped host memory)
+  int n_iters;                 // > 1: that many consecutive batch iterations in one launch (e_loc / log_amp: [n_iters][B])
 };
 int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, int64_t B,
                 float* e_loc, float* log_amp, float* diag, float* off, bool do_grad,

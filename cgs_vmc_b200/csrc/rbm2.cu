@@ -316,6 +316,9 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
     A.step0 = sweep->step0; A.step0_dev = a->step_counter_dev; A.accept_count = sweep->accept_count;
   }
   if (mc) A.configs_f32 = sweep->configs_f32;
+  const int n_iters = mc && sweep->n_iters > 1 ? sweep->n_iters : 1;
+  A.n_iters = n_iters;
+  A.out_stride = n_iters > 1 ? B : 0;
   // The cross-CTA reduction runs inside the walker kernel when the device can
   // launch it cooperatively (all CTAs co-resident: grid <= number of SMs, one
   // CTA per SM) and the staging buffer is large enough for its scratch.
@@ -350,7 +353,7 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
     A.fuse_reduce = (fuse_env != nullptr && atoi(fuse_env) == 2) ? 2 : 1;
     A.sync = a->grid_sync;
     A.out = out; A.n_out = (int64_t)K * P; A.stats = stats;
-    A.counter = step_counter; A.advance = mc ? (uint64_t)sweep->n_steps : 0ull;
+    A.counter = step_counter; A.advance = mc ? (uint64_t)sweep->n_steps * (uint64_t)n_iters : 0ull;
     A.stats_snapshot = snapshot;
   }
   int rc;
@@ -363,8 +366,9 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
   if (do_grad && !fuse) {
     const int64_t n_out = (int64_t)K * P;
     const int blocks = (int)((n_out + 31) / 32);
-    reduce_kernel<<<blocks, 256, 0, st>>>(A.partials, pl.grid, 2 * P, n_out, out, A.stat_partials, B, stats,
-                                          step_counter, mc ? (uint64_t)sweep->n_steps : 0ull, snapshot);
+    reduce_kernel<<<blocks, 256, 0, st>>>(A.partials, pl.grid, 2 * P, n_out, out, A.stat_partials, B * n_iters, stats,
+                                          step_counter, mc ? (uint64_t)sweep->n_steps * (uint64_t)n_iters : 0ull,
+                                          snapshot);
     return cuda_fail(cudaGetLastError(), "rbm2 reduce launch");
   }
   return CGSVMC_OK;

@@ -737,6 +737,14 @@ struct WalkerArgs {
   // iteration of run_optimization_epoch (training.py:614-617) in one launch
   uint64_t* packed_rw;
   int n_steps;
+  // n_iters > 1: that many consecutive batch iterations in ONE launch (the loop
+  // of training.py:614-617 moved into the kernel): tables and bonds are loaded
+  // once, a CTA keeps adding to its slice of `partials`, the cross-CTA
+  // reduction runs once at the end.  Iteration i uses Philox steps
+  // step0 + i n_steps ..., exactly like i separate launches; e_loc / log_amp
+  // rows of iteration i start at i * out_stride.
+  int n_iters;
+  int64_t out_stride;
   uint64_t seed, walker0, step0;
   const uint64_t* step0_dev;
   unsigned long long* accept_count;
@@ -855,7 +863,8 @@ __device__ __forceinline__ void grid_reduce(const WalkerArgs& A, float* red) {
     e = warp_sum(e);
     e2 = warp_sum(e2);
     if (lane == 0) {
-      const double s0 = A.stats[0] + e, s1 = A.stats[1] + e2, s2 = A.stats[2] + (double)A.B;
+      const double s0 = A.stats[0] + e, s1 = A.stats[1] + e2,
+                   s2 = A.stats[2] + (double)A.B * (double)(A.n_iters > 1 ? A.n_iters : 1);
       A.stats[0] = s0; A.stats[1] = s1; A.stats[2] = s2;
       if (A.stats_snapshot != nullptr) {
         volatile double* snap = A.stats_snapshot;
@@ -963,8 +972,17 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
   float acc_a[2] = {0.f, 0.f};
   double sum_e = 0.0, sum_e2 = 0.0;   // lane 0 of the last warp only
   float* part = A.partials + (size_t)blockIdx.x * 2 * A.P;
+  // pass = one walker batch of one iteration; with one batch per CTA the swept
+  // walker of an iteration stays in registers for the next one, otherwise it is
+  // read back from packed_rw
+  const int n_iters = MC ? max(A.n_iters, 1) : 1;
+  const bool keep_s = A.n_batches <= (int64_t)gridDim.x;
   int batch_no = 0;
+  uint64_t s[NW];
+#pragma unroll
+  for (int w = 0; w < NW; ++w) s[w] = 0ull;
 
+  for (int iter = 0; iter < n_iters; ++iter)
   for (int64_t batch = blockIdx.x; batch < A.n_batches; batch += gridDim.x, ++batch_no) {
     const int64_t b0 = batch * A.wpc;
     const int n_valid = (int)min((int64_t)A.wpc, A.B - b0);
@@ -972,20 +990,24 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
     const bool valid = slot < n_valid;
     const int64_t b = b0 + slot;
     const int64_t bb = valid ? b : b0 + n_valid - 1;
-    uint64_t s[NW];
+    const int64_t ob = (int64_t)iter * A.out_stride + b;      // row of this pass in e_loc / log_amp / diag / off
     float p[KJ], m[KJ];
     if (warp_on) {
       if (batch_no == 0) {
 #pragma unroll
         for (int w = 0; w < NW; ++w) s[w] = s_first[w];
-      } else {
+      } else if (iter == 0) {
         load_walker<NW, LPW>(A, im, bb, sub, grp, s);
+      } else if (!keep_s) {
+        // written by this lane group in the previous iteration (behind a CTA barrier)
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s[w] = w < im.words ? __ldcg(A.packed_rw + bb * im.words + w) : 0ull;
       }
       const bool want_z = A.log_amp != nullptr;
       float z = init_state<NW, LPW, KJV, WS>(t, im, s, sub, p, m, want_z);
       if (want_z) {
         z = group_sum<LPW>(z) + ld1<WS>(t.a0);
-        if (valid && sub == 0) A.log_amp[b] = z;
+        if (valid && sub == 0) A.log_amp[ob] = z;
       }
       RBM2_MARK(1, 2);
     }
@@ -1048,9 +1070,9 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
         e_val = __fadd_rn(diag, off);
         RBM2_MARK(1, 3);
         if (valid && sub == 0) {
-          if (A.e_loc) A.e_loc[b] = e_val;
-          if (A.diag) A.diag[b] = diag;
-          if (A.off) A.off[b] = off;
+          if (A.e_loc) A.e_loc[ob] = e_val;
+          if (A.diag) A.diag[ob] = diag;
+          if (A.off) A.off[ob] = off;
         }
       }
       if (A.do_grad && valid) {
@@ -1093,11 +1115,12 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
     }
     if (MC && warp_on) {
       n_acc += mc_sweep<NW, LPW, KJV, WS>(t, im, picker, lut, s, p, m, sub, valid, A.n_steps, A.seed,
-                                          A.walker0 + (uint64_t)bb, mc_step0);
+                                          A.walker0 + (uint64_t)bb, mc_step0 + (uint64_t)iter * (uint64_t)A.n_steps);
       if (valid && sub == 0) {
 #pragma unroll
         for (int w = 0; w < NW; ++w) if (w < im.words) A.packed_rw[b * im.words + w] = s[w];
       }
+      __syncwarp();        // a later iteration of this lane group may read the words back
       RBM2_MARK(1, 5);
     }
     if (A.do_grad) {

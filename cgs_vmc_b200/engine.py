@@ -103,6 +103,21 @@ class EnergyGradientSums:
     state.proposed += int(n_steps) * state.batch_size
     return e_row
 
+  def batch_steps(self, ham, state, n_steps, n_batches, on_device_counter=False, e_loc_out=None):
+    """n_batches x batch_step() in one library call (cgsvmc_batch_steps): the
+    inner loop of run_optimization_epoch (training.py:614-617) as ONE
+    persistent kernel for the pure RBM.  e_loc_out: optional float32
+    [n_batches, B]."""
+    counter = dict(step_counter=state.step_dev) if on_device_counter else dict(step0=state.step)
+    self.ansatz.batch_steps(ham, state.packed, n_batches, self.sums, self.stats, n_steps, state.seed,
+                            state.walker_id0, accept_count=state.accept_count, e_loc_out=e_loc_out,
+                            **counter)
+    if on_device_counter:      # capturable: the caller keeps state.step in sync
+      return
+    self.n_batches += int(n_batches)
+    state.step += int(n_steps) * int(n_batches)
+    state.proposed += int(n_steps) * int(n_batches) * state.batch_size
+
   def mean_energy(self):
     s = self.stats
     return s[0] / s[2]
@@ -162,6 +177,30 @@ class _CapturedStep:
     self.sums.n_batches += 1
     self.state.step += self.n_steps
     self.state.proposed += self.n_steps * self.state.batch_size
+
+
+class GraphedEpoch(_CapturedStep):
+  """The whole inner loop of run_optimization_epoch (training.py:614-617),
+  `n_batches` batch iterations, captured as one CUDA graph holding
+  cgsvmc_batch_steps: for the pure RBM one persistent cooperative kernel per
+  epoch (tables loaded once, walkers resident in registers across the
+  iterations, one cross-CTA reduction)."""
+
+  def __init__(self, state, ansatz, ham, sums, n_steps, n_batches):
+    self.n_batches = int(n_batches)
+    self._prepare(state, ansatz, ham, sums, n_steps, (0,))
+
+  def _body(self, variant):
+    self.sums.batch_steps(self.ham, self.state, self.n_steps, self.n_batches, on_device_counter=True)
+
+  def replay(self):
+    self._replay(0)
+    # _replay booked one iteration
+    extra = self.n_batches - 1
+    self.sums.n_batches += extra
+    self.state.step += extra * self.n_steps
+    self.state.proposed += extra * self.n_steps * self.state.batch_size
+    self._expected_step = self.state.step
 
 
 class GraphedBatchStep(_CapturedStep):

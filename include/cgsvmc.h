@@ -262,6 +262,27 @@ int cgsvmc_batch_step(const cgsvmc_ansatz* ansatz, const cgsvmc_ham* ham,
                       uint64_t* step_counter, unsigned long long* accept_count,
                       void* stream);
 
+/* n_batches consecutive batch iterations -- the whole inner loop of
+ * EnergyGradientOptimizer.run_optimization_epoch (training.py:614-617:
+ * `for _ in range(num_batches): accumulate_gradients; mc_step x sweeps`) -- in
+ * one call: the same results as n_batches cgsvmc_batch_step calls with step0
+ * advanced by n_steps each time (configurations and local energies bit for
+ * bit; sums and statistics to float32 / float64 rounding, the partial sums are
+ * reduced once instead of n_batches times).  For the pure RBM this is ONE
+ * persistent kernel: ratio tables and bonds are loaded once, every walker
+ * stays with its lane group across the iterations, the CTAs keep adding to
+ * their partial sums and the cross-CTA reduction runs once.  e_loc_out /
+ * log_amp_out (optional) are float32 [n_batches, n_walkers]; stats gains
+ * { sum E, sum E^2, n_batches * B, 0 }; step_counter (optional, device) is
+ * advanced by n_batches * n_steps. */
+int cgsvmc_batch_steps(const cgsvmc_ansatz* ansatz, const cgsvmc_ham* ham,
+                       uint64_t* packed_inout, int64_t n_walkers, int32_t n_batches,
+                       float* e_loc_out, float* log_amp_out, float* sums,
+                       double* stats, int32_t n_steps, uint64_t seed,
+                       uint64_t walker_id0, uint64_t step0,
+                       uint64_t* step_counter, unsigned long long* accept_count,
+                       void* stream);
+
 /* cgsvmc_batch_step for a caller that holds the walkers in the reference's own
  * layout (the float32 [B, N] variable of graph_builders.py:92-125) and reads
  * the energy statistics back every batch (training.py:619-620): configs_f32

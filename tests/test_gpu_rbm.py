@@ -578,6 +578,67 @@ def test_batch_step_equals_accumulate_then_sweep(native, n_side, hidden, batch, 
   assert torch.equal(sums1.log_amp, sums2.log_amp)
 
 
+@pytest.mark.parametrize('n_side,hidden,batch,n_batches', [(6, 144, 8192, 5), (6, 144, 777, 3), (4, 24, 130, 4),
+                                                           (16, 256, 6000, 3), (10, 64, 30000, 2)])
+def test_batch_steps_equals_repeated_batch_step(native, n_side, hidden, batch, n_batches):
+  """cgsvmc_batch_steps (the inner loop of run_optimization_epoch,
+  training.py:614-617, as one persistent kernel) against n_batches calls of
+  cgsvmc_batch_step: configurations, acceptance counts and the local energies
+  of every iteration bit for bit; gradient sums to float32 summation order
+  (the partial sums are reduced once instead of n_batches times), energy
+  statistics to float64 rounding.  Covers one walker batch per CTA (walkers
+  stay in registers) and several (read back from the packed array)."""
+  from cgs_vmc_b200 import engine
+  n = n_side * n_side
+  spec = oansatz.AnsatzSpec('rbm', n, num_layers=0, layer_size=hidden, size_x=n_side, size_y=n_side)
+  a, _, _ = _setup(spec, seed=11, batch=1)
+  ij, jx, jz = lattices.heisenberg_couplings(lattices.square_nn_bonds(n_side))
+  ham = native.Hamiltonian(ij, jx, jz, n)
+  s1 = engine.WalkerState(batch, n, seed=9, walker_id0=3)
+  s2 = engine.WalkerState(batch, n, seed=9, walker_id0=3)
+  sums1 = engine.EnergyGradientSums(a, batch)
+  sums2 = engine.EnergyGradientSums(a, batch)
+  e_all = torch.empty(n_batches, batch, dtype=torch.float32, device='cuda')
+  for rep in range(2):          # the second call continues from the first (step offsets, accumulation)
+    sums1.batch_steps(ham, s1, n, n_batches, e_loc_out=e_all)
+    for i in range(n_batches):
+      e2 = sums2.batch_step(ham, s2, n).clone()
+      assert torch.equal(e_all[i], e2), (rep, i)
+    assert torch.equal(s1.packed, s2.packed)
+  assert torch.equal(s1.accept_count, s2.accept_count) and s1.step == s2.step
+  assert sums1.n_batches == sums2.n_batches
+  _close_sums(sums1.sums, sums2.sums)
+  np.testing.assert_allclose(sums1.stats.cpu().numpy(), sums2.stats.cpu().numpy(), rtol=1e-12)
+  assert float(sums1.stats[2]) == 2 * n_batches * batch
+
+
+def test_graphed_epoch_equals_graphed_batch_steps(native):
+  """engine.GraphedEpoch (one captured persistent kernel per epoch) against
+  engine.GraphedBatchStep replayed per batch, across a parameter update."""
+  from cgs_vmc_b200 import engine
+  spec = _c2_spec()
+  a, _, _ = _setup(spec, seed=3, batch=1)
+  ij, jx, jz = lattices.heisenberg_couplings(lattices.square_nn_bonds(6))
+  ham = native.Hamiltonian(ij, jx, jz, 36)
+  B, nb = 8192, 6
+  s1 = engine.WalkerState(B, 36, seed=5)
+  s2 = engine.WalkerState(B, 36, seed=5)
+  sums1, sums2 = engine.EnergyGradientSums(a, B), engine.EnergyGradientSums(a, B)
+  g1 = engine.GraphedEpoch(s1, a, ham, sums1, 36, nb)
+  g2 = engine.GraphedBatchStep(s2, a, ham, sums2, 36)
+  for epoch in range(3):
+    if epoch == 2:
+      a.params.mul_(0.97)
+    g1.replay()
+    for _ in range(nb):
+      g2.replay()
+    assert torch.equal(s1.packed, s2.packed)
+    assert s1.step == s2.step and int(s1.step_dev.item()) == s1.step
+    _close_sums(sums1.sums, sums2.sums)
+    np.testing.assert_allclose(sums1.stats.cpu().numpy(), sums2.stats.cpu().numpy(), rtol=1e-12)
+  assert sums1.n_batches == sums2.n_batches == 3 * nb
+
+
 def test_pair_tables_of_two_hamiltonians_do_not_evict_each_other(native):
   """The walker kernel keeps one bond-pair table per (ansatz, Hamiltonian);
   a captured graph for one Hamiltonian must stay correct when the same
