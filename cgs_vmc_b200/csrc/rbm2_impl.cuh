@@ -991,6 +991,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
     const int64_t b = b0 + slot;
     const int64_t bb = valid ? b : b0 + n_valid - 1;
     const int64_t ob = (int64_t)iter * A.out_stride + b;      // row of this pass in e_loc / log_amp / diag / off
+    RBM2_MARK(1, 10);
     float p[KJ], m[KJ];
     if (warp_on) {
       if (batch_no == 0) {
@@ -1144,68 +1145,86 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
         sum_e += warp_sum(e1);
         sum_e2 += warp_sum(e2);
       }
+      // A grab = TG tiles x all walkers of the batch, the walkers split over the
+      // 32 / TG lane groups of the warp (group wg takes walkers wg, wg + TQ, ...)
+      // and the partial tiles reduce-scattered with 24 shuffles: lane (tl, wg)
+      // ends up with row wg of tile tl for both weight columns.  Small grabs
+      // keep the tail after the sweep short (a 32-tile grab runs ~4.5 us; the
+      // warps without walkers work through the grabs during the sweep and the
+      // last few used to keep 3 of 16 warps busy for ~8 us).
+      constexpr int TG = 8, TQ = 32 / TG;
+      const int tl = lane & (TG - 1), wg = lane / TG;
       for (;;) {
         int tile_base = 0;
-        if (lane == 0) tile_base = atomicAdd(tile_next_s, 32);
+        if (lane == 0) tile_base = atomicAdd(tile_next_s, TG);
         tile_base = __shfl_sync(CGSVMC_FULL_MASK, tile_base, 0);
         if (tile_base >= n_tiles) break;
-        const int tile = tile_base + lane;
-        if (tile < n_tiles) {
-          const int rt = tile / CT, ct = tile - rt * CT;
-          // the accumulators live only here: a CTA's partial sums are kept in
-          // its (L2-resident) slice of `partials` between batches
-          float acc[2][4][4];
+        const bool tile_ok = tile_base + tl < n_tiles;
+        const int tile = min(tile_base + tl, n_tiles - 1);
+        const int rt = tile / CT, ct = tile - rt * CT;
+        const int i_own = 4 * rt + wg;                       // the row this lane stores: i < N: W[i][j]; i == N: c[j]
+        // When the CTA's slice already holds sums (later passes of a launch)
+        // the old values are requested before the accumulation loop, so the
+        // L2 round trip hides behind it.
+        float old[2][4];
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            old[k][c] = 0.f;
+            if (batch_no != 0)
+              old[k][c] = __ldcg(part + (size_t)k * A.P + im.N + 1 + (size_t)min(i_own, im.N) * im.H +
+                                 min(4 * ct + c, im.H - 1));
+          }
+        float acc[2][4][4];
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[k][r][c] = 0.f;
+#pragma unroll 2
+        for (int sb = wg; sb < n_valid; sb += TQ) {
+          const float4 T = *reinterpret_cast<const float4*>(T_s + sb * HP + 4 * ct);
+          const float4 s0 = *reinterpret_cast<const float4*>(ws_s + (size_t)sb * 2 * NP4 + 4 * rt);
+          const float4 s1 = *reinterpret_cast<const float4*>(ws_s + (size_t)sb * 2 * NP4 + NP4 + 4 * rt);
+          const float tv[4] = {T.x, T.y, T.z, T.w};
+          const float a0v[4] = {s0.x, s0.y, s0.z, s0.w};
+          const float a1v[4] = {s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              acc[0][r][c] = fmaf(a0v[r], tv[c], acc[0][r][c]);
+              acc[1][r][c] = fmaf(a1v[r], tv[c], acc[1][r][c]);
+            }
+        }
+        // reduce-scatter over the walker groups (lane bits 4 and 3): fixed order, deterministic
+        const bool up1 = (wg & 2) != 0, up0 = (wg & 1) != 0;
+        float mine[2][4];
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float h[2];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const float send = up1 ? acc[k][rr][c] : acc[k][rr + 2][c];
+              const float keep = up1 ? acc[k][rr + 2][c] : acc[k][rr][c];
+              h[rr] = keep + __shfl_xor_sync(CGSVMC_FULL_MASK, send, 2 * TG);
+            }
+            const float send = up0 ? h[0] : h[1];
+            const float keep = up0 ? h[1] : h[0];
+            mine[k][c] = keep + __shfl_xor_sync(CGSVMC_FULL_MASK, send, TG);
+          }
+        if (tile_ok && i_own <= im.N) {
 #pragma unroll
           for (int k = 0; k < 2; ++k)
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-              for (int c = 0; c < 4; ++c) acc[k][r][c] = 0.f;
-#pragma unroll 4
-          for (int sb = 0; sb < n_valid; ++sb) {
-            const float4 T = *reinterpret_cast<const float4*>(T_s + sb * HP + 4 * ct);
-            const float4 s0 = *reinterpret_cast<const float4*>(ws_s + (size_t)sb * 2 * NP4 + 4 * rt);
-            const float4 s1 = *reinterpret_cast<const float4*>(ws_s + (size_t)sb * 2 * NP4 + NP4 + 4 * rt);
-            const float tv[4] = {T.x, T.y, T.z, T.w};
-            const float a0v[4] = {s0.x, s0.y, s0.z, s0.w};
-            const float a1v[4] = {s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                acc[0][r][c] = fmaf(a0v[r], tv[c], acc[0][r][c]);
-                acc[1][r][c] = fmaf(a1v[r], tv[c], acc[1][r][c]);
-              }
-          }
-          // row i < N: W[i][j]; row N: c[j].  When the CTA's slice already holds
-          // sums (later batches of a launch) all of the old values are requested
-          // before the first store -- a load-add-store chain per element would
-          // pay the memory latency 32 times.
-          if (batch_no != 0) {
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-#pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                const int i = min(4 * rt + r, im.N);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  const int j = min(4 * ct + c, im.H - 1);
-                  acc[k][r][c] += __ldcg(part + (size_t)k * A.P + im.N + 1 + (size_t)i * im.H + j);
-                }
-              }
-          }
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              const int i = 4 * rt + r;
-              if (i > im.N) continue;
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const int j = 4 * ct + c;
-                if (j >= im.H) continue;
-                part[(size_t)k * A.P + im.N + 1 + (size_t)i * im.H + j] = acc[k][r][c];
-              }
+            for (int c = 0; c < 4; ++c) {
+              const int j = 4 * ct + c;
+              if (j >= im.H) continue;
+              part[(size_t)k * A.P + im.N + 1 + (size_t)i_own * im.H + j] = mine[k][c] + old[k][c];
             }
         }
       }

@@ -30,6 +30,7 @@ MC_MARKS = ['entry', 'tables + select table', 'state built (warp 0)', 'sweep don
 def main():
   B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
   fused = '--split' not in sys.argv
+  epoch = int(sys.argv[sys.argv.index('--epoch') + 1]) if '--epoch' in sys.argv else 0
   N, H = 36, 144
   lib = _native.load()
   ansatz = _native.Ansatz('rbm', N, num_layers=0, layer_size=H)
@@ -42,7 +43,10 @@ def main():
   sums = engine.EnergyGradientSums(ansatz, B)
   state.mc_steps(ansatz, 20 * N)
   flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
-  if fused:
+  if epoch:
+    g = engine.GraphedEpoch(state, ansatz, ham, sums, N, epoch)     # cgsvmc_batch_steps: one persistent kernel
+    run = g.replay
+  elif fused:
     g = engine.GraphedBatchStep(state, ansatz, ham, sums, N)
     run = g.replay
   else:
@@ -59,6 +63,22 @@ def main():
   sm_hz = 1.965e9
   out = {'walkers': B, 'mode': 'fused batch step (graph)' if fused else 'accumulate + mc_steps'}
   n_cta = min(148, (B + 55) // 56)
+  if epoch:
+    # marks of the LAST iteration of the launch: 10 = iteration start, then 2 .. 7; 8 / 9 after the loop
+    m = marks[1, :n_cta].astype(np.int64)
+    order = [(10, 'iteration start'), (2, 'state built (warp 0)'), (3, 'E_loc done (warp 0)'),
+             (4, 'gradient inputs staged (warp 0)'), (5, 'sweep done (warp 0)'), (6, 'barrier passed'),
+             (7, 'gradient tiles done (thread 0)'), (8, 'loop left'), (9, 'exit (after the grid reduction)')]
+    phases = {}
+    for (k0, n0), (k1, n1) in zip(order[:-1], order[1:]):
+      d = (m[:, k1, 1] - m[:, k0, 1]) / sm_hz * 1e6
+      phases['%s -> %s' % (n0, n1)] = {'median_us': float(np.median(d)), 'max_us': float(d.max())}
+    span = float((m[:, 9, 0].max() - m[:, 0, 0].min()) * 1e-3)
+    out = {'walkers': B, 'mode': 'cgsvmc_batch_steps, %d iterations in one launch (graph)' % epoch,
+           'last_iteration_phases': phases, 'first_entry_to_last_exit_us (globaltimer)': span,
+           'us_per_iteration': span / epoch}
+    print(json.dumps(out, indent=1))
+    return
   for kern, names in ((1, WALKER_MARKS), (0, MC_MARKS)):
     m = marks[kern, :n_cta].astype(np.int64)
     if m[:, 0, 0].max() == 0 or (fused and kern == 0):
