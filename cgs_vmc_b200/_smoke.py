@@ -33,7 +33,8 @@ def run():
   e_fused = sums.batch_step(ham, state, 36).clone()
   torch.cuda.synchronize()
   assert torch.equal(e_fused, e), 'fused batch step: local energies differ from cgsvmc_local_energy'
-  assert torch.allclose(sums.sums, s, rtol=1e-5, atol=1e-5), 'fused batch step: gradient sums differ'
+  # (the fused kernel forms the sums on the tensor cores, cgsvmc_weighted_grad_sum in FP32 register tiles)
+  assert float((sums.sums - s).abs().max()) <= 2e-6 * float(s.abs().max()), 'fused batch step: gradient sums differ'
 
   cfg = bits.unpack(packed.cpu().numpy().view(np.uint64), 36)
   assert np.all(cfg.sum(axis=1) == 0), 'Sz not conserved'

@@ -153,7 +153,7 @@ size_t walker_smem_bytes(const Image& im, int slots, bool ws, bool do_eloc, int 
   const int NP4 = round_up(im.N + 1, 4);
   size_t b = ws ? (size_t)(im.total - (pt ? im.off_f : 0)) * 4 : 0;
   if (pt) b += (size_t)2 * n_bonds * im.HP * 4;
-  b += 16;
+  b += 32;
   if (do_eloc) b += (size_t)n_bonds * 16 + (size_t)slots * round_up(n_bonds, 8) * 4;
   // T_s (tanh staging; with the pair table at least N rows: the parked 2W table) and ws_s
   b += (size_t)std::max(do_grad ? slots * im.HP : 0, pt ? im.N * im.HP : 0) * 4;
@@ -314,6 +314,20 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
     A.packed_rw = const_cast<uint64_t*>(packed);
     A.n_steps = sweep->n_steps; A.seed = sweep->seed; A.walker0 = sweep->walker0;
     A.step0 = sweep->step0; A.step0_dev = a->step_counter_dev; A.accept_count = sweep->accept_count;
+  }
+  // gradient sums on the tensor cores: pair-table kernels with weights (1, E_loc),
+  // sigma + three weight pieces within M = 128 rows (N <= 39), a spare column for
+  // the constant 1 (H < HP), operand planes no larger than the float staging
+  // buffers they replace.  CGSVMC_RBM2_TC_GRAD=0 keeps the FP32 register tiles.
+  {
+    const char* e = getenv("CGSVMC_RBM2_TC_GRAD");
+    const bool off = e != nullptr && atoi(e) == 0;
+    const int np4 = round_up(pl.im.N + 1, 4), np8 = round_up(pl.im.N + 1, 8);
+    A.tc_grad = (!off && pl.pt && do_grad && weights == nullptr && np8 == np4 && 3 * np8 <= 128 &&
+                 pl.im.H < pl.im.HP && 3 * pl.im.HP <= 512 && (slots == 64 || slots == 128)) ? 1 : 0;
+    if (A.tc_grad && e != nullptr && atoi(e) == 2) A.tc_grad = 2;      // development: E_loc centred per segment
+    const char* sg = getenv("CGSVMC_RBM2_TC_SEGMENT");
+    A.tc_segment = sg != nullptr && atoi(sg) > 0 ? atoi(sg) : 8;
   }
   if (mc) A.configs_f32 = sweep->configs_f32;
   const int n_iters = mc && sweep->n_iters > 1 ? sweep->n_iters : 1;

@@ -27,6 +27,9 @@
 // phases of one walker (128 contiguous bytes) each -- conflict-free.
 // One persistent CTA per SM (1024 threads when the state fits 64 registers).
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "internal.h"
 #include "rbm2.h"
@@ -180,6 +183,8 @@ __device__ __forceinline__ uint8_t lut_entry(int e) {
 __device__ __forceinline__ void build_lut(uint8_t* lut) {
   for (int e = threadIdx.x; e < 2048; e += blockDim.x) lut[e] = lut_entry(e);
 }
+
+constexpr float kTcgPrescale = 9.5367431640625e-07f;   // 2^-20: E_loc prescale of the tensor-core gradient operands
 
 struct Tables {
   const float* w2;    // [N][HP]  2 W
@@ -717,6 +722,90 @@ mc_kernel(Image im, const float* __restrict__ img_g, uint64_t* __restrict__ pack
 // do_eloc / do_grad select the phases; with both, the gradient weights are
 // (1, E_loc) -- one session.run(accumulate_gradients).
 // ---------------------------------------------------------------------------
+// Drain of the tensor-core gradient accumulators (walker_kernel, A.tc_grad)
+// into the CTA's slice of `partials`, through a shared-memory staging buffer
+// [128 + 8 NC rows][17].  P0 / P1 / P2 at TMEM columns 0 / NCOL / 2 NCOL; rows
+// [0, NPC): sigma (k = 0), [NPC, 2 NPC) / [2 NPC, 3 NPC): pieces 1 / 2 of the
+// weights, P2 rows [0, NPC): piece 3.  The first drain of a launch stores, later
+// ones add with fire-and-forget reductions (one writer per address: the order
+// of the additions is the program order, the sums stay deterministic).
+// Deliberately compact and out of line: it runs a few times per launch and
+// would otherwise be paid in instruction fetches.
+template <int THREADS, int NCOL>
+__device__ __noinline__ void tcg_drain(uint32_t tmem, float* stg, float* part, int64_t P, int N, int H, int NC,
+                                       float e_center, bool add) {
+  constexpr int LD = 20;                     // staging row stride (floats): 16-byte aligned rows
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int NPC = 8 * NC;
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncthreads();
+#pragma unroll 1
+  for (int c0 = 0; c0 < NCOL; c0 += 16) {
+    if (warp < 4) {
+      const int mrow = 32 * warp + lane;
+      const uint32_t tbase = tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0;
+      uint32_t q0[16], q1[16], q2[16];
+#define RBM2_TMEM_LD16(ADDR, R)                                                                                  \
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
+                   : "=r"(R[0]), "=r"(R[1]), "=r"(R[2]), "=r"(R[3]), "=r"(R[4]), "=r"(R[5]), "=r"(R[6]), "=r"(R[7]), \
+                     "=r"(R[8]), "=r"(R[9]), "=r"(R[10]), "=r"(R[11]), "=r"(R[12]), "=r"(R[13]), "=r"(R[14]), "=r"(R[15]) \
+                   : "r"(ADDR) : "memory")
+      RBM2_TMEM_LD16(tbase, q0);
+      RBM2_TMEM_LD16(tbase + (uint32_t)NCOL, q1);
+      if (warp < 2) RBM2_TMEM_LD16(tbase + (uint32_t)(2 * NCOL), q2);      // piece 3: rows [0, NPC) only
+#undef RBM2_TMEM_LD16
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) {
+        float4 v;
+        v.x = fmaf(__uint_as_float(q1[c]), 1.f / 2048.f, __uint_as_float(q0[c]));
+        v.y = fmaf(__uint_as_float(q1[c + 1]), 1.f / 2048.f, __uint_as_float(q0[c + 1]));
+        v.z = fmaf(__uint_as_float(q1[c + 2]), 1.f / 2048.f, __uint_as_float(q0[c + 2]));
+        v.w = fmaf(__uint_as_float(q1[c + 3]), 1.f / 2048.f, __uint_as_float(q0[c + 3]));
+        *reinterpret_cast<float4*>(stg + mrow * LD + c) = v;
+        if (warp < 2 && mrow < NPC)
+          *reinterpret_cast<float4*>(stg + (128 + mrow) * LD + c) =
+              make_float4(__uint_as_float(q2[c]), __uint_as_float(q2[c + 1]), __uint_as_float(q2[c + 2]),
+                          __uint_as_float(q2[c + 3]));
+      }
+    }
+    __syncthreads();
+    // one (weight column k, row i, 4 columns) group per thread
+#pragma unroll 1
+    for (int e = threadIdx.x; e < 2 * NPC * 4; e += THREADS) {
+      const int k = e >= NPC * 4 ? 1 : 0, r = e - k * NPC * 4;
+      const int i = r >> 2, c = (r & 3) * 4;
+      if (i > N) continue;
+      const float4 s0 = *reinterpret_cast<const float4*>(stg + i * LD + c);
+      float v[4] = {s0.x, s0.y, s0.z, s0.w};
+      if (k == 1) {
+        const float4 p1 = *reinterpret_cast<const float4*>(stg + (NPC + i) * LD + c);
+        const float4 p2 = *reinterpret_cast<const float4*>(stg + (2 * NPC + i) * LD + c);
+        const float4 p3 = *reinterpret_cast<const float4*>(stg + (128 + i) * LD + c);
+        const float a1[4] = {p1.x, p1.y, p1.z, p1.w}, a2[4] = {p2.x, p2.y, p2.z, p2.w},
+                    a3[4] = {p3.x, p3.y, p3.z, p3.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          v[u] = fmaf(e_center, v[u],
+                      fmaf(fmaf(a3[u], 1.f / 2048.f, a2[u]), 1.f / 2048.f, a1[u]) * (1.f / kTcgPrescale));
+      }
+      float* row_w = part + (size_t)k * P + (size_t)(N + 1) + (size_t)i * H;    // W[i][.] (i < N), c[.] (i == N)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = c0 + c + u;
+        if (j > H) continue;
+        float* dst = j < H ? row_w + j : part + (size_t)k * P + i;              // column H: a_i (i < N), a0 (i == N)
+        if (add) atomicAdd(dst, v[u]);
+        else *dst = v[u];
+      }
+    }
+    __syncthreads();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
 struct WalkerArgs {
   const uint64_t* packed;
   int64_t B;
@@ -751,6 +840,11 @@ struct WalkerArgs {
   // bond-pair table (PT kernels): [2 n_bonds][HP], row 2 k + o = F[d] * G[u]
   // for bond k with d = (o ? j_k : i_k) raised and the other end lowered
   const float* pair_table;
+  // PT kernels: gradient sums on the tensor cores (tcgen05, accumulators in
+  // TMEM for the whole launch) instead of the FP32 register tiles; planned by
+  // the host when the shapes fit (N <= 39, H <= 159: the C2 class)
+  int tc_grad;
+  int tc_segment;   // passes accumulated in TMEM between two drains (truncating fp32 accumulation)
   // walkers given as the reference's float32 [B][N] of +-1 instead of packed
   // words (the packed configurations are still written to packed_rw)
   const float* configs_f32;
@@ -910,7 +1004,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
   const int img_skip = PT ? im.off_f : 0;          // floats of the image left in global memory
   float* img_s = smem - img_skip;                  // so that img_s + off_x addresses table x
   char* cur = reinterpret_cast<char*>(smem + (WS ? im.total - img_skip : 0));
-  uint64_t* bar = reinterpret_cast<uint64_t*>(cur); cur += 16;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(cur); cur += 32;   // table mbarrier, tile counter, MMA mbarrier, TMEM address
   int4* bond_s = reinterpret_cast<int4*>(cur); cur += (size_t)(A.do_eloc ? A.n_bonds : 0) * 16;
   const int list_ld = (A.n_bonds + 7) / 8 * 8;
   uint32_t* list_s = reinterpret_cast<uint32_t*>(cur); cur += (size_t)(A.do_eloc ? SLOTS * list_ld : 0) * 4;
@@ -927,6 +1021,38 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
   // one row per amplitude ratio instead of two and no multiply per hidden unit
   const float* pair_s = PT ? reinterpret_cast<const float*>(cur) : (!WS ? A.pair_table : nullptr);
   int* tile_next_s = reinterpret_cast<int*>(bar) + 2;                // behind the 8-byte mbarrier
+  uint64_t* mma_bar = bar + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar) + 3;
+  // ---- gradient sums on the tensor cores (PT kernels, A.tc_grad) ----
+  // S_k[i][j] = sum_b (w_kb sigma_bi) tanh(theta_bj) is a GEMM over the walkers
+  // of the CTA: A[m][b] (MN-major, K = walker slot) x B[b][j] (MN-major).
+  //   B planes (in T_s): tanh theta as two fp16 planes t = t1 + t2 / S, [split][8-column chunk][slot][8];
+  //       column H is the constant 1 (the a / a0 gradients ride along).
+  //   A planes (in ws_s), fp16:
+  //       chunks [0, NC): sigma_i (+-1; row N: 1 = the c / a0 gradients), w_0 = 1;
+  //       chunks [NC, 4 NC): the three fp16 pieces of x = w_1 sigma_i 2^-20 (w_1 = E_loc;
+  //       x = x1 + x2 / S + x3 / S^2; the prescale covers |E_loc| < 6.8e10).
+  //   P0 += A[chunks 0 ..] x t1, P1 += A[chunks 0 ..] x t2 (M = 128: sigma and the pieces 1, 2),
+  //   P2 += A[chunks 3 NC ..] x t1 (piece 3);   S_0 = P0 + P1 / S on the sigma rows,
+  //   S_1 = 2^20 (rows of piece 1 + rows of piece 2 / S + rows of piece 3 / S^2).
+  //   12 MMAs per batch iteration; the accumulators
+  //   stay in TMEM for the whole launch (all iterations of an epoch) and are
+  //   drained once.
+  constexpr int NCOL = HP;                       // B columns: H real ones + the constant 1 (needs H < HP)
+  constexpr int NB = NCOL / 8;                   // B chunks per split
+  const bool tcg = PT && A.do_grad && A.tc_grad;
+  const int NC = (im.N + 1 + 7) / 8;             // A chunks per group
+  uint32_t tmem = 0;
+  // The tensor cores accumulate in fp32 with truncation: over the 200 MMA steps
+  // of a 50-iteration launch the coherent sum E sum_b O_b drifted by 1.3e-5 of
+  // its value.  The accumulators are therefore drained every A.tc_segment
+  // passes (1.7e-6 against the FP32 register tiles after 50 iterations,
+  // profiles/r02u_precision.txt).  Development option (A.tc_grad == 2): the
+  // weight planes hold E_loc - e_center, e_center = mean local energy of the
+  // CTA's walkers in the first pass of the segment, S_1 += sum_b (E_b -
+  // e_center) O_b + e_center S_0 in the drain -- better for equilibrated
+  // walkers, worse while the energy still drifts; off by default.
+  float e_center = 0.f;
 
   RBM2_MARK(1, 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -952,7 +1078,27 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
       bond_s[k] = make_int4(ij.x, ij.y, __float_as_int(A.bonds_jx[k]), __float_as_int(A.bonds_jz[k]));
     }
   }
+  if (tcg) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mma_bar)) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                   "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // A planes: slots without a walker must read as zero
+    for (int e = threadIdx.x; e < SLOTS * 2 * NP4 / 4; e += THREADS)
+      reinterpret_cast<uint4*>(ws_s)[e] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
   __syncthreads();
+  if (tcg) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tmem = *tmem_holder;
+  }
   RBM2_MARK(1, 1);
   Tables t = tables_at(WS ? img_s : img_g, im);
   if (PT) t.w2 = T_s;
@@ -982,6 +1128,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
 #pragma unroll
   for (int w = 0; w < NW; ++w) s[w] = 0ull;
 
+  int n_drained = 0;
   for (int iter = 0; iter < n_iters; ++iter)
   for (int64_t batch = blockIdx.x; batch < A.n_batches; batch += gridDim.x, ++batch_no) {
     const int64_t b0 = batch * A.wpc;
@@ -1018,9 +1165,31 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
     if (PT && A.do_grad && batch_no == 0) {
       __syncthreads();
       t.w2 = img_g + im.off_w2;
+      if (tcg) {      // B planes: rows of empty slots stay zero (finite) for the whole launch
+        for (int e = threadIdx.x; e < SLOTS * HP / 4; e += THREADS)
+          reinterpret_cast<uint4*>(T_s)[e] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+      }
     }
+    // the MMAs of the previous pass have read the operand planes; a full
+    // segment of A.tc_segment passes is drained before the next one starts
+    // (bounds the truncating accumulation in TMEM and lets e_center follow
+    // the energy of the walkers)
+    const bool seg_start = tcg && (batch_no % A.tc_segment) == 0;
+    const bool centre = seg_start && A.tc_grad == 2;          // development: E_loc centred per segment
+    if (tcg && batch_no > 0) {
+      const uint32_t bar_a = smem_u32(mma_bar), parity = (uint32_t)(batch_no - 1) & 1u;
+      uint32_t ok = 0;
+      while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar_a), "r"(parity) : "memory");
+      if (seg_start) {
+        tcg_drain<THREADS, NCOL>(tmem, ws_s, part, A.P, im.N, im.H, NC, e_center, n_drained > 0);
+        ++n_drained;
+      }
+    }
+    float e_val = 0.f;
     if (warp_on) {
-      float e_val = 0.f;
       if (A.do_eloc) {
         // ---- enumerate antiparallel bonds (operators.py:154-167) ----
         // list entry = site to raise | site to lower << 8 | bond index << 16
@@ -1076,6 +1245,19 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
           if (A.off) A.off[ob] = off;
         }
       }
+      if (centre) {
+        // e_center: every thread sums the staged local energies in the same order
+        if (valid && sub == 0) e_s[slot] = e_val;
+      }
+    }
+    if (centre) {
+      __syncthreads();
+      float acc_e = 0.f;
+      for (int sb = 0; sb < n_valid; ++sb) acc_e += e_s[sb];
+      acc_e /= (float)n_valid;
+      e_center = fabsf(acc_e) < 1.0e30f ? acc_e : 0.f;       // (NaN / inf: no centring)
+    }
+    if (warp_on) {
       if (A.do_grad && valid) {
         // stage tanh(theta) = p - m, the signed weights w_k sigma_i and E_loc
         float w0, w1;
@@ -1085,6 +1267,60 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
         } else {
           w0 = 1.f; w1 = e_val;
         }
+        if (tcg) {
+          // B planes: this lane's hidden units j = VW (sub + LPW q) + c -> chunk j / 8, halves (j % 8) ..
+          char* bp = reinterpret_cast<char*>(T_s);
+#pragma unroll
+          for (int q = 0; q < KJV; ++q) {
+            const int j0 = VW * sub + 32 * q;
+            uint32_t h1[VW / 2], h2[VW / 2];
+#pragma unroll
+            for (int c = 0; c < VW; c += 2) {
+              float v0 = p[VW * q + c] - m[VW * q + c], v1 = p[VW * q + c + 1] - m[VW * q + c + 1];
+              if (j0 + c == im.H) v0 = 1.f;          // column H: the constant 1 (a / a0 gradients)
+              if (j0 + c + 1 == im.H) v1 = 1.f;
+              const __half2 a1 = __floats2half2_rn(v0, v1);
+              const float2 f1 = __half22float2(a1);
+              const __half2 a2 = __floats2half2_rn((v0 - f1.x) * 2048.f, (v1 - f1.y) * 2048.f);
+              h1[c / 2] = *reinterpret_cast<const uint32_t*>(&a1);
+              h2[c / 2] = *reinterpret_cast<const uint32_t*>(&a2);
+            }
+            char* dst = bp + ((size_t)(j0 >> 3) * SLOTS + slot) * 16 + (j0 & 7) * 2;
+            if (VW == 4) {
+              *reinterpret_cast<uint2*>(dst) = make_uint2(h1[0], h1[(VW / 2) - 1]);
+              *reinterpret_cast<uint2*>(dst + (size_t)NB * SLOTS * 16) = make_uint2(h2[0], h2[(VW / 2) - 1]);
+            } else {
+              *reinterpret_cast<uint32_t*>(dst) = h1[0];
+              *reinterpret_cast<uint32_t*>(dst + (size_t)NB * SLOTS * 16) = h2[0];
+            }
+          }
+          // A planes: sigma, then the three fp16 pieces of w1 sigma 2^-20 (w0 = 1 on this path):
+          // x = x1 + x2 / S + x3 / S^2, 33 mantissa bits; the prescale keeps |E_loc| < 6.8e10
+          // inside the fp16 range, small values stay exact through the scaled residuals
+          float rem = (w1 - e_center) * kTcgPrescale;
+          uint32_t piece[3];
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            const __half b = __float2half_rn(rem);
+            piece[g] = (uint32_t)__half_as_ushort(b);
+            rem = (rem - __half2float(b)) * 2048.f;
+          }
+          char* ap = reinterpret_cast<char*>(ws_s);
+          for (int ch = sub; ch < 4 * NC; ch += LPW) {
+            const int g = ch / NC, c = ch - g * NC;
+            const uint32_t mag = g == 0 ? 0x3c00u : g == 1 ? piece[0] : g == 2 ? piece[1] : piece[2];
+            uint32_t wds[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int i = 8 * c + e;
+              uint32_t hb = 0u;
+              if (i < im.N) hb = spin_bit<NW>(s, i) ? mag : (mag ^ 0x8000u);
+              else if (i == im.N) hb = mag;
+              wds[e >> 1] |= hb << (16 * (e & 1));
+            }
+            *reinterpret_cast<uint4*>(ap + ((size_t)ch * SLOTS + slot) * 16) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+          }
+        } else {
         float* Trow = T_s + slot * HP + VW * sub;
 #pragma unroll
         for (int q = 0; q < KJV; ++q) {
@@ -1101,6 +1337,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
           wrow[i] = w0 * sg;
           wrow[NP4 + i] = w1 * sg;
         }
+        }
         if (sub == 0) e_s[slot] = e_val;
       }
       RBM2_MARK(1, 4);
@@ -1112,7 +1349,48 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
     // they are done.  (FMA-pipe tile work under the sampler's issue gaps.)
     if (A.do_grad) {
       if (threadIdx.x == 0) *tile_next_s = 0;
+      if (tcg) {
+        // slots beyond this batch's walkers: zero A rows (a shorter last batch of a launch)
+        for (int e = threadIdx.x; e < (SLOTS - n_valid) * 4 * NC; e += THREADS) {
+          const int ch = e / (SLOTS - n_valid), sl = n_valid + e % (SLOTS - n_valid);
+          *reinterpret_cast<uint4*>(reinterpret_cast<char*>(ws_s) + ((size_t)ch * SLOTS + sl) * 16) =
+              make_uint4(0u, 0u, 0u, 0u);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
       __syncthreads();
+      if (tcg && warp == THREADS / 32 - 1) {
+        // the last warp (no walkers when wpc < SLOTS) issues the 3 x SLOTS / 16 MMAs of this pass
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_units = smem_u32(ws_s) >> 4, b_units = smem_u32(T_s) >> 4;
+        const uint32_t hi = (uint32_t)SLOTS | (1u << 14);               // MN-major: SBO = chunk stride, LBO = 8 rows
+        // D = F32, A = B = F16, both MN-major, N = NCOL, M = 128
+        const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(NCOL >> 3) << 17) | (8u << 24);
+        uint32_t elected = 0;
+        asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(elected));
+        if (elected) {
+          for (int ks = 0; ks < SLOTS / 16; ++ks) {
+            const uint32_t accf = ((batch_no % A.tc_segment) > 0 || ks > 0) ? 1u : 0u;
+            const uint64_t a0d = ((uint64_t)hi << 32) | ((a_units + (uint32_t)(16 * ks)) | (8u << 16));
+            const uint64_t a3d = ((uint64_t)hi << 32) | ((a_units + (uint32_t)(3 * NC * SLOTS + 16 * ks)) | (8u << 16));
+            const uint64_t b1d = ((uint64_t)hi << 32) | ((b_units + (uint32_t)(16 * ks)) | (8u << 16));
+            const uint64_t b2d = ((uint64_t)hi << 32) | ((b_units + (uint32_t)(NB * SLOTS + 16 * ks)) | (8u << 16));
+            const uint64_t ad[3] = {a0d, a0d, a3d}, bd[3] = {b1d, b2d, b1d};
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+                  :
+                  : "r"(tmem + (uint32_t)(u * NCOL)), "l"(ad[u]), "l"(bd[u]), "r"(idesc), "r"(accf), "r"(0u)
+                  : "memory");
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                           smem_u32(mma_bar))
+                       : "memory");
+        }
+        __syncwarp();
+      }
     }
     if (MC && warp_on) {
       n_acc += mc_sweep<NW, LPW, KJV, WS>(t, im, picker, lut, s, p, m, sub, valid, A.n_steps, A.seed,
@@ -1130,7 +1408,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
         const int e = rev + h2 * THREADS;
-        if (e < 2 * NP4) {
+        if (!tcg && e < 2 * NP4) {
 #pragma unroll 4
           for (int sb = 0; sb < n_valid; ++sb) acc_a[h2] += ws_s[(size_t)sb * 2 * NP4 + e];
         }
@@ -1155,6 +1433,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
       constexpr int TG = 8, TQ = 32 / TG;
       const int tl = lane & (TG - 1), wg = lane / TG;
       for (;;) {
+        if (tcg) break;                                      // the tensor cores do the tiles
         int tile_base = 0;
         if (lane == 0) tile_base = atomicAdd(tile_next_s, TG);
         tile_base = __shfl_sync(CGSVMC_FULL_MASK, tile_base, 0);
@@ -1238,11 +1517,20 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(CGSVMC_FULL_MASK, mine, o);
     if (lane == 0 && mine) atomicAdd(A.accept_count, (unsigned long long)mine);
   }
+  if (tcg && batch_no > 0) {
+    // the passes since the last drain are still in TMEM
+    const uint32_t bar_a = smem_u32(mma_bar), parity = (uint32_t)(batch_no - 1) & 1u;
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok) : "r"(bar_a), "r"(parity) : "memory");
+    tcg_drain<THREADS, NCOL>(tmem, ws_s, part, A.P, im.N, im.H, NC, e_center, n_drained > 0);
+  }
   if (A.do_grad) {
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2) {
       const int e = rev + h2 * THREADS;
-      if (e < 2 * NP4) {
+      if (!tcg && e < 2 * NP4) {
         const int k = e / NP4, i = e - k * NP4;
         if (i <= im.N) part[(size_t)k * A.P + i] = acc_a[h2];   // a_i (i < N) and a0 (i == N)
       }
@@ -1255,6 +1543,12 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
   RBM2_MARK(1, 8);
   if (A.do_grad && A.fuse_reduce)
     grid_reduce<THREADS>(A, T_s);      // the staging buffer is free: every tile pass ended with a CTA barrier
+  if (tcg) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
   RBM2_MARK(1, 9);
 }
 

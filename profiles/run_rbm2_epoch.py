@@ -14,7 +14,10 @@ from cgs_vmc_b200 import engine  # noqa: E402
 
 dev = torch.device('cuda', 0)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+only = os.environ.get('RBM2_EPOCH_CONFIGS', 'C2,C5').split(',')
 for name, walkers in (('C2', 8192), ('C5', 131072)):
+  if name not in only:
+    continue
   w = bench.EnergyGradientWorkload(name, walkers, 0, 1, dev)
   ev = lambda: torch.cuda.Event(enable_timing=True)
   for _ in range(5):

@@ -185,12 +185,19 @@ def test_tc_weighted_grad_sum_vs_oracle_and_simt(native, spec, batch):
   out, simt = _grad_both(a, packed, wt)
   cfg64 = torch.from_numpy(cfg).to(F64)
   ref = estimators.weighted_grad_sum(spec, params, cfg64, torch.from_numpy(w).to(F64)).numpy()
+  # relu: a pre-activation within rounding of the kink may be switched the other
+  # way by the tcgen05 forward (a whole unit's contribution each): entries such
+  # a unit can move get that spread added to the tolerance (gpu_util.relu_kink_band;
+  # zero for smooth nonlinearities and when no unit is within 2e-5 of its kink)
+  from gpu_util import relu_kink_band
+  band = relu_kink_band(spec, params, cfg64, torch.from_numpy(w).to(F64))
+  band = band if isinstance(band, np.ndarray) else np.zeros_like(ref)
   for k in range(3):
     scale = np.abs(ref[k]).max() + 1e-3
     err = np.abs(out[k] - ref[k])
-    assert err.max() <= 1e-4 * scale + 1e-4, (k, err.max(), scale, int(err.argmax()))
-    assert np.linalg.norm(out[k] - ref[k]) <= 3e-5 * np.linalg.norm(ref[k]) + 1e-4
-    assert np.abs(out[k] - simt[k]).max() <= 1e-4 * scale + 1e-4
+    assert np.all(err <= 1e-4 * scale + 1e-4 + 1.5 * band[k]), (k, err.max(), scale, int(err.argmax()))
+    assert np.linalg.norm(out[k] - ref[k]) <= 3e-5 * np.linalg.norm(ref[k]) + 1e-4 + 1.5 * np.linalg.norm(band[k])
+    assert np.all(np.abs(out[k] - simt[k]) <= 1e-4 * scale + 1e-4 + 1.5 * band[k])
   one = a.weighted_grad_sum(packed, wt[1:2].contiguous())
   np.testing.assert_allclose(one[0].cpu().numpy(), out[1], rtol=1e-5, atol=1e-5)
   twice = a.weighted_grad_sum(packed, wt[1:2].contiguous(), out=one.clone())

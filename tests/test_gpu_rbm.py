@@ -639,6 +639,46 @@ def test_graphed_epoch_equals_graphed_batch_steps(native):
   assert sums1.n_batches == sums2.n_batches == 3 * nb
 
 
+@pytest.mark.parametrize('n_side,hidden,batch,scale', [(6, 144, 8192, 1.0), (6, 144, 777, 1.0), (6, 100, 300, 1.0),
+                                                       (4, 24, 130, 1.0), (6, 144, 96, 2.0), (6, 144, 96, 3.0)])
+def test_tensor_core_gradient_equals_register_tiles(native, n_side, hidden, batch, scale, monkeypatch):
+  """The pair-table walker kernel forms S_k = sum_b w_kb sigma_bi tanh theta_bj
+  on the tensor cores (bf16 x fp16 split planes, TMEM accumulators) when the
+  shape fits; CGSVMC_RBM2_TC_GRAD=0 keeps the FP32 register tiles.  Same
+  local energies bit for bit; sums within 2e-6 x sqrt(B) of the largest entry
+  (22-bit tanh planes, 33-bit weights; fp32 accumulation both ways).  The
+  scaled cases have local energies beyond the plain fp16 range (the operand
+  planes hold E_loc 2^-20: |E_loc| < 6.8e10 is representable; beyond that the
+  tensor-core sums overflow and CGSVMC_RBM2_TC_GRAD=0 is the way out)."""
+  from cgs_vmc_b200 import engine
+  n = n_side * n_side
+  spec = oansatz.AnsatzSpec('rbm', n, num_layers=0, layer_size=hidden, size_x=n_side, size_y=n_side)
+  a, _, _ = _setup(spec, seed=11, batch=1, scale=scale)
+  ij, jx, jz = lattices.heisenberg_couplings(lattices.square_nn_bonds(n_side))
+  ham = native.Hamiltonian(ij, jx, jz, n)
+  res = []
+  for flag in ('1', '0'):
+    monkeypatch.setenv('CGSVMC_RBM2_TC_GRAD', flag)
+    st = engine.WalkerState(batch, n, seed=9, walker_id0=3)
+    sums = engine.EnergyGradientSums(a, batch)
+    e = []
+    for _ in range(3):
+      e.append(sums.batch_step(ham, st, n).clone())
+    sums.batch_steps(ham, st, n, 2)
+    res.append((torch.stack(e), sums.sums.clone(), sums.stats.clone(), st.packed.clone()))
+  assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][3], res[1][3])
+  assert torch.equal(res[0][2], res[1][2])
+  e_max = float(res[0][0].abs().max())
+  if not e_max < 6.0e10:
+    pytest.skip('local energies up to %.3g: outside the range of the tensor-core operand planes' % e_max)
+  ref = res[1][1]
+  finite = torch.isfinite(ref)
+  assert finite.float().mean() > 0.99 or scale > 1.0
+  scale_s = float(ref[finite].abs().max()) + 1.0
+  err = float((res[0][1] - ref)[finite].abs().max())
+  assert err <= 2e-6 * scale_s * max(1.0, (5 * batch) ** 0.5), (err, scale_s)
+
+
 def test_pair_tables_of_two_hamiltonians_do_not_evict_each_other(native):
   """The walker kernel keeps one bond-pair table per (ansatz, Hamiltonian);
   a captured graph for one Hamiltonian must stay correct when the same
