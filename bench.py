@@ -478,7 +478,8 @@ def roofline_for(w, t_step, n_act, pk):
     smem_peak = 148 * 128 * f_hz / 1e12
     smem_alg = ratios * 2 * H * 4 + B * (n // 2) * H * 4
     return {
-        'kernel': 'rbm2::walker_kernel<MC> (cgsvmc_batch_step: E_loc + gradient sums + sweep)',
+        'kernel': 'rbm2::walker_kernel<MC> (cgsvmc_batch_step(s): E_loc + gradient sums%s + sweep)' % (
+            ' on tcgen05' if (n <= 39 and H < 160) else ''),
         'bound': 'shared-memory bandwidth (walker state and ratio tables are SM-resident; neither HBM nor the '
                  'tensor pipe bounds this kernel, SURVEY.md 8(d))' + (
                      '; at H=256 the 786 KB tables do not fit shared memory and are read through L1/L2'
@@ -510,7 +511,7 @@ def roofline_for(w, t_step, n_act, pk):
             'columns (4 F_fwd)); F_inc = F_fwd for conv (no incremental credit)')
   peak = pk['bf16_tflops_sustained']
   if kind == 'fully_connected':
-    return {'kernel': 'fc_tc.cu tcgen05 kernels (sampler, local energy) + net.cu mlp_grad_kernel (FP32 SIMT)',
+    return {'kernel': 'fc_tc.cu tcgen05 kernels (sampler, local energy) + fc_tc_grad.cu tcgen05 gradient sums',
             'bound': 'tensor', 'achieved': flop / t_step / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
             'frac': flop / t_step / 1e12 / peak, 'traffic': None,
             'peak_source': '%s bf16 cuBLAS, sustained' % pk['source'],
@@ -523,7 +524,7 @@ def roofline_for(w, t_step, n_act, pk):
             'what': what, 'kernel_ms': t_step * 1e3, 'n_active_bonds_mean': n_act,
             'note': 'at 1024 walkers (8 tiles of 128 for the sampler) the step is launch- and latency-bound; '
                     'profiles/ holds the 65536-walker numbers where the tensor path is 2.5-3.4x the SIMT path'}
-  return {'kernel': 'conv_tc.cu tcgen05 kernels (sampler, local energy) + net.cu conv_grad_kernel (FP32 SIMT)',
+  return {'kernel': 'conv_tc.cu tcgen05 kernels (sampler, local energy) + conv_tc_grad.cu tcgen05 gradient sums',
           'bound': 'tensor', 'achieved': flop / t_step / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
           'frac': flop / t_step / 1e12 / peak, 'traffic': None,
           'peak_source': '%s bf16 cuBLAS, sustained' % pk['source'],

@@ -298,7 +298,18 @@ class EnergyGradientOptimizer(WavefunctionOptimizer):
       graphed['g'].replay()
       state['reduced'] = False
 
+    def epoch_steps(n_batches):
+      """The whole inner loop of run_optimization_epoch (training.py:614-617) as
+      one replayed CUDA graph around cgsvmc_batch_steps: for the pure RBM ONE
+      persistent kernel for all n_batches iterations."""
+      key = ('e', int(n_batches))
+      if key not in graphed:
+        graphed[key] = engine.GraphedEpoch(configs.state, ansatz, ham, sums, n_sweep_steps, int(n_batches))
+      graphed[key].replay()
+      state['reduced'] = False
+
     self._batch_step = Op(batch_step, 'batch_step') if (self.use_cuda_graph and model.fast) else None
+    self._epoch_steps = Op(epoch_steps, 'epoch_steps') if (self.use_cuda_graph and model.fast) else None
     return TrainOpsTraditional(
         accumulate_gradients=Op(accumulate, 'accumulate_gradients'),
         apply_gradients=Op(apply_gradients, 'apply_gradients'),
@@ -316,13 +327,19 @@ class EnergyGradientOptimizer(WavefunctionOptimizer):
       session.run(train_ops.update_wf_norm)
     session.run(train_ops.reset_gradients)
     fused = getattr(self, '_batch_step', None)
-    for _ in range(hparams.num_batches_per_epoch):
-      if fused is not None:       # the same two ops, fused and graph-replayed
-        session.run(fused)
-      else:
-        session.run(train_ops.accumulate_gradients)
-        session.run(train_ops.mc_step,
-                    n_steps=hparams.num_monte_carlo_sweeps * hparams.num_sites)
+    fused_epoch = getattr(self, '_epoch_steps', None)
+    if fused_epoch is not None and hparams.num_batches_per_epoch > 0:
+      # the loop below in one library call (same trajectories and local
+      # energies as the per-batch launches, tests/test_gpu_rbm.py)
+      session.run(fused_epoch, n_batches=hparams.num_batches_per_epoch)
+    else:
+      for _ in range(hparams.num_batches_per_epoch):
+        if fused is not None:       # the same two ops, fused and graph-replayed
+          session.run(fused)
+        else:
+          session.run(train_ops.accumulate_gradients)
+          session.run(train_ops.mc_step,
+                      n_steps=hparams.num_monte_carlo_sweeps * hparams.num_sites)
     session.run(train_ops.apply_gradients)
     energy = session.run(train_ops.metrics)
     session.run(train_ops.reset_gradients)

@@ -150,6 +150,50 @@ def test_energy_gradient_training_reaches_ed_energy():
   assert np.mean(energies[-10:]) > e0 - 0.05          # variational within MC noise
 
 
+@pytest.mark.parametrize('kind,overrides', [
+    ('rbm', dict(num_fc_layers=0, fc_layer_size=24)),                       # one persistent kernel per epoch
+    ('fully_connected', dict(num_fc_layers=2, fc_layer_size=20)),          # the launches of every iteration
+])
+def test_energy_gradient_epoch_launch_equals_per_batch_ops(kind, overrides):
+  """EnergyGradientOptimizer.run_optimization_epoch (training.py:589-623) with
+  the inner loop as one cgsvmc_batch_steps call, as one captured
+  cgsvmc_batch_step per batch, and as the reference's separate
+  accumulate_gradients / mc_step ops: same walkers, same energies, same
+  parameters (float32 summation order of the gradient sums aside)."""
+  from cgs_vmc_b200 import graph_builders, operators, training, utils, wavefunctions
+  from cgs_vmc_b200.session import Session
+  results = []
+  for mode in ('epoch', 'batch', 'ops'):
+    graph_builders.reset_num_epochs()
+    hp = utils.create_hparams(wavefunction_type=kind, num_sites=16, size_x=4, size_y=4, batch_size=640,
+                              num_batches_per_epoch=5, num_equilibration_sweeps=1,
+                              learning_rates=[0.01] * 4, **overrides)
+    wf = wavefunctions.build_wavefunction(hp).seed(5)
+    ij, jx, jz = lattices.j1j2_couplings(4, 0.5)
+    ham = operators.HeisenbergHamiltonian(ij.tolist(), jx, jz)
+    opt = training.EnergyGradientOptimizer()
+    opt.use_cuda_graph = mode != 'ops'
+    shared = {}
+    ops = opt.build_opt_ops(wavefunction=wf, hamiltonian=ham, hparams=hp, shared_resources=shared)
+    if mode == 'batch':
+      opt._epoch_steps = None
+    assert (opt._epoch_steps is not None) == (mode == 'epoch')
+    s = Session()
+    energies = [opt.run_optimization_epoch(ops, s, hp, e) for e in range(3)]
+    configs = shared[graph_builders.ResourceName.CONFIGS]
+    results.append((wf.flat_parameters.clone(), configs.packed.clone(), energies, configs.state.step))
+  for other in results[1:]:
+    assert other[3] == results[0][3]
+    assert torch.equal(other[1], results[0][1])
+    np.testing.assert_allclose(other[2], results[0][2], rtol=1e-5)
+    # the constant a0 (rbm) only rescales psi: its energy gradient <E> - <E> is
+    # pure rounding noise that Adam normalises to steps of +-lr -- left out
+    keep = torch.ones_like(other[0], dtype=torch.bool)
+    if kind == 'rbm':
+      keep[16] = False
+    torch.testing.assert_close(other[0][keep], results[0][0][keep], rtol=2e-4, atol=2e-5)
+
+
 def test_supervised_training_reduces_loss():
   from cgs_vmc_b200 import training, utils, wavefunctions
   from cgs_vmc_b200.session import Session
