@@ -268,8 +268,6 @@ class EnergyGradientWorkload:
     self.sums = engine.EnergyGradientSums(self.ansatz, walkers, device=dev)
     self.opt = training.AdamOptimizer(hp)
     P = self.ansatz.num_params
-    self.tot_sums = torch.zeros(2, P, dtype=torch.float32, device=dev)
-    self.tot_stats = torch.zeros(4, dtype=torch.float64, device=dev)
     self.host_stats = torch.zeros(4, dtype=torch.float64).pin_memory()
     self.state.mc_steps(self.ansatz, 20 * self.n if name in ('C1', 'C2') else self.n)   # equilibrate a little
     self.graphed = engine.GraphedBatchStep(self.state, self.ansatz, self.ham, self.sums, self.sweep_steps)
@@ -309,18 +307,21 @@ class EnergyGradientWorkload:
 
   def epoch_end(self):
     """training.py:618-622: apply_gradients (all-reduce over the walker shards,
-    gradient, Adam), metrics (mean energy read back), reset_gradients."""
+    gradient, Adam), metrics (mean energy read back), reset_gradients -- the
+    float64 all-reduce (N > 1) + ONE kernel (cgsvmc_epoch_end) that reads the
+    all-reduced payload, applies the Adam step, stores the energy statistics
+    into pinned host memory and zeroes the accumulators; the same call
+    EnergyGradientOptimizer.run_optimization_epoch makes."""
     from cgs_vmc_b200 import distributed
     a0, a1 = ev(), ev()
     a0.record()
-    distributed.allreduce_sums(self.sums.sums, self.sums.stats, self.tot_sums, self.tot_stats)
+    payload = distributed.allreduce_payload(self.sums.sums, self.sums.stats) if self.world > 1 else None
     a1.record()
-    self.opt.apply_gradients(self.ansatz.params, sums=self.tot_sums, stats=self.tot_stats,
-                             num_batches=self.sums.n_batches)
-    self.host_stats.copy_(self.tot_stats, non_blocking=True)
-    self.sums.reset()
+    self.opt.epoch_end(self.ansatz.params, self.sums.sums, self.sums.stats, self.sums.n_batches,
+                       self.host_stats, total_payload=payload)
     done = torch.cuda.Event()
     done.record()
+    self.sums.n_batches = 0
     done.synchronize()                      # session.run(metrics) returns the energy to the host
     self.energies.append(float(self.host_stats[0] / self.host_stats[2]))
     self.allreduce_ms.append((a0, a1))

@@ -31,6 +31,7 @@ EXPORTS = [
     'cgsvmc_energy_stats', 'cgsvmc_accumulate', 'cgsvmc_batch_step',
     'cgsvmc_propose_exchange', 'cgsvmc_accept_exchange', 'cgsvmc_local_energy_from_amps',
     'cgsvmc_swo_weights', 'cgsvmc_adam_step', 'cgsvmc_batch_step_fed', 'cgsvmc_batch_steps',
+    'cgsvmc_epoch_end',
 ]
 
 
@@ -90,6 +91,7 @@ def load():
   lib.cgsvmc_batch_step_fed.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, u64, u64, u64, vp, vp, vp, vp]
   lib.cgsvmc_swo_weights.argtypes = [vp, vp, vp, vp, i64, f32, f32, vp, vp, vp]
   lib.cgsvmc_adam_step.argtypes = [vp, vp, vp, i64, vp, vp, vp, f32, f32, vp, f32, f32, f32, u64, vp, vp]
+  lib.cgsvmc_epoch_end.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, u64, vp, vp, vp]
   for name in EXPORTS:
     fn = getattr(lib, name)
     if name not in ('cgsvmc_last_error', 'cgsvmc_ansatz_num_params'):
@@ -524,6 +526,42 @@ def swo_weights(log_amp, log_amp_target, log_norm, total, sign=None, sign_target
                                   float(log_norm), 1.0 / float(total), _ptr(out), _ptr(loss_acc),
                                   _stream()))
   return out
+
+
+def epoch_end(params, m, v, local_sums, local_stats, ticket, total_sums=None, total_stats=None,
+              total_payload=None, num_batches=1.0, lr=0.0, beta1=0.9, beta2=0.99, eps=1e-8, t=1,
+              stats_out=None):
+  """apply_gradients + metrics + reset_gradients of an EnergyGradientOptimizer
+  epoch (training.py:618-622) in one kernel (cgsvmc_epoch_end): the Adam step on
+  the energy gradient of the totals, the totals' statistics stored to
+  `stats_out` (a pinned host tensor is written directly), the local
+  accumulators zeroed.  Totals: (total_sums, total_stats), defaulting to the
+  local accumulators, or the all-reduced float64 `total_payload` [2 P + 4]."""
+  n = params.numel()
+  for name, x in (('params', params), ('m', m), ('v', v)):
+    _want(x, torch.float32, (n,), name)
+  _want(local_sums, torch.float32, (2, n), 'local_sums')
+  _want(local_stats, torch.float64, (4,), 'local_stats')
+  _want(ticket, torch.int32, (1,), 'ticket')
+  if total_payload is not None:
+    _want(total_payload, torch.float64, (2 * n + 4,), 'total_payload')
+    total_sums = total_stats = None
+  else:
+    total_sums = local_sums if total_sums is None else total_sums
+    total_stats = local_stats if total_stats is None else total_stats
+    _want(total_sums, torch.float32, (2, n), 'total_sums')
+    _want(total_stats, torch.float64, (4,), 'total_stats')
+  out_ptr = None
+  if stats_out is not None:
+    if stats_out.dtype != torch.float64 or stats_out.numel() != 4 or not stats_out.is_contiguous() or not (
+        stats_out.is_cuda or stats_out.is_pinned()):
+      raise ValueError('stats_out must be a contiguous float64 [4] tensor on the device or in pinned host memory')
+    out_ptr = _ptr(stats_out)
+  check(load().cgsvmc_epoch_end(_ptr(params), _ptr(m), _ptr(v), n, _ptr(total_sums), _ptr(total_payload),
+                                _ptr(total_stats), _ptr(local_sums), _ptr(local_stats),
+                                1.0 / float(num_batches), float(lr), float(beta1), float(beta2), float(eps),
+                                int(t), out_ptr, _ptr(ticket), _stream()))
+  torch.autograd.graph.increment_version(params)
 
 
 def adam_step(params, m, v, grad=None, sums=None, stats=None, num_batches=1.0, lr=0.0, lr_dev=None,

@@ -578,6 +578,26 @@ int cgsvmc_adam_step(float* params, float* m, float* v, int64_t n, const float* 
   return CGSVMC_OK;
 }
 
+int cgsvmc_epoch_end(float* params, float* m, float* v, int64_t n, const float* total_sums,
+                     const double* total_payload, const double* total_stats, float* local_sums,
+                     double* local_stats, float inv_num_batches, float lr, float beta1, float beta2, float eps,
+                     uint64_t t, double* stats_out, uint32_t* ticket, void* stream) {
+  NvtxRange range("cgsvmc:epoch_end");
+  if (n < 0) return invalid("epoch_end: n < 0");
+  if (n == 0) return CGSVMC_OK;
+  if (params == nullptr || m == nullptr || v == nullptr || ticket == nullptr) return invalid("epoch_end: NULL buffer");
+  if ((total_sums == nullptr) == (total_payload == nullptr))
+    return invalid("epoch_end: give either total_sums + total_stats or total_payload");
+  if (total_sums != nullptr && total_stats == nullptr) return invalid("epoch_end: total_sums need total_stats");
+  if (t < 1) return invalid("epoch_end: t starts at 1");
+  // the float32 totals are scratch of the all-reduce when they are not the local accumulators
+  float* zero_b = (total_sums != nullptr && total_sums != local_sums) ? const_cast<float*>(total_sums) : nullptr;
+  double* zero_sb = (total_stats != nullptr && total_stats != local_stats) ? const_cast<double*>(total_stats) : nullptr;
+  return launch_epoch_end(params, m, v, n, total_sums, total_payload, total_stats, local_sums, zero_b,
+                          local_stats, zero_sb, inv_num_batches, lr, beta1, beta2, eps, t, stats_out, ticket,
+                          (cudaStream_t)stream);
+}
+
 int cgsvmc_energy_stats(const float* e_loc, int64_t B, double* stats, void* stream) {
   NvtxRange range("cgsvmc:K5 energy_stats");
   if (B < 0) return invalid("energy_stats: n_walkers < 0");

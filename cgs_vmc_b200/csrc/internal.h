@@ -90,6 +90,10 @@ int launch_reduce_partials(const float* partials, int n_parts, int64_t n, float*
                            cudaStream_t s);
 int launch_swo_weights(const float* z, const float* sign, const float* zt, const float* sign_t, int64_t B,
                        float log_norm, float inv_total, float* weights, double* acc, cudaStream_t s);
+int launch_epoch_end(float* params, float* m, float* v, int64_t n, const float* tot_sums,
+                     const double* tot_payload, const double* tot_stats, float* zero_a, float* zero_b,
+                     double* zero_stats_a, double* zero_stats_b, float inv_nb, float lr, float b1, float b2,
+                     float eps, uint64_t t, double* stats_out, unsigned int* ticket, cudaStream_t s);
 int launch_adam(float* params, float* m, float* v, int64_t n, const float* grad, const float* sums,
                 const double* stats, float inv_nb, float lr, const float* lr_dev, float b1, float b2,
                 float eps, uint64_t t, const uint64_t* t_dev, cudaStream_t s);

@@ -297,6 +297,26 @@ __global__ void swo_weights_kernel(const float* __restrict__ z, const float* __r
 // sums of EnergyGradientOptimizer (training.py:562-564):
 //   g = (S[1][i] - (stats[0] / stats[2]) S[0][i]) * inv_nb.
 // lr / t come from device scalars when given (CUDA-graph replays).
+__device__ __forceinline__ float adam_lr_t(float lr, float b1, float b2, uint64_t t) {
+  const double td = (double)t;
+  return (float)((double)lr * sqrt(1.0 - pow((double)b2, td)) / (1.0 - pow((double)b1, td)));
+}
+
+// g = (S[1][i] - mean_e S[0][i]) * inv_nb in the rounding order both kernels share
+__device__ __forceinline__ float energy_gradient(float so, float seo, float mean_e, float inv_nb) {
+  return __fsub_rn(__fmul_rn(seo, inv_nb), __fmul_rn(mean_e, __fmul_rn(so, inv_nb)));
+}
+
+__device__ __forceinline__ void adam_update(float* __restrict__ params, float* __restrict__ m,
+                                            float* __restrict__ v, int64_t i, float g, float lr_t, float b1,
+                                            float b2, float eps) {
+  const float mi = __fadd_rn(__fmul_rn(b1, m[i]), __fmul_rn(1.0f - b1, g));
+  const float vi = __fadd_rn(__fmul_rn(b2, v[i]), __fmul_rn(__fmul_rn(1.0f - b2, g), g));
+  m[i] = mi;
+  v[i] = vi;
+  params[i] = __fsub_rn(params[i], __fdiv_rn(__fmul_rn(lr_t, mi), __fadd_rn(sqrtf(vi), eps)));
+}
+
 __global__ void adam_kernel(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v,
                             int64_t n, const float* __restrict__ grad, const float* __restrict__ sums,
                             const double* __restrict__ stats, float inv_nb, float lr,
@@ -304,17 +324,57 @@ __global__ void adam_kernel(float* __restrict__ params, float* __restrict__ m, f
                             uint64_t t, const uint64_t* __restrict__ t_dev) {
   if (lr_dev != nullptr) lr = *lr_dev;
   if (t_dev != nullptr) t = *t_dev + 1;
-  const double td = (double)t;
-  const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, td)) / (1.0 - pow((double)b1, td)));
+  const float lr_t = adam_lr_t(lr, b1, b2, t);
   const float mean_e = stats != nullptr ? (float)(stats[0] / stats[2]) : 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const float g = sums != nullptr ? (sums[n + i] * inv_nb - mean_e * (sums[i] * inv_nb)) : grad[i];
-    const float mi = b1 * m[i] + (1.0f - b1) * g;
-    const float vi = b2 * v[i] + (1.0f - b2) * g * g;
-    m[i] = mi;
-    v[i] = vi;
-    params[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    const float g = sums != nullptr ? energy_gradient(sums[i], sums[n + i], mean_e, inv_nb) : grad[i];
+    adam_update(params, m, v, i, g, lr_t, b1, b2, eps);
+  }
+}
+
+// End of an EnergyGradientOptimizer epoch (training.py:618-622) in one kernel:
+// apply_gradients (the Adam step above on the energy gradient of the TOTALS --
+// float32 sums [2][n] + double stats [4], or the all-reduced float64 payload
+// [2 n + 4] itself), metrics (the totals' statistics written to stats_out,
+// which may be mapped host memory) and reset_gradients (the local
+// accumulators, and the float32 totals when they are separate buffers, are
+// zeroed by the thread that consumed the entry; the statistics by the last
+// block to finish -- every block has read them by then).
+template <typename TS>
+__global__ void epoch_end_kernel(float* __restrict__ params, float* __restrict__ m, float* __restrict__ v,
+                                 int64_t n, const TS* __restrict__ tot_sums, const double* __restrict__ tot_stats,
+                                 float* __restrict__ zero_a, float* __restrict__ zero_b,
+                                 double* __restrict__ zero_stats_a, double* __restrict__ zero_stats_b,
+                                 float inv_nb, float lr, float b1, float b2, float eps, uint64_t t,
+                                 double* stats_out, unsigned int* ticket) {
+  const float lr_t = adam_lr_t(lr, b1, b2, t);
+  const double s0 = tot_stats[0], s1 = tot_stats[1], s2 = tot_stats[2], s3 = tot_stats[3];
+  const float mean_e = (float)(s0 / s2);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float g = energy_gradient((float)tot_sums[i], (float)tot_sums[n + i], mean_e, inv_nb);
+    adam_update(params, m, v, i, g, lr_t, b1, b2, eps);
+    if (zero_a != nullptr) { zero_a[i] = 0.f; zero_a[n + i] = 0.f; }
+    if (zero_b != nullptr) { zero_b[i] = 0.f; zero_b[n + i] = 0.f; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int done = atomicAdd(ticket, 1u);
+    if (done == gridDim.x - 1) {
+      if (stats_out != nullptr) {
+        volatile double* o = stats_out;
+        o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3;
+        __threadfence_system();
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (zero_stats_a != nullptr) zero_stats_a[k] = 0.0;
+        if (zero_stats_b != nullptr) zero_stats_b[k] = 0.0;
+      }
+      *ticket = 0u;
+    }
   }
 }
 
@@ -395,6 +455,23 @@ int launch_adam(float* params, float* m, float* v, int64_t n, const float* grad,
   adam_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(params, m, v, n, grad, sums, stats, inv_nb, lr,
                                                           lr_dev, b1, b2, eps, t, t_dev);
   return cuda_fail(cudaGetLastError(), "adam launch");
+}
+
+int launch_epoch_end(float* params, float* m, float* v, int64_t n, const float* tot_sums,
+                     const double* tot_payload, const double* tot_stats, float* zero_a, float* zero_b,
+                     double* zero_stats_a, double* zero_stats_b, float inv_nb, float lr, float b1, float b2,
+                     float eps, uint64_t t, double* stats_out, unsigned int* ticket, cudaStream_t s) {
+  if (n == 0) return CGSVMC_OK;
+  const int blocks = blocks_for(n, kThreads);
+  if (tot_payload != nullptr)
+    epoch_end_kernel<double><<<blocks, kThreads, 0, s>>>(params, m, v, n, tot_payload, tot_payload + 2 * n,
+                                                         zero_a, zero_b, zero_stats_a, zero_stats_b, inv_nb, lr,
+                                                         b1, b2, eps, t, stats_out, ticket);
+  else
+    epoch_end_kernel<float><<<blocks, kThreads, 0, s>>>(params, m, v, n, tot_sums, tot_stats, zero_a, zero_b,
+                                                        zero_stats_a, zero_stats_b, inv_nb, lr, b1, b2, eps, t,
+                                                        stats_out, ticket);
+  return cuda_fail(cudaGetLastError(), "epoch_end launch");
 }
 
 int launch_reduce_partials(const float* partials, int n_parts, int64_t n, float* out,

@@ -69,6 +69,15 @@ def allreduce_sums(sums, stats, out_sums=None, out_stats=None):
   return out_sums, out_stats
 
 
+def allreduce_payload(sums, stats):
+  """The all-reduced FLOAT64 payload [K * P + 4] itself (cgsvmc_epoch_end reads
+  it directly: no unpacking pass)."""
+  payload = pack_sums(sums, stats)
+  if world_size() > 1:
+    dist.all_reduce(payload, op=dist.ReduceOp.SUM)
+  return payload
+
+
 def broadcast_(tensor, src=0):
   """Rank `src`'s values on every rank (parameter replicas start identical)."""
   if world_size() > 1:

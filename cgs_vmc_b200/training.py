@@ -79,6 +79,20 @@ class AdamOptimizer(_Optimizer):
                       num_batches=num_batches, lr=self.learning_rate(), beta1=self.beta1,
                       beta2=self.beta2, eps=self.eps, t=self.t)
 
+  def epoch_end(self, params, local_sums, local_stats, num_batches, stats_out, total_sums=None,
+                total_stats=None, total_payload=None):
+    """apply_gradients on the totals + the totals' statistics to `stats_out` +
+    reset of the local accumulators in ONE kernel (cgsvmc_epoch_end;
+    training.py:618-622)."""
+    self._state(params)
+    self.t += 1
+    if getattr(self, '_ticket', None) is None:
+      self._ticket = torch.zeros(1, dtype=torch.int32, device=params.device)
+    _native.epoch_end(params, self.m, self.v, local_sums, local_stats, self._ticket, total_sums=total_sums,
+                      total_stats=total_stats, total_payload=total_payload, num_batches=num_batches,
+                      lr=self.learning_rate(), beta1=self.beta1, beta2=self.beta2, eps=self.eps, t=self.t,
+                      stats_out=stats_out)
+
   def device_state(self, params):
     """(t_dev, lr_dev): step count and learning rate in device memory for a
     captured update; sync_device() refreshes them before a replay."""
@@ -308,8 +322,34 @@ class EnergyGradientOptimizer(WavefunctionOptimizer):
       graphed[key].replay()
       state['reduced'] = False
 
+    host_stats = {}
+
+    def epoch_end():
+      """apply_gradients, metrics and reset_gradients (training.py:618-622) as
+      one all-reduce (walker-sharded runs) + ONE kernel that also stores the
+      energy statistics into pinned host memory; returns the mean energy."""
+      if 'h' not in host_stats:
+        host_stats['h'] = torch.zeros(4, dtype=torch.float64).pin_memory()
+        host_stats['done'] = torch.cuda.Event()
+      payload = None
+      if total is not sums and not state['reduced']:
+        payload = distributed.allreduce_payload(sums.sums, sums.stats)
+      elif total is not sums:       # already reduced by a metrics / apply_gradients call of the caller
+        payload = distributed.pack_sums(total.sums, total.stats)
+      model.optimizers[0].epoch_end(model.leaf_params[0], sums.sums, sums.stats, sums.n_batches,
+                                    host_stats['h'], total_payload=payload)
+      host_stats['done'].record()
+      sums.n_batches = 0
+      state['reduced'] = False
+      host_stats['done'].synchronize()
+      h = host_stats['h']
+      return float(h[0] / h[2])
+
     self._batch_step = Op(batch_step, 'batch_step') if (self.use_cuda_graph and model.fast) else None
     self._epoch_steps = Op(epoch_steps, 'epoch_steps') if (self.use_cuda_graph and model.fast) else None
+    fusable = (self.use_cuda_graph and model.fast and len(model.leaf_params) == 1 and
+               isinstance(model.optimizers[0], AdamOptimizer))
+    self._epoch_end = Op(epoch_end, 'epoch_end') if fusable else None
     return TrainOpsTraditional(
         accumulate_gradients=Op(accumulate, 'accumulate_gradients'),
         apply_gradients=Op(apply_gradients, 'apply_gradients'),
@@ -340,9 +380,13 @@ class EnergyGradientOptimizer(WavefunctionOptimizer):
           session.run(train_ops.accumulate_gradients)
           session.run(train_ops.mc_step,
                       n_steps=hparams.num_monte_carlo_sweeps * hparams.num_sites)
-    session.run(train_ops.apply_gradients)
-    energy = session.run(train_ops.metrics)
-    session.run(train_ops.reset_gradients)
+    fused_end = getattr(self, '_epoch_end', None)
+    if fused_end is not None:     # the three ops below as one kernel
+      energy = session.run(fused_end)
+    else:
+      session.run(train_ops.apply_gradients)
+      energy = session.run(train_ops.metrics)
+      session.run(train_ops.reset_gradients)
     session.run(train_ops.epoch_increment)
     return energy
 

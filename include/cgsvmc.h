@@ -374,6 +374,25 @@ int cgsvmc_adam_step(float* params, float* m, float* v, int64_t n,
                      float beta1, float beta2, float eps, uint64_t t,
                      uint64_t* t_dev, void* stream);
 
+/* Replaces the three session.run calls that end an epoch of
+ * EnergyGradientOptimizer.run_optimization_epoch (training.py:618-622) with one
+ * kernel: apply_gradients (cgsvmc_adam_step on the energy gradient of the
+ * all-reduced totals, training.py:562-567), metrics (the totals' statistics
+ * [sum E, sum E^2, n, .] are stored to stats_out, which may be mapped pinned
+ * host memory; training.py:555, 619-620) and reset_gradients (local_sums
+ * [2, n] and local_stats [4] are zeroed; training.py:568, 621).
+ * The totals are either total_sums (float32 [2, n]) + total_stats (double [4])
+ * -- the same pointers as the local accumulators on one rank -- or
+ * total_payload, the float64 all-reduce payload [2 n + 4] itself.  `ticket`:
+ * one zero-initialised uint32 of device memory owned by the caller (returned
+ * to zero by the kernel). */
+int cgsvmc_epoch_end(float* params, float* m, float* v, int64_t n,
+                     const float* total_sums, const double* total_payload,
+                     const double* total_stats, float* local_sums,
+                     double* local_stats, float inv_num_batches, float lr,
+                     float beta1, float beta2, float eps, uint64_t t,
+                     double* stats_out, uint32_t* ticket, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -252,6 +252,41 @@ def test_adam_step_kernel_matches_tf_rule():
     _native.adam_step(params, m, v, lr=lr, t=1)           # neither grad nor sums
 
 
+@pytest.mark.parametrize('use_payload', [False, True])
+def test_epoch_end_kernel_equals_separate_ops(use_payload):
+  """cgsvmc_epoch_end (apply_gradients + metrics + reset_gradients of
+  training.py:618-622 in one kernel) against cgsvmc_adam_step on the same sums
+  followed by the read-back and the reset: identical parameters and moments,
+  statistics in pinned host memory, accumulators zeroed, ticket re-armed."""
+  from cgs_vmc_b200 import _native
+  _native.require_cuda()
+  g = torch.Generator().manual_seed(5)
+  n = 70001
+  params0 = torch.randn(n, generator=g).cuda()
+  ticket = torch.zeros(1, dtype=torch.int32, device='cuda')
+  host = torch.zeros(4, dtype=torch.float64).pin_memory()
+  pa, ma, va = params0.clone(), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+  pb, mb, vb = params0.clone(), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+  for t in range(1, 4):
+    sums = torch.randn(2, n, generator=g).cuda() * 50
+    stats = torch.tensor([-1234.5 * t, 2.0e6, 4096.0 * t, 0.0], dtype=torch.float64, device='cuda')
+    local_sums, local_stats = sums.clone(), stats.clone()
+    kw = {}
+    if use_payload:      # walker-sharded run: the all-reduced float64 payload of two equal shards
+      sums, stats = 2 * sums, 2 * stats
+      kw['total_payload'] = torch.cat([sums.reshape(-1).double(), stats])
+    _native.adam_step(pa, ma, va, sums=sums, stats=stats, num_batches=3, lr=0.01, beta2=0.99, t=t)
+    version = pb._version
+    _native.epoch_end(pb, mb, vb, local_sums, local_stats, ticket, num_batches=3, lr=0.01, beta2=0.99, t=t,
+                      stats_out=host, **kw)
+    torch.cuda.synchronize()
+    assert pb._version > version
+    assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb)
+    assert torch.equal(host, stats.cpu())
+    assert float(local_sums.abs().max()) == 0.0 and float(local_stats.abs().max()) == 0.0
+    assert int(ticket.item()) == 0
+
+
 def test_supervised_captured_batch_equals_eager_ops():
   """SupervisedWavefunctionOptimizer: the replayed graph of one batch (sweep +
   train step) leaves the same parameters and walkers as session.run(mc_step) x
