@@ -687,7 +687,12 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     return max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev, world), d2h[0] / args.steps
 
-  e2e_s, d2h_per_step = e2e_timed(host_cfg)
+  e2e_s, d2h_per_step = e2e_timed(host_cfg)           # the engine's own choice ('auto') of the upload form
+  e2e_h2d_bytes = fed.h2d_bytes
+  auto_pack = fed.host_pack
+  fed.host_pack = not auto_pack                         # and the other form, for comparison
+  e2e_other_s, _ = e2e_timed(host_cfg)
+  fed.host_pack = auto_pack
   host_packed = w.state.packed.cpu().pin_memory()
   e2e_packed_s, _ = e2e_timed(host_packed)
 
@@ -761,11 +766,20 @@ def run_ours(args, rank, world, local_rank):
       'e2e': {'value': walkers_total * SWEEP_STEPS * args.steps / e2e_s, 'unit': 'walker-steps/s',
               'eloc_evals_per_sec': walkers_total * args.steps / e2e_s,
               'ms_per_step': e2e_s / args.steps * 1e3,
-              'h2d_bytes_per_step': fed.h2d_bytes, 'd2h_bytes_per_step': d2h_per_step,
+              'h2d_bytes_per_step': e2e_h2d_bytes, 'd2h_bytes_per_step': d2h_per_step,
               'd2h': 'the energy statistics (32 B) after every step and the all-reduced statistics at every '
                      'epoch end; the gradient never leaves the device (the Adam update runs there)',
-              'input': 'float32 [B, N] +-1 configurations (the reference layout) from pinned host memory, '
-                       'uploaded and bit-packed every step',
+              'input': 'float32 [B, N] +-1 configurations (the reference layout) in pinned host memory, every '
+                       'step; ' + ('bit-packed by the host cores (cgsvmc_pack_configs_host, inside the timed '
+                                   'region) and uploaded as uint64 words' if auto_pack else
+                                   'uploaded as float32 and bit-packed by the walker kernel'),
+              'host_pack': bool(auto_pack),
+              'host_pack_choice': 'engine.HostFedBatchStep(host_pack="auto"): packs on the host when the measured '
+                                  'float32 upload exceeds the measured packing time + 50 us',
+              'host_pack_probe': fed.host_pack_probe,
+              'other_upload_form': {'host_pack': not auto_pack,
+                                    'value': walkers_total * SWEEP_STEPS * args.steps / e2e_other_s,
+                                    'ms_per_step': e2e_other_s / args.steps * 1e3},
               'walkers': 'the swept walkers stay on the device like the reference\'s session-owned variable '
                          '(graph_builders.py:92-125); they are not copied back to the host',
               'packed_host_input': {

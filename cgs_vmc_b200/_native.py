@@ -31,7 +31,7 @@ EXPORTS = [
     'cgsvmc_energy_stats', 'cgsvmc_accumulate', 'cgsvmc_batch_step',
     'cgsvmc_propose_exchange', 'cgsvmc_accept_exchange', 'cgsvmc_local_energy_from_amps',
     'cgsvmc_swo_weights', 'cgsvmc_adam_step', 'cgsvmc_batch_step_fed', 'cgsvmc_batch_steps',
-    'cgsvmc_epoch_end',
+    'cgsvmc_epoch_end', 'cgsvmc_pack_configs_host',
 ]
 
 
@@ -91,6 +91,7 @@ def load():
   lib.cgsvmc_batch_step_fed.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, u64, u64, u64, vp, vp, vp, vp]
   lib.cgsvmc_swo_weights.argtypes = [vp, vp, vp, vp, i64, f32, f32, vp, vp, vp]
   lib.cgsvmc_adam_step.argtypes = [vp, vp, vp, i64, vp, vp, vp, f32, f32, vp, f32, f32, f32, u64, vp, vp]
+  lib.cgsvmc_pack_configs_host.argtypes = [vp, i64, i32, vp, i32]
   lib.cgsvmc_epoch_end.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, u64, vp, vp, vp]
   for name in EXPORTS:
     fn = getattr(lib, name)
@@ -424,6 +425,19 @@ def pack_configs(configs, out=None):
     packed = out
   check(load().cgsvmc_pack_configs(_ptr(configs), b, n, _ptr(packed), _stream()))
   return packed
+
+
+def pack_configs_host(configs, out, n_threads=0):
+  """float32 [B, N] of +-1 in HOST memory -> int64-viewed uint64 [B, W] in host
+  memory (normally a pinned staging buffer), on the host cores
+  (cgsvmc_pack_configs_host)."""
+  b, n = configs.shape
+  if configs.is_cuda or configs.dtype != torch.float32 or not configs.is_contiguous():
+    raise ValueError('configs must be a contiguous float32 host tensor')
+  if out.is_cuda or out.dtype != torch.int64 or not out.is_contiguous() or tuple(out.shape) != (b, n_words(n)):
+    raise ValueError('out must be a contiguous int64 host tensor of shape [B, ceil(N / 64)]')
+  check(load().cgsvmc_pack_configs_host(_ptr(configs), b, n, _ptr(out), int(n_threads)))
+  return out
 
 
 def unpack_configs(packed, n_sites, out=None):

@@ -253,6 +253,15 @@ int cgsvmc_pack_configs(const float* configs, int64_t B, int32_t N, uint64_t* pa
   return launch_pack(configs, B, N, packed, (cudaStream_t)stream);
 }
 
+int cgsvmc_pack_configs_host(const float* configs_host, int64_t B, int32_t N, uint64_t* packed_host,
+                             int32_t n_threads) {
+  NvtxRange range("cgsvmc:K0 pack_configs_host");
+  if (B < 0 || N < 1 || N > CGSVMC_MAX_SITES) return invalid("pack_configs_host: bad shape");
+  if (B > 0 && (configs_host == nullptr || packed_host == nullptr)) return invalid("pack_configs_host: NULL buffer");
+  if (B == 0) return CGSVMC_OK;
+  return pack_configs_host(configs_host, B, N, packed_host, n_threads);
+}
+
 int cgsvmc_unpack_configs(const uint64_t* packed, int64_t B, int32_t N, float* configs, void* stream) {
   NvtxRange range("cgsvmc:K0 unpack_configs");
   if (B < 0 || N < 1 || N > CGSVMC_MAX_SITES) return invalid("unpack_configs: bad shape");

@@ -237,16 +237,25 @@ class HostFedBatchStep(_CapturedStep):
   batch has landed.  The [2, P] gradient sums are accumulated on the device
   like the reference's local variables; fetch_sums() copies them out."""
 
-  def __init__(self, state, ansatz, ham, sums, n_steps):
+  def __init__(self, state, ansatz, ham, sums, n_steps, host_pack='auto'):
     dev = state.packed.device
     B, N, P = state.batch_size, state.n_sites, ansatz.num_params
     self.copy_stream = torch.cuda.Stream(device=dev)
+    # float32 host input: either uploaded as it is (4 N bytes per walker, packed
+    # by the walker kernel) or bit-packed by the host cores into a pinned staging
+    # buffer first (cgsvmc_pack_configs_host: 8 bytes per 64 sites over PCIe).
+    # 'auto' measures both on this box and packs when the upload would bound the step.
+    self.host_staging = [torch.zeros(B, _native.n_words(N), dtype=torch.int64).pin_memory() for _ in range(2)]
+    self.host_pack_probe = None
+    if host_pack == 'auto':
+      host_pack = self._probe_host_pack(B, N, dev)
+    self.host_pack = bool(host_pack)
     self.dev_cfg = [torch.empty(B, N, dtype=torch.float32, device=dev) for _ in range(2)]
     self.host_stats = [torch.zeros(4, dtype=torch.float64).pin_memory() for _ in range(2)]
     self.host_sums = torch.empty(2, P, dtype=torch.float32).pin_memory()
     self.uploaded = [torch.cuda.Event() for _ in range(2)]
     self.landed = [torch.cuda.Event() for _ in range(2)]
-    self.h2d_bytes = B * N * 4
+    self._h2d_bytes = (B * N * 4, B * _native.n_words(N) * 8)      # float32 upload, host-packed upload
     self.d2h_bytes_stats = 32
     self.d2h_bytes_sums = 2 * P * 4
     self._submitted = 0
@@ -272,6 +281,37 @@ class HostFedBatchStep(_CapturedStep):
                                st.seed, st.walker_id0, st.step_dev, accept_count=st.accept_count,
                                e_loc_out=self.sums.weights[1], stats_out=self.host_stats[slot])
 
+  @property
+  def h2d_bytes(self):
+    return self._h2d_bytes[1 if self.host_pack else 0]
+
+  def _probe_host_pack(self, B, N, dev):
+    """True when packing a float32 [B, N] batch on the host cores takes less
+    time than the extra bytes of its float32 upload on this box."""
+    import time
+    host = torch.ones(B, N, dtype=torch.float32).pin_memory()
+    dst = torch.empty(B, N, dtype=torch.float32, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dst.copy_(host, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(4):
+      dst.copy_(host, non_blocking=True)
+    e1.record()
+    e1.synchronize()
+    t_h2d = e0.elapsed_time(e1) * 1e-3 / 4
+    _native.pack_configs_host(host, self.host_staging[0])
+    t0 = time.perf_counter()
+    for _ in range(4):
+      _native.pack_configs_host(host, self.host_staging[0])
+    t_pack = (time.perf_counter() - t0) / 4
+    self.host_pack_probe = {'h2d_float32_us': t_h2d * 1e6, 'host_pack_us': t_pack * 1e6,
+                            'h2d_float32_gbps': B * N * 4 / t_h2d / 1e9}
+    # the upload runs on the copy engine under the previous step's kernel; the
+    # packing runs on the submitting thread in front of ~50 us of launch work
+    # per step: it only pays when the upload alone exceeds both
+    return t_h2d > t_pack + 50e-6
+
   def submit(self, host_configs):
     """host_configs: pinned host tensor, either the reference's float32 [B, N]
     of +-1 or the library's own walker layout, int64 [B, ceil(N / 64)]
@@ -279,6 +319,11 @@ class HostFedBatchStep(_CapturedStep):
     Asynchronous."""
     slot = self._submitted & 1
     main = torch.cuda.current_stream()
+    if host_configs.dtype == torch.float32 and self.host_pack:
+      if tuple(host_configs.shape) != tuple(self.dev_cfg[slot].shape):
+        raise ValueError('Size of existing variable does not match.')
+      self.uploaded[slot].synchronize()          # the copy engine is done with this staging buffer
+      host_configs = _native.pack_configs_host(host_configs, self.host_staging[slot])
     from_packed = host_configs.dtype == torch.int64
     with torch.cuda.stream(self.copy_stream):
       self.copy_stream.wait_event(self.landed[slot])

@@ -143,6 +143,14 @@ int cgsvmc_pack_configs(const float* configs, int64_t n_walkers,
                         int32_t n_sites, uint64_t* packed, void* stream);
 int cgsvmc_unpack_configs(const uint64_t* packed, int64_t n_walkers,
                           int32_t n_sites, float* configs, void* stream);
+/* The same conversion on the HOST, for a caller that keeps the reference's
+ * float32 [B, N] tensor in host memory and feeds a batch per step: 4 N bytes
+ * per walker shrink to 8 W before the PCIe link (bit = 1 <=> value > 0, the
+ * rule of cgsvmc_pack_configs).  Synchronous; n_threads <= 0 picks a thread
+ * count from the size (persistent worker pool).  Layout conversion only. */
+int cgsvmc_pack_configs_host(const float* configs_host, int64_t n_walkers,
+                             int32_t n_sites, uint64_t* packed_host,
+                             int32_t n_threads);
 /* Replaces utils.random_configurations (utils.py:169-192): uniformly random
  * configurations with n_sites / 2 spins down, Philox keyed by
  * (seed, walker_id0 + b). */

@@ -65,3 +65,23 @@ def test_product_fails_loudly_without_cuda():
   from cgs_vmc_b200 import _native
   with pytest.raises(_native.NativeError, match='no CPU fallback'):
     _native.Ansatz('rbm', 8, layer_size=4)
+
+
+@pytest.mark.parametrize('shape', [(1, 1), (7, 20), (300, 36), (64, 64), (33, 65), (20, 100), (9, 256), (5000, 36)])
+@pytest.mark.parametrize('threads', [0, 1, 3])
+def test_pack_configs_host_matches_oracle_layout(shape, threads):
+  """cgsvmc_pack_configs_host is host code (layout conversion of the
+  reference's float32 [B, N] tensor before the upload): bit-exact against the
+  oracle's packed layout, for ragged word counts and any thread count."""
+  import numpy as np
+  import torch
+  from cgs_vmc_b200 import _native
+  from oracle import bits
+  b, n = shape
+  rng = np.random.default_rng(b * 1000 + n)
+  cfg = rng.choice([-1.0, 1.0], size=(b, n)).astype(np.float32)
+  out = torch.full((b, (n + 63) // 64), -1, dtype=torch.int64)
+  _native.pack_configs_host(torch.from_numpy(cfg), out, threads)
+  assert np.array_equal(out.numpy().view(np.uint64), bits.pack(cfg).reshape(b, -1))
+  with pytest.raises(ValueError):
+    _native.pack_configs_host(torch.from_numpy(cfg), out[:, :0].contiguous(), threads)

@@ -714,11 +714,14 @@ def test_pair_tables_of_two_hamiltonians_do_not_evict_each_other(native):
   assert torch.equal(sums1.sums, sums2.sums)
 
 
-def test_host_fed_batch_step(native):
+@pytest.mark.parametrize('host_pack', [False, True, 'auto'])
+def test_host_fed_batch_step(native, host_pack):
   """engine.HostFedBatchStep (pinned host configurations in, energy statistics
   out every batch, gradient sums on request; one graph per buffer slot) gives
   the statistics and sums of accumulate() on the same configurations, batch
-  after batch, including after a parameter update."""
+  after batch, including after a parameter update -- with the float32 batch
+  uploaded as it is, and bit-packed on the host cores first
+  (cgsvmc_pack_configs_host)."""
   from cgs_vmc_b200 import engine
   spec = _c2_spec()
   a, _, _ = _setup(spec, seed=3, batch=1)
@@ -727,7 +730,8 @@ def test_host_fed_batch_step(native):
   B = 600
   s1 = engine.WalkerState(B, 36, seed=5)
   sums1 = engine.EnergyGradientSums(a, B)
-  fed = engine.HostFedBatchStep(s1, a, ham, sums1, 36)
+  fed = engine.HostFedBatchStep(s1, a, ham, sums1, 36, host_pack=host_pack)
+  assert fed.h2d_bytes == (B * 8 if fed.host_pack else B * 36 * 4)
   ref_sums = engine.EnergyGradientSums(a, B)
   gen = np.random.default_rng(0)
   for k in range(5):
