@@ -31,7 +31,7 @@ EXPORTS = [
     'cgsvmc_energy_stats', 'cgsvmc_accumulate', 'cgsvmc_batch_step',
     'cgsvmc_propose_exchange', 'cgsvmc_accept_exchange', 'cgsvmc_local_energy_from_amps',
     'cgsvmc_swo_weights', 'cgsvmc_adam_step', 'cgsvmc_batch_step_fed', 'cgsvmc_batch_steps',
-    'cgsvmc_epoch_end', 'cgsvmc_pack_configs_host',
+    'cgsvmc_epoch_end', 'cgsvmc_pack_configs_host', 'cgsvmc_upload_configs',
 ]
 
 
@@ -92,6 +92,7 @@ def load():
   lib.cgsvmc_swo_weights.argtypes = [vp, vp, vp, vp, i64, f32, f32, vp, vp, vp]
   lib.cgsvmc_adam_step.argtypes = [vp, vp, vp, i64, vp, vp, vp, f32, f32, vp, f32, f32, f32, u64, vp, vp]
   lib.cgsvmc_pack_configs_host.argtypes = [vp, i64, i32, vp, i32]
+  lib.cgsvmc_upload_configs.argtypes = [vp, i64, i32, vp, vp, i32, vp]
   lib.cgsvmc_epoch_end.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, u64, vp, vp, vp]
   for name in EXPORTS:
     fn = getattr(lib, name)
@@ -438,6 +439,17 @@ def pack_configs_host(configs, out, n_threads=0):
     raise ValueError('out must be a contiguous int64 host tensor of shape [B, ceil(N / 64)]')
   check(load().cgsvmc_pack_configs_host(_ptr(configs), b, n, _ptr(out), int(n_threads)))
   return out
+
+
+def upload_configs(configs, dst, stream, staging=None, n_threads=0):
+  """One float32 [B, N] host batch to the device on `stream` (a
+  torch.cuda.Stream), as float32 into `dst` [B, N] or -- with a pinned
+  `staging` buffer -- bit-packed on the host cores first, into `dst` [B, W]
+  (cgsvmc_upload_configs).  No shape checks beyond the library's: the caller
+  (engine.HostFedBatchStep) owns the buffers."""
+  b, n = configs.shape
+  check(load().cgsvmc_upload_configs(_ptr(configs), b, n, _ptr(staging), _ptr(dst), int(n_threads),
+                                     ctypes.c_void_p(stream.cuda_stream)))
 
 
 def unpack_configs(packed, n_sites, out=None):

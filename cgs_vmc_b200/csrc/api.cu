@@ -262,6 +262,23 @@ int cgsvmc_pack_configs_host(const float* configs_host, int64_t B, int32_t N, ui
   return pack_configs_host(configs_host, B, N, packed_host, n_threads);
 }
 
+int cgsvmc_upload_configs(const float* configs_host, int64_t B, int32_t N, uint64_t* staging_host,
+                          void* dst, int32_t n_threads, void* stream) {
+  NvtxRange range("cgsvmc:K0 upload_configs");
+  if (B < 0 || N < 1 || N > CGSVMC_MAX_SITES) return invalid("upload_configs: bad shape");
+  if (B == 0) return CGSVMC_OK;
+  if (configs_host == nullptr || dst == nullptr) return invalid("upload_configs: NULL buffer");
+  const void* src = configs_host;
+  size_t bytes = (size_t)B * (size_t)N * sizeof(float);
+  if (staging_host != nullptr) {
+    if (int rc = pack_configs_host(configs_host, B, N, staging_host, n_threads)) return rc;
+    src = staging_host;
+    bytes = (size_t)B * (size_t)n_words(N) * sizeof(uint64_t);
+  }
+  return cuda_fail(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream),
+                   "upload_configs copy");
+}
+
 int cgsvmc_unpack_configs(const uint64_t* packed, int64_t B, int32_t N, float* configs, void* stream) {
   NvtxRange range("cgsvmc:K0 unpack_configs");
   if (B < 0 || N < 1 || N > CGSVMC_MAX_SITES) return invalid("unpack_configs: bad shape");

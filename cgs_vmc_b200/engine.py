@@ -319,23 +319,24 @@ class HostFedBatchStep(_CapturedStep):
     Asynchronous."""
     slot = self._submitted & 1
     main = torch.cuda.current_stream()
-    if host_configs.dtype == torch.float32 and self.host_pack:
-      if tuple(host_configs.shape) != tuple(self.dev_cfg[slot].shape):
+    from_packed = host_configs.dtype == torch.int64 or self.host_pack
+    self.copy_stream.wait_event(self.landed[slot])
+    if host_configs.dtype == torch.int64:
+      if tuple(host_configs.shape) != tuple(self.slot_packed[slot].shape):
         raise ValueError('Size of existing variable does not match.')
-      self.uploaded[slot].synchronize()          # the copy engine is done with this staging buffer
-      host_configs = _native.pack_configs_host(host_configs, self.host_staging[slot])
-    from_packed = host_configs.dtype == torch.int64
-    with torch.cuda.stream(self.copy_stream):
-      self.copy_stream.wait_event(self.landed[slot])
-      if from_packed:
-        if tuple(host_configs.shape) != tuple(self.slot_packed[slot].shape):
-          raise ValueError('Size of existing variable does not match.')
+      with torch.cuda.stream(self.copy_stream):
         self.slot_packed[slot].copy_(host_configs, non_blocking=True)
+    else:
+      if (tuple(host_configs.shape) != tuple(self.dev_cfg[slot].shape) or host_configs.dtype != torch.float32 or
+          host_configs.is_cuda or not host_configs.is_contiguous()):
+        raise ValueError('Size of existing variable does not match.')
+      if self.host_pack:
+        self.uploaded[slot].synchronize()        # the copy engine is done with this staging buffer
+        _native.upload_configs(host_configs, self.slot_packed[slot], self.copy_stream,
+                               staging=self.host_staging[slot])
       else:
-        if tuple(host_configs.shape) != tuple(self.dev_cfg[slot].shape):
-          raise ValueError('Size of existing variable does not match.')
-        self.dev_cfg[slot].copy_(host_configs, non_blocking=True)
-      self.uploaded[slot].record(self.copy_stream)
+        _native.upload_configs(host_configs, self.dev_cfg[slot], self.copy_stream)
+    self.uploaded[slot].record(self.copy_stream)
     main.wait_event(self.uploaded[slot])
     self._replay(slot + (2 if from_packed else 0))
     self.state.packed = self.slot_packed[slot]

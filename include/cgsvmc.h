@@ -151,6 +151,15 @@ int cgsvmc_unpack_configs(const uint64_t* packed, int64_t n_walkers,
 int cgsvmc_pack_configs_host(const float* configs_host, int64_t n_walkers,
                              int32_t n_sites, uint64_t* packed_host,
                              int32_t n_threads);
+/* One host batch to the device, asynchronously on `stream` (the caller's copy
+ * stream): with staging_host == NULL the float32 [B, N] tensor itself goes to
+ * dst (float32 [B, N], for cgsvmc_batch_step_fed); otherwise the batch is
+ * packed into staging_host (pinned, uint64 [B, W]; must not be in flight) by
+ * cgsvmc_pack_configs_host and the packed words go to dst (uint64 [B, W]).
+ * configs_host should be pinned for the copy to be asynchronous. */
+int cgsvmc_upload_configs(const float* configs_host, int64_t n_walkers,
+                          int32_t n_sites, uint64_t* staging_host, void* dst,
+                          int32_t n_threads, void* stream);
 /* Replaces utils.random_configurations (utils.py:169-192): uniformly random
  * configurations with n_sites / 2 spins down, Philox keyed by
  * (seed, walker_id0 + b). */
