@@ -774,8 +774,8 @@ def run_ours(args, rank, world, local_rank):
                                    'region) and uploaded as uint64 words' if auto_pack else
                                    'uploaded as float32 and bit-packed by the walker kernel'),
               'host_pack': bool(auto_pack),
-              'host_pack_choice': 'engine.HostFedBatchStep(host_pack="auto"): packs on the host when the measured '
-                                  'float32 upload exceeds the measured packing time + 50 us',
+              'host_pack_choice': 'engine.HostFedBatchStep(host_pack="auto"): packs on the host unless the measured '
+                                  'packing time exceeds the measured float32 upload + 60 us',
               'host_pack_probe': fed.host_pack_probe,
               'other_upload_form': {'host_pack': not auto_pack,
                                     'value': walkers_total * SWEEP_STEPS * args.steps / e2e_other_s,

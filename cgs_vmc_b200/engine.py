@@ -237,19 +237,22 @@ class HostFedBatchStep(_CapturedStep):
   batch has landed.  The [2, P] gradient sums are accumulated on the device
   like the reference's local variables; fetch_sums() copies them out."""
 
-  def __init__(self, state, ansatz, ham, sums, n_steps, host_pack='auto'):
+  def __init__(self, state, ansatz, ham, sums, n_steps, host_pack='auto', native_step=True):
     dev = state.packed.device
     B, N, P = state.batch_size, state.n_sites, ansatz.num_params
     self.copy_stream = torch.cuda.Stream(device=dev)
     # float32 host input: either uploaded as it is (4 N bytes per walker, packed
     # by the walker kernel) or bit-packed by the host cores into a pinned staging
     # buffer first (cgsvmc_pack_configs_host: 8 bytes per 64 sites over PCIe).
-    # 'auto' measures both on this box and packs when the upload would bound the step.
+    # 'auto' measures both on this box and packs unless the host cores are far slower than the link.
     self.host_staging = [torch.zeros(B, _native.n_words(N), dtype=torch.int64).pin_memory() for _ in range(2)]
     self.host_pack_probe = None
     if host_pack == 'auto':
       host_pack = self._probe_host_pack(B, N, dev)
     self.host_pack = bool(host_pack)
+    # float32 batches: one library call per step (cgsvmc_host_fed_step) instead of the
+    # event / copy / graph-replay calls issued from Python (False keeps those)
+    self.native_step = native_step
     self.dev_cfg = [torch.empty(B, N, dtype=torch.float32, device=dev) for _ in range(2)]
     self.host_stats = [torch.zeros(4, dtype=torch.float64).pin_memory() for _ in range(2)]
     self.host_sums = torch.empty(2, P, dtype=torch.float32).pin_memory()
@@ -272,6 +275,8 @@ class HostFedBatchStep(_CapturedStep):
     main = torch.cuda.current_stream()
     for ev in self.landed:
       ev.record(main)
+    for ev in self.uploaded:                 # (an event has no handle before its first record)
+      ev.record(self.copy_stream)
 
   def _body(self, variant):
     slot, from_packed = variant & 1, variant >= 2
@@ -307,10 +312,13 @@ class HostFedBatchStep(_CapturedStep):
     t_pack = (time.perf_counter() - t0) / 4
     self.host_pack_probe = {'h2d_float32_us': t_h2d * 1e6, 'host_pack_us': t_pack * 1e6,
                             'h2d_float32_gbps': B * N * 4 / t_h2d / 1e9}
-    # the upload runs on the copy engine under the previous step's kernel; the
-    # packing runs on the submitting thread in front of ~50 us of launch work
-    # per step: it only pays when the upload alone exceeds both
-    return t_h2d > t_pack + 50e-6
+    # Measured on this pool (profiles/r02A_bench_steps{20,200}.json): even on a
+    # box whose link moves the float32 batch in 27 us the packed form wins (69
+    # against 76 us per step in steady state, 73 against 98 us over the first
+    # 20 steps after an idle period -- the link and the in-kernel packing of
+    # 1.18 MB cost more than 46 us of host cores), so pack unless the host
+    # cores are pathologically slow next to the link
+    return t_pack < t_h2d + 60e-6
 
   def submit(self, host_configs):
     """host_configs: pinned host tensor, either the reference's float32 [B, N]
@@ -319,6 +327,25 @@ class HostFedBatchStep(_CapturedStep):
     Asynchronous."""
     slot = self._submitted & 1
     main = torch.cuda.current_stream()
+    if host_configs.dtype == torch.float32 and self.native_step:
+      # the whole choreography below in ONE library call (cgsvmc_host_fed_step)
+      if (tuple(host_configs.shape) != tuple(self.dev_cfg[slot].shape) or host_configs.is_cuda or
+          not host_configs.is_contiguous()):
+        raise ValueError('Size of existing variable does not match.')
+      st = self.state
+      if self.host_pack:
+        self.uploaded[slot].synchronize()        # the copy engine is done with this staging buffer
+      self.ansatz.host_fed_step(
+          self.ham, host_configs, self.host_staging[slot] if self.host_pack else None, self.dev_cfg[slot],
+          self.slot_packed[slot], self.sums.weights[1], self.sums.sums, self.sums.stats, self.n_steps, st.seed,
+          st.walker_id0, st.step, st.accept_count, self.host_stats[slot], self.copy_stream, self.landed[slot],
+          self.uploaded[slot])
+      st.packed = self.slot_packed[slot]
+      self.sums.n_batches += 1
+      st.step += self.n_steps
+      st.proposed += self.n_steps * st.batch_size
+      self._submitted += 1
+      return
     from_packed = host_configs.dtype == torch.int64 or self.host_pack
     self.copy_stream.wait_event(self.landed[slot])
     if host_configs.dtype == torch.int64:
