@@ -32,7 +32,6 @@ EXPORTS = [
     'cgsvmc_propose_exchange', 'cgsvmc_accept_exchange', 'cgsvmc_local_energy_from_amps',
     'cgsvmc_swo_weights', 'cgsvmc_adam_step', 'cgsvmc_batch_step_fed', 'cgsvmc_batch_steps',
     'cgsvmc_epoch_end', 'cgsvmc_pack_configs_host', 'cgsvmc_upload_configs',
-    'cgsvmc_host_fed_step',
 ]
 
 
@@ -94,8 +93,6 @@ def load():
   lib.cgsvmc_adam_step.argtypes = [vp, vp, vp, i64, vp, vp, vp, f32, f32, vp, f32, f32, f32, u64, vp, vp]
   lib.cgsvmc_pack_configs_host.argtypes = [vp, i64, i32, vp, i32]
   lib.cgsvmc_upload_configs.argtypes = [vp, i64, i32, vp, vp, i32, vp]
-  lib.cgsvmc_host_fed_step.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, u64, u64, u64, vp, vp, vp, vp, vp, vp,
-                                       i32]
   lib.cgsvmc_epoch_end.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, u64, vp, vp, vp]
   for name in EXPORTS:
     fn = getattr(lib, name)
@@ -372,24 +369,6 @@ class Ansatz:
                                        _ptr(e_loc_out), None, _ptr(sums), _ptr(stats), int(n_steps),
                                        int(seed), int(walker_id0), 0, _ptr(step_counter),
                                        _ptr(accept_count), _ptr(stats_out), _stream()))
-
-
-  def host_fed_step(self, ham, host_configs, staging, configs_dev, packed_dev, e_loc_out, sums, stats, n_steps,
-                    seed, walker_id0, step0, accept_count, stats_out, copy_stream, landed_event,
-                    uploaded_event, n_threads=0):
-    """One double-buffered host-fed batch step in one library call
-    (cgsvmc_host_fed_step): upload (bit-packed on the host through the pinned
-    `staging` buffer when it is given, else float32 into `configs_dev`) on
-    `copy_stream`, the fused batch step on the current stream, the slot's two
-    torch.cuda.Events (already recorded once) as the hand-shake.  The caller
-    (engine.HostFedBatchStep) owns and has validated the buffers."""
-    self._sync_params()
-    b = packed_dev.shape[0]
-    check(load().cgsvmc_host_fed_step(
-        self._handle, ham._handle, _ptr(host_configs), b, _ptr(staging), _ptr(configs_dev), _ptr(packed_dev),
-        _ptr(e_loc_out), _ptr(sums), _ptr(stats), int(n_steps), int(seed), int(walker_id0), int(step0),
-        _ptr(accept_count), _ptr(stats_out), ctypes.c_void_p(copy_stream.cuda_stream), _stream(),
-        ctypes.c_void_p(landed_event.cuda_event), ctypes.c_void_p(uploaded_event.cuda_event), int(n_threads)))
 
 
 class Hamiltonian:

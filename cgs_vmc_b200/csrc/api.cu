@@ -540,36 +540,6 @@ int cgsvmc_batch_step_fed(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const flo
                          walker_id0, step0, step_counter, accept_count, stats_out, stream);
 }
 
-int cgsvmc_host_fed_step(const cgsvmc_ansatz* a, const cgsvmc_ham* h, const float* configs_host, int64_t B,
-                         uint64_t* staging_host, float* configs_dev, uint64_t* packed_dev, float* e_loc_out,
-                         float* sums, double* stats, int32_t n_steps, uint64_t seed, uint64_t walker_id0,
-                         uint64_t step0, unsigned long long* accept_count, double* stats_out, void* copy_stream,
-                         void* stream, void* landed_event, void* uploaded_event, int32_t n_threads) {
-  NvtxRange range("cgsvmc:host_fed_step");
-  if (int rc = check_ready(a)) return rc;
-  if (B < 0) return invalid("host_fed_step: negative size");
-  if (B == 0) return CGSVMC_OK;
-  if (configs_host == nullptr || packed_dev == nullptr || landed_event == nullptr || uploaded_event == nullptr)
-    return invalid("host_fed_step: NULL buffer / event");
-  if (staging_host == nullptr && configs_dev == nullptr)
-    return invalid("host_fed_step: give a staging buffer (host packing) or a float32 device buffer");
-  cudaStream_t cs = (cudaStream_t)copy_stream, ms = (cudaStream_t)stream;
-  cudaEvent_t landed = (cudaEvent_t)landed_event, uploaded = (cudaEvent_t)uploaded_event;
-  // the slot's buffers are free once the step that last used them has finished
-  if (int rc = cuda_fail(cudaStreamWaitEvent(cs, landed, 0), "host_fed_step wait (copy stream)")) return rc;
-  if (int rc = cgsvmc_upload_configs(configs_host, B, a->desc.n_sites, staging_host,
-                                     staging_host != nullptr ? (void*)packed_dev : (void*)configs_dev, n_threads,
-                                     copy_stream))
-    return rc;
-  if (int rc = cuda_fail(cudaEventRecord(uploaded, cs), "host_fed_step record (upload)")) return rc;
-  if (int rc = cuda_fail(cudaStreamWaitEvent(ms, uploaded, 0), "host_fed_step wait (compute stream)")) return rc;
-  if (int rc = batch_step_impl(a, h, staging_host != nullptr ? nullptr : configs_dev, packed_dev, B, e_loc_out,
-                               nullptr, sums, stats, n_steps, seed, walker_id0, step0, nullptr, accept_count,
-                               stats_out, stream))
-    return rc;
-  return cuda_fail(cudaEventRecord(landed, ms), "host_fed_step record (step)");
-}
-
 int cgsvmc_propose_exchange(const uint64_t* packed, int64_t B, int32_t N, uint64_t seed,
                             uint64_t walker_id0, uint64_t step, uint64_t* proposed, float* u_acc,
                             void* stream) {

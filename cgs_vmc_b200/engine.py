@@ -237,7 +237,7 @@ class HostFedBatchStep(_CapturedStep):
   batch has landed.  The [2, P] gradient sums are accumulated on the device
   like the reference's local variables; fetch_sums() copies them out."""
 
-  def __init__(self, state, ansatz, ham, sums, n_steps, host_pack='auto', native_step=True):
+  def __init__(self, state, ansatz, ham, sums, n_steps, host_pack='auto'):
     dev = state.packed.device
     B, N, P = state.batch_size, state.n_sites, ansatz.num_params
     self.copy_stream = torch.cuda.Stream(device=dev)
@@ -250,9 +250,6 @@ class HostFedBatchStep(_CapturedStep):
     if host_pack == 'auto':
       host_pack = self._probe_host_pack(B, N, dev)
     self.host_pack = bool(host_pack)
-    # float32 batches: one library call per step (cgsvmc_host_fed_step) instead of the
-    # event / copy / graph-replay calls issued from Python (False keeps those)
-    self.native_step = native_step
     self.dev_cfg = [torch.empty(B, N, dtype=torch.float32, device=dev) for _ in range(2)]
     self.host_stats = [torch.zeros(4, dtype=torch.float64).pin_memory() for _ in range(2)]
     self.host_sums = torch.empty(2, P, dtype=torch.float32).pin_memory()
@@ -275,8 +272,6 @@ class HostFedBatchStep(_CapturedStep):
     main = torch.cuda.current_stream()
     for ev in self.landed:
       ev.record(main)
-    for ev in self.uploaded:                 # (an event has no handle before its first record)
-      ev.record(self.copy_stream)
 
   def _body(self, variant):
     slot, from_packed = variant & 1, variant >= 2
@@ -327,25 +322,6 @@ class HostFedBatchStep(_CapturedStep):
     Asynchronous."""
     slot = self._submitted & 1
     main = torch.cuda.current_stream()
-    if host_configs.dtype == torch.float32 and self.native_step:
-      # the whole choreography below in ONE library call (cgsvmc_host_fed_step)
-      if (tuple(host_configs.shape) != tuple(self.dev_cfg[slot].shape) or host_configs.is_cuda or
-          not host_configs.is_contiguous()):
-        raise ValueError('Size of existing variable does not match.')
-      st = self.state
-      if self.host_pack:
-        self.uploaded[slot].synchronize()        # the copy engine is done with this staging buffer
-      self.ansatz.host_fed_step(
-          self.ham, host_configs, self.host_staging[slot] if self.host_pack else None, self.dev_cfg[slot],
-          self.slot_packed[slot], self.sums.weights[1], self.sums.sums, self.sums.stats, self.n_steps, st.seed,
-          st.walker_id0, st.step, st.accept_count, self.host_stats[slot], self.copy_stream, self.landed[slot],
-          self.uploaded[slot])
-      st.packed = self.slot_packed[slot]
-      self.sums.n_batches += 1
-      st.step += self.n_steps
-      st.proposed += self.n_steps * st.batch_size
-      self._submitted += 1
-      return
     from_packed = host_configs.dtype == torch.int64 or self.host_pack
     self.copy_stream.wait_event(self.landed[slot])
     if host_configs.dtype == torch.int64:

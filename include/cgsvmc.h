@@ -410,28 +410,6 @@ int cgsvmc_epoch_end(float* params, float* m, float* v, int64_t n,
                      float beta1, float beta2, float eps, uint64_t t,
                      double* stats_out, uint32_t* ticket, void* stream);
 
-/* One host-fed batch step for a caller that keeps the reference's float32
- * [B, N] configuration tensor in (pinned) host memory and reads the energy
- * statistics back every batch (graph_builders.py:92-125 seen from outside the
- * session; training.py:614-620): the stream / event choreography of a
- * double-buffered feed in one call, so the host pays one library call per
- * step.  On `copy_stream`: wait for `landed_event` (the step that last used
- * this buffer slot), cgsvmc_upload_configs (packed through staging_host when
- * it is given, else float32 into configs_dev), record `uploaded_event`; on
- * `stream`: wait for it, cgsvmc_batch_step_fed (statistics to stats_out, which
- * may be mapped host memory), record `landed_event`.  Events are cudaEvent_t
- * handles owned by the caller, one pair per buffer slot; staging_host must not
- * be in flight (synchronise on the slot's uploaded_event first). */
-int cgsvmc_host_fed_step(const cgsvmc_ansatz* ansatz, const cgsvmc_ham* ham,
-                         const float* configs_host, int64_t n_walkers,
-                         uint64_t* staging_host, float* configs_dev,
-                         uint64_t* packed_dev, float* e_loc_out, float* sums,
-                         double* stats, int32_t n_steps, uint64_t seed,
-                         uint64_t walker_id0, uint64_t step0,
-                         unsigned long long* accept_count, double* stats_out,
-                         void* copy_stream, void* stream, void* landed_event,
-                         void* uploaded_event, int32_t n_threads);
-
 #ifdef __cplusplus
 }
 #endif

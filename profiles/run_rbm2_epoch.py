@@ -28,6 +28,14 @@ for name, walkers in (('C2', 8192), ('C5', 131072)):
   torch.cuda.synchronize()
   per_step = float(np.mean([a.elapsed_time(b) for a, b in marks]))
   print(json.dumps({'config': name, 'variant': 'one graph per step (cgsvmc_batch_step)', 'ms_per_step': per_step}))
+  a0, b0 = ev(), ev()
+  a0.record()
+  for _ in range(50):
+    w.graphed.replay()
+  b0.record()
+  torch.cuda.synchronize()
+  print(json.dumps({'config': name, 'variant': 'one graph per step, 50 replays back to back (no L2 flush)',
+                    'ms_per_step': a0.elapsed_time(b0) / 50}))
   for nb in (5, 20, 50):
     if name == 'C5' and nb > 20:
       continue
