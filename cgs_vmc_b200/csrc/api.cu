@@ -326,6 +326,9 @@ int cgsvmc_mc_steps(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int32_t
   if (conv_tc_supported(a, nullptr))
     return conv_tc_mc_steps(const_cast<cgsvmc_ansatz*>(a), packed, B, n_steps, seed, walker_id0, step0,
                             accept_count, log_amp_out, (cudaStream_t)stream);
+  if (fc_warp_supported(a, B))      // small batches: one warp per walker beats the 128-walker tensor-core tiles
+    return fc_warp_mc_steps(a, packed, B, n_steps, seed, walker_id0, step0, accept_count, log_amp_out,
+                            (cudaStream_t)stream);
   if (fc_tc_supported(a, nullptr))
     return fc_tc_mc_steps(const_cast<cgsvmc_ansatz*>(a), packed, B, n_steps, seed, walker_id0, step0,
                           accept_count, log_amp_out, (cudaStream_t)stream);

@@ -172,6 +172,12 @@ int fc_tc_local_energy(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* pa
                        float* e_loc, float* log_amp_out, float* diag_out, float* off_out,
                        cudaStream_t s);
 
+// warp-per-walker sampler of the fully connected ansatz for small batches (fc_warp.cu)
+bool fc_warp_supported(const cgsvmc_ansatz* a, int64_t B);
+int fc_warp_mc_steps(const cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int n_steps, uint64_t seed,
+                     uint64_t walker0, uint64_t step0, unsigned long long* accept_count, float* log_amp_out,
+                     cudaStream_t s);
+
 // weighted gradient sums of the fully connected ansatz on tcgen05 (fc_tc_grad.cu):
 // forward, backward-data and the weight-gradient GEMMs dW_l = h_{l-1}^T (w delta_l)
 int fc_tc_image(cgsvmc_ansatz* a, const void** wimg, const float** consts, cudaStream_t s);

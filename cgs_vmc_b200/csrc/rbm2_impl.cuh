@@ -732,18 +732,24 @@ mc_kernel(Image im, const float* __restrict__ img_g, uint64_t* __restrict__ pack
 // Deliberately compact and out of line: it runs a few times per launch and
 // would otherwise be paid in instruction fetches.
 template <int THREADS, int NCOL>
-__device__ __noinline__ void tcg_drain(uint32_t tmem, float* stg, float* part, int64_t P, int N, int H, int NC,
-                                       float e_center, bool add) {
+__device__ __noinline__ void tcg_drain(uint32_t tmem, float* stg, int n_groups, float* part, int64_t P, int N, int H,
+                                       int NC, float e_center, bool add) {
   constexpr int LD = 20;                     // staging row stride (floats): 16-byte aligned rows
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int NPC = 8 * NC;
+  const int grp_floats = (128 + NPC) * LD;   // one staging buffer: rows of P0 / P1 (128) + piece-3 rows (NPC)
+  const int wq = warp & 3, g = warp >> 2;    // TMEM lane quarter of this warp, column-chunk group
+  const int per = 2 * NPC * 4;               // (k, row, 4-column group) items of one chunk
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   __syncthreads();
+  // n_groups chunks of 16 columns per round: warp (wq, g) reads lane quarter wq of chunk g
 #pragma unroll 1
-  for (int c0 = 0; c0 < NCOL; c0 += 16) {
-    if (warp < 4) {
-      const int mrow = 32 * warp + lane;
-      const uint32_t tbase = tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0;
+  for (int cbase = 0; cbase < NCOL; cbase += 16 * n_groups) {
+    const int c0 = cbase + 16 * g;
+    if (g < n_groups && c0 < NCOL) {
+      float* sg = stg + (size_t)g * grp_floats;
+      const int mrow = 32 * wq + lane;
+      const uint32_t tbase = tmem + ((uint32_t)(32 * wq) << 16) + (uint32_t)c0;
       uint32_t q0[16], q1[16], q2[16];
 #define RBM2_TMEM_LD16(ADDR, R)                                                                                  \
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
@@ -752,7 +758,7 @@ __device__ __noinline__ void tcg_drain(uint32_t tmem, float* stg, float* part, i
                    : "r"(ADDR) : "memory")
       RBM2_TMEM_LD16(tbase, q0);
       RBM2_TMEM_LD16(tbase + (uint32_t)NCOL, q1);
-      if (warp < 2) RBM2_TMEM_LD16(tbase + (uint32_t)(2 * NCOL), q2);      // piece 3: rows [0, NPC) only
+      if (wq < 2) RBM2_TMEM_LD16(tbase + (uint32_t)(2 * NCOL), q2);      // piece 3: rows [0, NPC) only
 #undef RBM2_TMEM_LD16
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
@@ -762,26 +768,30 @@ __device__ __noinline__ void tcg_drain(uint32_t tmem, float* stg, float* part, i
         v.y = fmaf(__uint_as_float(q1[c + 1]), 1.f / 2048.f, __uint_as_float(q0[c + 1]));
         v.z = fmaf(__uint_as_float(q1[c + 2]), 1.f / 2048.f, __uint_as_float(q0[c + 2]));
         v.w = fmaf(__uint_as_float(q1[c + 3]), 1.f / 2048.f, __uint_as_float(q0[c + 3]));
-        *reinterpret_cast<float4*>(stg + mrow * LD + c) = v;
-        if (warp < 2 && mrow < NPC)
-          *reinterpret_cast<float4*>(stg + (128 + mrow) * LD + c) =
+        *reinterpret_cast<float4*>(sg + mrow * LD + c) = v;
+        if (wq < 2 && mrow < NPC)
+          *reinterpret_cast<float4*>(sg + (128 + mrow) * LD + c) =
               make_float4(__uint_as_float(q2[c]), __uint_as_float(q2[c + 1]), __uint_as_float(q2[c + 2]),
                           __uint_as_float(q2[c + 3]));
       }
     }
     __syncthreads();
-    // one (weight column k, row i, 4 columns) group per thread
+    // one (chunk group, weight column k, row i, 4 columns) item per thread
 #pragma unroll 1
-    for (int e = threadIdx.x; e < 2 * NPC * 4; e += THREADS) {
-      const int k = e >= NPC * 4 ? 1 : 0, r = e - k * NPC * 4;
+    for (int e = threadIdx.x; e < n_groups * per; e += THREADS) {
+      const int gg = e / per, e1 = e - gg * per;
+      const int cc0 = cbase + 16 * gg;
+      if (cc0 >= NCOL) continue;
+      const float* sg = stg + (size_t)gg * grp_floats;
+      const int k = e1 >= NPC * 4 ? 1 : 0, r = e1 - k * NPC * 4;
       const int i = r >> 2, c = (r & 3) * 4;
       if (i > N) continue;
-      const float4 s0 = *reinterpret_cast<const float4*>(stg + i * LD + c);
+      const float4 s0 = *reinterpret_cast<const float4*>(sg + i * LD + c);
       float v[4] = {s0.x, s0.y, s0.z, s0.w};
       if (k == 1) {
-        const float4 p1 = *reinterpret_cast<const float4*>(stg + (NPC + i) * LD + c);
-        const float4 p2 = *reinterpret_cast<const float4*>(stg + (2 * NPC + i) * LD + c);
-        const float4 p3 = *reinterpret_cast<const float4*>(stg + (128 + i) * LD + c);
+        const float4 p1 = *reinterpret_cast<const float4*>(sg + (NPC + i) * LD + c);
+        const float4 p2 = *reinterpret_cast<const float4*>(sg + (2 * NPC + i) * LD + c);
+        const float4 p3 = *reinterpret_cast<const float4*>(sg + (128 + i) * LD + c);
         const float a1[4] = {p1.x, p1.y, p1.z, p1.w}, a2[4] = {p2.x, p2.y, p2.z, p2.w},
                     a3[4] = {p3.x, p3.y, p3.z, p3.w};
 #pragma unroll
@@ -792,7 +802,7 @@ __device__ __noinline__ void tcg_drain(uint32_t tmem, float* stg, float* part, i
       float* row_w = part + (size_t)k * P + (size_t)(N + 1) + (size_t)i * H;    // W[i][.] (i < N), c[.] (i == N)
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int j = c0 + c + u;
+        const int j = cc0 + c + u;
         if (j > H) continue;
         float* dst = j < H ? row_w + j : part + (size_t)k * P + i;              // column H: a_i (i < N), a0 (i == N)
         if (add) atomicAdd(dst, v[u]);
@@ -1053,6 +1063,10 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
   // e_center) O_b + e_center S_0 in the drain -- better for equilibrated
   // walkers, worse while the energy still drifts; off by default.
   float e_center = 0.f;
+  // drain: T_s and ws_s (contiguous, free between two passes) stage up to four
+  // 16-column chunks at a time, one per group of four warps
+  const int drain_groups = max(1, min(min(THREADS / 128, 4),
+                                      (SLOTS * HP + SLOTS * 2 * NP4) / ((128 + 8 * NC) * 20)));
 
   RBM2_MARK(1, 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1184,8 +1198,14 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(ok) : "r"(bar_a), "r"(parity) : "memory");
       if (seg_start) {
-        tcg_drain<THREADS, NCOL>(tmem, ws_s, part, A.P, im.N, im.H, NC, e_center, n_drained > 0);
+        tcg_drain<THREADS, NCOL>(tmem, T_s, drain_groups, part, A.P, im.N, im.H, NC, e_center, n_drained > 0);
         ++n_drained;
+        // the staging went through the operand planes: rows of empty slots must read as zero again
+        for (int e = threadIdx.x; e < SLOTS * HP / 4; e += THREADS)
+          reinterpret_cast<uint4*>(T_s)[e] = make_uint4(0u, 0u, 0u, 0u);
+        for (int e = threadIdx.x; e < SLOTS * 2 * NP4 / 4; e += THREADS)
+          reinterpret_cast<uint4*>(ws_s)[e] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
       }
     }
     float e_val = 0.f;
@@ -1524,7 +1544,7 @@ walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
     while (!ok)
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                    : "=r"(ok) : "r"(bar_a), "r"(parity) : "memory");
-    tcg_drain<THREADS, NCOL>(tmem, ws_s, part, A.P, im.N, im.H, NC, e_center, n_drained > 0);
+    tcg_drain<THREADS, NCOL>(tmem, T_s, drain_groups, part, A.P, im.N, im.H, NC, e_center, n_drained > 0);
   }
   if (A.do_grad) {
 #pragma unroll

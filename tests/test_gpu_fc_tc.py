@@ -43,8 +43,10 @@ def native():
 @pytest.fixture(autouse=True)
 def _tc_on():
   os.environ['CGSVMC_FC_TC'] = '1'
+  os.environ['CGSVMC_FC_WARP'] = '0'      # small batches too: these tests are about the tensor-core kernels
   yield
   os.environ.pop('CGSVMC_FC_TC', None)
+  os.environ.pop('CGSVMC_FC_WARP', None)
 
 
 def _setup(spec, seed, batch, bias=0.1):
@@ -252,3 +254,72 @@ def test_fc_tc_energy_gradient_golden(native):
   grad = (s[1] - mean_e * s[0]).cpu().numpy()
   ref = g['eg_gradient']
   assert np.linalg.norm(grad - ref) <= 5e-4 * np.linalg.norm(ref) + 1e-4
+
+
+# ---------------------------------------------------------------------------
+# warp-per-walker sampler for small batches (fc_warp.cu)
+# ---------------------------------------------------------------------------
+FC_WARP_SHAPES = FC_SHAPES + [
+    oansatz.AnsatzSpec('fully_connected', 130, num_layers=1, layer_size=16, nonlinearity='tanh'),   # three words
+    oansatz.AnsatzSpec('fully_connected', 16, num_layers=8, layer_size=96, nonlinearity='tanh'),    # widest, deepest
+]
+
+
+@pytest.mark.parametrize('spec', FC_WARP_SHAPES, ids=_id)
+def test_fc_warp_sampler_matches_oracle_philox(native, spec):
+  """cgsvmc_mc_steps on the warp-per-walker kernel (what batches of at most
+  2,048 walkers of a fully connected ansatz get): every proposal identical to
+  the Philox restatement of graph_builders.py:54-89, accept decisions identical
+  away from near-ties (float32 forward), acceptance count, Sz conserved,
+  multi-step == single steps, and the same trajectories as the tensor-core /
+  tile kernels up to near-ties."""
+  from gpu_util import packed_cuda, unpack_np
+  os.environ['CGSVMC_FC_WARP'] = '1'
+  batch = 77
+  a, params, cfg = _setup(spec, seed=9, batch=batch)
+  seed, w0 = 0xC65, 500
+  fn = lambda c: oansatz.log_amp(spec, params, c)
+  cur = cfg.copy()
+  walker_ids = np.arange(batch, dtype=np.uint64) + np.uint64(w0)
+  mismatches = 0
+  for step in range(8):
+    packed = packed_cuda(cur)
+    count = torch.zeros(1, dtype=torch.int64, device='cuda')
+    a.mc_steps(packed, 1, seed, walker_id0=w0, step0=step, accept_count=count)
+    got = unpack_np(packed, spec.n_sites)
+    down, up, u = philox.fast_proposal(cur, seed, walker_ids, step)
+    prop = cur.copy()
+    rows = np.arange(batch)
+    prop[rows, down] += 2
+    prop[rows, up] -= 2
+    t = torch.from_numpy
+    dl = (fn(t(prop).to(F64)) - fn(t(cur).to(F64))).numpy()
+    acc = np.exp(2 * dl) > u
+    exp = np.where(acc[:, None], prop, cur)
+    near = np.abs(np.exp(2 * dl) - u) < 1e-3 * np.exp(2 * dl)
+    row_same = np.all(got == exp, axis=1)
+    assert np.all(row_same | near)
+    other = np.where(acc[:, None], cur, prop)
+    assert np.all(row_same | np.all(got == other, axis=1))
+    assert int(count.item()) == int(np.all(got == prop, axis=1).sum())
+    mismatches += int((~row_same).sum())
+    cur = got
+  assert mismatches <= 2
+  assert np.all(cur.sum(axis=1) == 0)
+  p_all = packed_cuda(cfg)
+  z_all = torch.empty(batch, device='cuda')
+  a.mc_steps(p_all, 6, 11, walker_id0=3, step0=0, log_amp_out=z_all)
+  p_steps = packed_cuda(cfg)
+  for s in range(0, 6, 2):
+    a.mc_steps(p_steps, 2, 11, walker_id0=3, step0=s)
+  assert torch.equal(p_all, p_steps)
+  # two shards of the walkers: same trajectories (Philox keyed by the global walker id)
+  p_a, p_b = packed_cuda(cfg[:30]), packed_cuda(cfg[30:])
+  a.mc_steps(p_a, 6, 11, walker_id0=3, step0=0)
+  a.mc_steps(p_b, 6, 11, walker_id0=33, step0=0)
+  assert torch.equal(torch.cat([p_a, p_b]), p_all)
+  os.environ['CGSVMC_FC_WARP'] = '0'
+  torch.testing.assert_close(z_all, a.log_amp(p_all), rtol=0, atol=2e-4)
+  p_other = packed_cuda(cfg)
+  a.mc_steps(p_other, 6, 11, walker_id0=3, step0=0)
+  assert (p_other == p_all).all(dim=1).float().mean().item() >= 0.97

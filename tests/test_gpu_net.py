@@ -180,8 +180,14 @@ def test_multi_step_and_sharding_invariance(native, spec):
     a.mc_steps(p, 10, 5, walker_id0=lo, step0=0)
     shards.append(p)
   assert torch.equal(p_all, torch.cat(shards))
-  # cached log-amplitude returned by the sampler == fresh forward pass
-  assert torch.equal(z_all, a.log_amp(p_all))
+  # cached log-amplitude returned by the sampler == fresh forward pass (bit for
+  # bit where both run the same forward code; the fully connected ansatz samples
+  # small batches on the warp-per-walker kernel and evaluates amplitudes on the
+  # tensor-core tiles: float32 grade)
+  if spec.kind == 'fully_connected':
+    torch.testing.assert_close(z_all, a.log_amp(p_all), rtol=0, atol=1e-4)
+  else:
+    assert torch.equal(z_all, a.log_amp(p_all))
   cfg_after = bits.unpack(p_all.cpu().numpy().view(np.uint64), spec.n_sites)
   assert np.all(cfg_after.sum(axis=1) == 0)
 

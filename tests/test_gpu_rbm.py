@@ -640,6 +640,7 @@ def test_graphed_epoch_equals_graphed_batch_steps(native):
 
 
 @pytest.mark.parametrize('n_side,hidden,batch,scale', [(6, 144, 8192, 1.0), (6, 144, 777, 1.0), (6, 100, 300, 1.0),
+                                                       (6, 60, 500, 1.0), (6, 60, 16000, 1.0),
                                                        (4, 24, 130, 1.0), (6, 144, 96, 2.0), (6, 144, 96, 3.0)])
 def test_tensor_core_gradient_equals_register_tiles(native, n_side, hidden, batch, scale, monkeypatch):
   """The pair-table walker kernel forms S_k = sum_b w_kb sigma_bi tanh theta_bj
