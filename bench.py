@@ -512,7 +512,8 @@ def roofline_for(w, t_step, n_act, pk):
             'columns (4 F_fwd)); F_inc = F_fwd for conv (no incremental credit)')
   peak = pk['bf16_tflops_sustained']
   if kind == 'fully_connected':
-    return {'kernel': 'fc_tc.cu tcgen05 kernels (sampler, local energy) + fc_tc_grad.cu tcgen05 gradient sums',
+    return {'kernel': 'fc_warp.cu warp-per-walker sampler (batches <= 2048) / fc_tc.cu tcgen05 sampler, fc_tc.cu tcgen05 '
+                      'local energy, fc_tc_grad.cu tcgen05 gradient sums',
             'bound': 'tensor', 'achieved': flop / t_step / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
             'frac': flop / t_step / 1e12 / peak, 'traffic': None,
             'peak_source': '%s bf16 cuBLAS, sustained' % pk['source'],
