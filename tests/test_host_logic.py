@@ -152,6 +152,15 @@ def _worker(rank, world, port, out_dir):
                                rtol=1e-6, atol=1e-6)
     m = distributed.allreduce_(torch.tensor([float(rank)]), op='max')
     assert m.item() == world - 1
+    # the payload cgsvmc_epoch_end reads directly: all-reduced in float64, local accumulators untouched
+    part_s = per_walker[mine].sum(0)
+    part_t = torch.tensor([e[mine].sum(), (e[mine] ** 2).sum(), float(local), 0.0], dtype=torch.float64)
+    before = (part_s.clone(), part_t.clone())
+    payload = distributed.allreduce_payload(part_s, part_t)
+    assert payload.dtype == torch.float64 and payload.numel() == part_s.numel() + 4
+    assert torch.equal(part_s, before[0]) and torch.equal(part_t, before[1])
+    torch.testing.assert_close(payload[:part_s.numel()].view_as(part_s).float(), sums, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(payload[part_s.numel():], stats, rtol=1e-12, atol=1e-12)
     # totals into separate buffers: the local accumulators stay local, so a
     # second reduce after further accumulation does not double count
     # (metrics in the middle of an epoch, then accumulate again)
