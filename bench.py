@@ -777,7 +777,7 @@ def run_ours(args, rank, world, local_rank):
               'host_pack': bool(auto_pack),
               'host_pack_choice': 'engine.HostFedBatchStep(host_pack="auto"): packs on the host unless the measured '
                                   'packing time exceeds the measured float32 upload + 60 us',
-              'host_pack_probe': fed.host_pack_probe,
+              'host_pack_probe': fed.host_pack_probe, 'host_pack_threads': fed.pack_threads,
               'other_upload_form': {'host_pack': not auto_pack,
                                     'value': walkers_total * SWEEP_STEPS * args.steps / e2e_other_s,
                                     'ms_per_step': e2e_other_s / args.steps * 1e3},

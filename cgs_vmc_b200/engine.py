@@ -246,6 +246,11 @@ class HostFedBatchStep(_CapturedStep):
     # buffer first (cgsvmc_pack_configs_host: 8 bytes per 64 sites over PCIe).
     # 'auto' measures both on this box and packs unless the host cores are far slower than the link.
     self.host_staging = [torch.zeros(B, _native.n_words(N), dtype=torch.int64).pin_memory() for _ in range(2)]
+    # packing threads: the ranks of one box share its cores (8 ranks x 8 threads on 16 cores
+    # measured 98 us per e2e step against 74 us for one rank)
+    import os
+    ranks_here = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
+    self.pack_threads = max(1, min(8, (os.cpu_count() or 8) // ranks_here))
     self.host_pack_probe = None
     if host_pack == 'auto':
       host_pack = self._probe_host_pack(B, N, dev)
@@ -300,10 +305,10 @@ class HostFedBatchStep(_CapturedStep):
     e1.record()
     e1.synchronize()
     t_h2d = e0.elapsed_time(e1) * 1e-3 / 4
-    _native.pack_configs_host(host, self.host_staging[0])
+    _native.pack_configs_host(host, self.host_staging[0], self.pack_threads)
     t0 = time.perf_counter()
     for _ in range(4):
-      _native.pack_configs_host(host, self.host_staging[0])
+      _native.pack_configs_host(host, self.host_staging[0], self.pack_threads)
     t_pack = (time.perf_counter() - t0) / 4
     self.host_pack_probe = {'h2d_float32_us': t_h2d * 1e6, 'host_pack_us': t_pack * 1e6,
                             'h2d_float32_gbps': B * N * 4 / t_h2d / 1e9}
@@ -336,7 +341,7 @@ class HostFedBatchStep(_CapturedStep):
       if self.host_pack:
         self.uploaded[slot].synchronize()        # the copy engine is done with this staging buffer
         _native.upload_configs(host_configs, self.slot_packed[slot], self.copy_stream,
-                               staging=self.host_staging[slot])
+                               staging=self.host_staging[slot], n_threads=self.pack_threads)
       else:
         _native.upload_configs(host_configs, self.dev_cfg[slot], self.copy_stream)
     self.uploaded[slot].record(self.copy_stream)
