@@ -7,10 +7,12 @@
 // Layout conversion only (bit = 1 <=> value > 0, exactly the rule of
 // pack_kernel / load_walker); no amplitude is ever evaluated on the host.
 //
-// A small persistent pool: workers sleep on a condition variable between calls
-// (a job is a contiguous range of walkers), the caller takes the last share
-// itself.
+// A small persistent pool (a job is a contiguous range of walkers; the caller
+// takes the last share itself): workers poll briefly for the next batch of a
+// feed loop before they sleep on a condition variable.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <mutex>
@@ -72,35 +74,28 @@ struct Job {
 
 class Pool {
  public:
-  ~Pool() {
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      stop_ = true;
-    }
-    cv_.notify_all();
-    for (auto& t : workers_) t.join();
-  }
-
   // one caller at a time (the pool is process-wide)
   void run(const Job& job) {
     std::lock_guard<std::mutex> call(call_mu_);
     const int helpers = job.shares - 1;
-    {
-      std::lock_guard<std::mutex> lk(mu_);
+    if (helpers > 0) {
       while ((int)workers_.size() < helpers) {
         const int id = (int)workers_.size();
         workers_.emplace_back([this, id] { loop(id); });
+        workers_.back().detach();        // never joined: the pool lives as long as the process
       }
       job_ = job;
-      pending_ = helpers;
-      ++generation_;
+      // EVERY worker acknowledges every job (after it has read job_), also those without a
+      // share: the next call must not overwrite job_ under a late reader
+      pending_.store((int)workers_.size(), std::memory_order_relaxed);
+      {
+        std::lock_guard<std::mutex> lk(mu_);      // (a worker about to sleep re-checks under this lock)
+        generation_.fetch_add(1, std::memory_order_release);
+      }
+      cv_.notify_all();
     }
-    if (helpers > 0) cv_.notify_all();
     share(job, job.shares - 1);
-    if (helpers > 0) {
-      std::unique_lock<std::mutex> lk(mu_);
-      done_cv_.wait(lk, [this] { return pending_ == 0; });
-    }
+    while (pending_.load(std::memory_order_acquire) != 0) _mm_pause();
   }
 
  private:
@@ -110,33 +105,40 @@ class Pool {
     if (b1 > b0) pack_rows(j.cfg, b0, b1, j.N, j.W, j.out);
   }
 
+  // A feed loop submits a batch every ~70 us: a worker that has just finished
+  // keeps polling for the next job for kSpinUs before it goes to sleep on the
+  // condition variable (a futex wake-up costs 5-10 us per worker -- more than
+  // its share of a C2 batch).
   void loop(int id) {
+    constexpr int64_t kSpinUs = 300;
     uint64_t seen = 0;
     for (;;) {
-      Job j;
-      {
+      const auto t0 = std::chrono::steady_clock::now();
+      bool got = false;
+      for (int it = 0;; ++it) {
+        if (generation_.load(std::memory_order_acquire) != seen) { got = true; break; }
+        _mm_pause();
+        if ((it & 63) == 63 &&
+            std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() > kSpinUs)
+          break;
+      }
+      if (!got) {
         std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
-        if (stop_) return;
-        seen = generation_;
-        j = job_;
+        cv_.wait(lk, [&] { return generation_.load(std::memory_order_acquire) != seen; });
       }
-      const bool mine = id < j.shares - 1;
-      if (mine) share(j, id);
-      {
-        std::lock_guard<std::mutex> lk(mu_);
-        if (mine && --pending_ == 0) done_cv_.notify_one();
-      }
+      seen = generation_.load(std::memory_order_acquire);
+      const Job j = job_;
+      if (id < j.shares - 1) share(j, id);
+      pending_.fetch_sub(1, std::memory_order_release);
     }
   }
 
   std::mutex mu_, call_mu_;
-  std::condition_variable cv_, done_cv_;
+  std::condition_variable cv_;
   std::vector<std::thread> workers_;
   Job job_;
-  uint64_t generation_ = 0;
-  int pending_ = 0;
-  bool stop_ = false;
+  std::atomic<uint64_t> generation_{0};
+  std::atomic<int> pending_{0};
 };
 
 Pool& pool() {

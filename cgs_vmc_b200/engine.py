@@ -305,13 +305,22 @@ class HostFedBatchStep(_CapturedStep):
     e1.record()
     e1.synchronize()
     t_h2d = e0.elapsed_time(e1) * 1e-3 / 4
-    _native.pack_configs_host(host, self.host_staging[0], self.pack_threads)
-    t0 = time.perf_counter()
-    for _ in range(4):
-      _native.pack_configs_host(host, self.host_staging[0], self.pack_threads)
-    t_pack = (time.perf_counter() - t0) / 4
+    # packing threads: the fastest of 1 / 2 / 4 / 8 within this rank's share of the cores (a
+    # container with a CPU quota below its visible core count is faster single-threaded)
+    timings = {}
+    for threads in sorted({1, 2, 4, 8, self.pack_threads}):
+      if threads > self.pack_threads:
+        continue
+      _native.pack_configs_host(host, self.host_staging[0], threads)
+      t0 = time.perf_counter()
+      for _ in range(6):
+        _native.pack_configs_host(host, self.host_staging[0], threads)
+      timings[threads] = (time.perf_counter() - t0) / 6
+    self.pack_threads = min(timings, key=timings.get)
+    t_pack = timings[self.pack_threads]
     self.host_pack_probe = {'h2d_float32_us': t_h2d * 1e6, 'host_pack_us': t_pack * 1e6,
-                            'h2d_float32_gbps': B * N * 4 / t_h2d / 1e9}
+                            'h2d_float32_gbps': B * N * 4 / t_h2d / 1e9,
+                            'host_pack_us_by_threads': {str(k): v * 1e6 for k, v in timings.items()}}
     # Measured on this pool (profiles/r02A_bench_steps{20,200}.json): even on a
     # box whose link moves the float32 batch in 27 us the packed form wins (69
     # against 76 us per step in steady state, 73 against 98 us over the first
