@@ -32,6 +32,7 @@ EXPORTS = [
     'cgsvmc_propose_exchange', 'cgsvmc_accept_exchange', 'cgsvmc_local_energy_from_amps',
     'cgsvmc_swo_weights', 'cgsvmc_adam_step', 'cgsvmc_batch_step_fed', 'cgsvmc_batch_steps',
     'cgsvmc_epoch_end', 'cgsvmc_pack_configs_host', 'cgsvmc_upload_configs',
+    'cgsvmc_conv_periodic',
 ]
 
 
@@ -93,6 +94,7 @@ def load():
   lib.cgsvmc_adam_step.argtypes = [vp, vp, vp, i64, vp, vp, vp, f32, f32, vp, f32, f32, f32, u64, vp, vp]
   lib.cgsvmc_pack_configs_host.argtypes = [vp, i64, i32, vp, i32]
   lib.cgsvmc_upload_configs.argtypes = [vp, i64, i32, vp, vp, i32, vp]
+  lib.cgsvmc_conv_periodic.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
   lib.cgsvmc_epoch_end.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, u64, vp, vp, vp]
   for name in EXPORTS:
     fn = getattr(lib, name)
@@ -450,6 +452,32 @@ def upload_configs(configs, dst, stream, staging=None, n_threads=0):
   b, n = configs.shape
   check(load().cgsvmc_upload_configs(_ptr(configs), b, n, _ptr(staging), _ptr(dst), int(n_threads),
                                      ctypes.c_void_p(stream.cuda_stream)))
+
+
+def conv_periodic(inputs, weights, bias=None):
+  """layers.Conv1dPeriodic / Conv2dPeriodic (layers.py:24-160) on the device:
+  inputs float32 [B, L, C_in] with weights [k, C_in, C_out], or [B, X, Y, C_in]
+  with weights [k, k, C_in, C_out]; returns [B, ..., C_out]
+  (cgsvmc_conv_periodic)."""
+  require_cuda()
+  rank = inputs.dim() - 2
+  if rank not in (1, 2) or weights.dim() != rank + 2:
+    raise ValueError('conv_periodic: inputs [B, L, C] / [B, X, Y, C] and weights [k, (k,) C_in, C_out] expected')
+  k, c_in, c_out = weights.shape[0], weights.shape[-2], weights.shape[-1]
+  if rank == 2 and weights.shape[1] != k:
+    raise ValueError('conv_periodic: square kernels only')
+  if inputs.shape[-1] != c_in:
+    raise ValueError('conv_periodic: input channels do not match the weights')
+  _want(inputs, torch.float32, None, 'inputs')
+  _want(weights, torch.float32, None, 'weights')
+  if bias is not None:
+    _want(bias, torch.float32, (c_out,), 'bias')
+  b, x = inputs.shape[0], inputs.shape[1]
+  y = inputs.shape[2] if rank == 2 else 1
+  out = torch.empty(tuple(inputs.shape[:-1]) + (c_out,), dtype=torch.float32, device=inputs.device)
+  check(load().cgsvmc_conv_periodic(_ptr(inputs), b, x, y, c_in, c_out, k, rank, _ptr(weights), _ptr(bias),
+                                    _ptr(out), _stream()))
+  return out
 
 
 def unpack_configs(packed, n_sites, out=None):

@@ -627,6 +627,24 @@ int cgsvmc_epoch_end(float* params, float* m, float* v, int64_t n, const float* 
                           (cudaStream_t)stream);
 }
 
+int cgsvmc_conv_periodic(const float* input, int64_t B, int32_t size_x, int32_t size_y, int32_t c_in, int32_t c_out,
+                         int32_t kernel_size, int32_t rank, const float* weights, const float* bias, float* output,
+                         void* stream) {
+  NvtxRange range("cgsvmc:conv_periodic");
+  if (rank != 1 && rank != 2) return invalid("conv_periodic: rank must be 1 or 2");
+  if (B < 0 || size_x < 1 || size_y < 1 || c_in < 1 || c_out < 1 || kernel_size < 1)
+    return invalid("conv_periodic: bad shape");
+  if (rank == 1 && size_y != 1) return invalid("conv_periodic: rank 1 needs size_y = 1");
+  if (B == 0) return CGSVMC_OK;
+  if (input == nullptr || weights == nullptr || output == nullptr) return invalid("conv_periodic: NULL buffer");
+  // wrap padding placed BEFORE the data: layers.py:64-73 (1-D: k/2 for even kernels) and
+  // 132-141 (2-D: k/2 - 1 for even kernels); (k - 1) / 2 for odd kernels
+  const int k = kernel_size;
+  const int pad = k % 2 == 1 ? (k - 1) / 2 : (rank == 1 ? k / 2 : k / 2 - 1);
+  return launch_conv_periodic(input, B, size_x, size_y, c_in, c_out, k, rank == 2 ? k : 1, pad, rank == 2 ? pad : 0,
+                              weights, bias, output, (cudaStream_t)stream);
+}
+
 int cgsvmc_energy_stats(const float* e_loc, int64_t B, double* stats, void* stream) {
   NvtxRange range("cgsvmc:K5 energy_stats");
   if (B < 0) return invalid("energy_stats: n_walkers < 0");

@@ -91,6 +91,8 @@ int launch_reduce_partials(const float* partials, int n_parts, int64_t n, float*
 int launch_swo_weights(const float* z, const float* sign, const float* zt, const float* sign_t, int64_t B,
                        float log_norm, float inv_total, float* weights, double* acc, cudaStream_t s);
 int pack_configs_host(const float* configs, int64_t B, int N, uint64_t* packed, int n_threads);
+int launch_conv_periodic(const float* in, int64_t B, int X, int Y, int Cin, int Cout, int kx, int ky, int pad_x,
+                         int pad_y, const float* w, const float* bias, float* out, cudaStream_t s);
 int launch_epoch_end(float* params, float* m, float* v, int64_t n, const float* tot_sums,
                      const double* tot_payload, const double* tot_stats, float* zero_a, float* zero_b,
                      double* zero_stats_a, double* zero_stats_b, float inv_nb, float lr, float b1, float b2,

@@ -378,6 +378,42 @@ __global__ void epoch_end_kernel(float* __restrict__ params, float* __restrict__
   }
 }
 
+// One periodic convolution layer on its own (layers.py:24-160: Conv1dPeriodic /
+// Conv2dPeriodic = wrap padding + snt.Conv with padding VALID, stride 1):
+//   out[b, x, y, co] = bias[co] + sum_{dx, dy, ci} in[b, (x + dx - pad_x) mod X, (y + dy - pad_y) mod Y, ci]
+//                                                  * w[dx, dy, ci, co]
+// NHWC, w as [kx, ky, C_in, C_out] (Sonnet's layout).  One thread per output
+// element with the output channel fastest: coalesced stores and weight reads,
+// the input value of a (position, tap, ci) is a broadcast within the channel
+// group.  The ansatz kernels fuse this into whole networks; this entry exists
+// so that the layer is callable by itself like the reference's module.
+__global__ void conv_periodic_kernel(const float* __restrict__ in, int64_t B, int X, int Y, int Cin, int Cout,
+                                     int kx, int ky, int pad_x, int pad_y, const float* __restrict__ w,
+                                     const float* __restrict__ bias, float* __restrict__ out) {
+  const int64_t total = B * X * Y * Cout;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(e % Cout);
+    int64_t r = e / Cout;
+    const int y = (int)(r % Y); r /= Y;
+    const int x = (int)(r % X);
+    const int64_t b = r / X;
+    float acc = bias != nullptr ? bias[co] : 0.f;
+    for (int dx = 0; dx < kx; ++dx) {
+      int sx = (x + dx - pad_x) % X;
+      if (sx < 0) sx += X;
+      for (int dy = 0; dy < ky; ++dy) {
+        int sy = (y + dy - pad_y) % Y;
+        if (sy < 0) sy += Y;
+        const float* src = in + ((b * X + sx) * Y + sy) * Cin;
+        const float* wt = w + ((size_t)(dx * ky + dy) * Cin) * Cout + co;
+        for (int ci = 0; ci < Cin; ++ci) acc = fmaf(src[ci], wt[(size_t)ci * Cout], acc);
+      }
+    }
+    out[e] = acc;
+  }
+}
+
 int blocks_for(int64_t work_items, int per_block) {
   const int64_t need = (work_items + per_block - 1) / per_block;
   return (int)std::max<int64_t>(1, std::min<int64_t>(need, 148 * 16));
@@ -472,6 +508,15 @@ int launch_epoch_end(float* params, float* m, float* v, int64_t n, const float* 
                                                         zero_stats_a, zero_stats_b, inv_nb, lr, b1, b2, eps, t,
                                                         stats_out, ticket);
   return cuda_fail(cudaGetLastError(), "epoch_end launch");
+}
+
+int launch_conv_periodic(const float* in, int64_t B, int X, int Y, int Cin, int Cout, int kx, int ky, int pad_x,
+                         int pad_y, const float* w, const float* bias, float* out, cudaStream_t s) {
+  const int64_t total = B * X * Y * Cout;
+  if (total == 0) return CGSVMC_OK;
+  conv_periodic_kernel<<<blocks_for(total, kThreads), kThreads, 0, s>>>(in, B, X, Y, Cin, Cout, kx, ky, pad_x, pad_y,
+                                                                        w, bias, out);
+  return cuda_fail(cudaGetLastError(), "conv_periodic launch");
 }
 
 int launch_reduce_partials(const float* partials, int n_parts, int64_t n, float* out,

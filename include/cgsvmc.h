@@ -410,6 +410,20 @@ int cgsvmc_epoch_end(float* params, float* m, float* v, int64_t n,
                      float beta1, float beta2, float eps, uint64_t t,
                      double* stats_out, uint32_t* ticket, void* stream);
 
+/* Replaces one call of layers.Conv1dPeriodic / Conv2dPeriodic (layers.py:24-160):
+ * periodic (wrap) padding followed by snt.Conv1D / snt.Conv2D with padding
+ * VALID and stride 1.  input: float32 [B, size_x, size_y, c_in] (NHWC; rank 1:
+ * size_y = 1, i.e. [B, L, c_in]), weights: [k, (k,) c_in, c_out] (Sonnet's
+ * layout), bias: [c_out] or NULL, output: [B, size_x, size_y, c_out].  The
+ * padding placed before the data is (k - 1) / 2 for odd k and, for even k,
+ * k / 2 in 1-D (layers.py:64-73) but k / 2 - 1 in 2-D (layers.py:132-141).
+ * The ansatz entry points fuse these layers into whole networks; this one makes
+ * the layer callable by itself. */
+int cgsvmc_conv_periodic(const float* input, int64_t n_batch, int32_t size_x,
+                         int32_t size_y, int32_t c_in, int32_t c_out,
+                         int32_t kernel_size, int32_t rank, const float* weights,
+                         const float* bias, float* output, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

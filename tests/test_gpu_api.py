@@ -194,6 +194,35 @@ def test_energy_gradient_epoch_launch_equals_per_batch_ops(kind, overrides):
     torch.testing.assert_close(other[0][keep], results[0][0][keep], rtol=2e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize('rank,shape,c_in,c_out,k', [
+    (1, (7,), 1, 5, 3), (1, (10,), 3, 16, 4), (1, (12,), 2, 3, 5), (1, (9,), 4, 6, 6), (1, (5,), 1, 2, 1),
+    (2, (4, 6), 1, 5, 2), (2, (10, 10), 1, 16, 5), (2, (6, 6), 16, 16, 3), (2, (5, 7), 3, 4, 4), (2, (3, 3), 2, 2, 5),
+])
+def test_periodic_conv_layers_standalone(rank, shape, c_in, c_out, k):
+  """layers.Conv1dPeriodic / Conv2dPeriodic called by themselves
+  (cgsvmc_conv_periodic) against the oracle's restatement of layers.py:51-80 /
+  117-160 -- wrap padding (with the 1-D / 2-D asymmetry of even kernels, also
+  for kernels wider than the lattice) + VALID cross-correlation + bias -- which
+  the network goldens recorded from the reference pin."""
+  from cgs_vmc_b200 import layers
+  g = torch.Generator().manual_seed(100 * rank + k)
+  x = torch.randn((11,) + shape + (c_in,), generator=g)
+  cls = layers.Conv1dPeriodic if rank == 1 else layers.Conv2dPeriodic
+  layer = cls(c_out, k).initialize(c_in, generator=g)
+  layer.b = torch.randn(c_out, generator=g).cuda()
+  got = layer(x.cuda()).cpu().double()
+  pad = oansatz._pad_periodic_1d if rank == 1 else oansatz._pad_periodic_2d
+  ref = oansatz._conv_valid(pad(x.double(), k), layer.w.cpu().double(), layer.b.cpu().double())
+  assert got.shape == ref.shape == (11,) + shape + (c_out,)
+  torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
+  assert layer.pad_sizes() == ((k - 1) // 2, (k - 1) // 2) if k % 2 else True
+  with pytest.raises(ValueError):
+    layer(x.cuda()[0])                       # wrong rank
+  lazy = cls(c_out, k)                       # Sonnet-style lazy initialisation on first call
+  out = lazy(x.cuda())
+  assert out.shape == got.shape and lazy.w.shape == layer.w.shape and float(lazy.b.abs().max()) == 0.0
+
+
 def test_supervised_training_reduces_loss():
   from cgs_vmc_b200 import training, utils, wavefunctions
   from cgs_vmc_b200.session import Session
