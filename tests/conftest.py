@@ -25,7 +25,7 @@ def _names():
 
 def golden_names():
   """Cases of make_golden.py (amplitudes, sampler, Hamiltonian, EnergyGradient, SWO)."""
-  return [n for n in _names() if not n.startswith(('opt_', 'cmp_'))]
+  return [n for n in _names() if not n.startswith(('opt_', 'cmp_', 'layers_'))]
 
 
 def opt_golden_names():

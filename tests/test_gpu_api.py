@@ -223,6 +223,24 @@ def test_periodic_conv_layers_standalone(rank, shape, c_in, c_out, k):
   assert out.shape == got.shape and lazy.w.shape == layer.w.shape and float(lazy.b.abs().max()) == 0.0
 
 
+def test_periodic_conv_layers_reference_golden():
+  """cgsvmc_conv_periodic through layers.Conv1dPeriodic / Conv2dPeriodic against
+  the outputs recorded from the reference's own modules on the same inputs and
+  variables (tests/golden/make_golden_layers.py)."""
+  from cgs_vmc_b200 import layers
+  g = np.load(os.path.join(REPO, 'tests', 'golden', 'layers_periodic.npz'))
+  n = 0
+  while 'case%d_meta' % n in g:
+    rank, c_in, c_out, k = (int(v) for v in g['case%d_meta' % n])
+    layer = (layers.Conv1dPeriodic if rank == 1 else layers.Conv2dPeriodic)(c_out, k)
+    layer.w = torch.from_numpy(g['case%d_w' % n]).cuda()
+    layer.b = torch.from_numpy(g['case%d_b' % n]).cuda()
+    y = layer(torch.from_numpy(g['case%d_x' % n]).cuda()).cpu().numpy()
+    np.testing.assert_allclose(y, g['case%d_y' % n], rtol=2e-5, atol=2e-5)
+    n += 1
+  assert n == 8
+
+
 def test_supervised_training_reduces_loss():
   from cgs_vmc_b200 import training, utils, wavefunctions
   from cgs_vmc_b200.session import Session

@@ -109,3 +109,23 @@ def test_exact_expectation_and_acceptance_known_answers():
   assert abs(ed.exact_acceptance_rate(n, lambda c: np.ones(len(c))) - 1.0) < 1e-12
   rate = ed.exact_acceptance_rate(n, lambda c: psi_fn(c).numpy())
   assert 0.0 < rate < 1.0
+
+
+def test_periodic_padding_against_reference_layers():
+  """oracle.ansatz._pad_periodic_1d / _2d + _conv_valid against the outputs of
+  the reference's own layers.Conv1dPeriodic / Conv2dPeriodic modules
+  (tests/golden/make_golden_layers.py; layers.py:24-160), odd and even kernels."""
+  import os
+  import numpy as np
+  import torch
+  from oracle import ansatz as oansatz
+  g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'layers_periodic.npz'))
+  n = 0
+  while 'case%d_meta' % n in g:
+    rank, c_in, c_out, k = (int(v) for v in g['case%d_meta' % n])
+    x, w, b = (torch.from_numpy(g['case%d_%s' % (n, key)]).double() for key in 'xwb')
+    pad = oansatz._pad_periodic_1d if rank == 1 else oansatz._pad_periodic_2d
+    y = oansatz._conv_valid(pad(x, k), w, b).numpy()
+    np.testing.assert_allclose(y, g['case%d_y' % n], rtol=2e-5, atol=2e-5)
+    n += 1
+  assert n == 8
