@@ -365,3 +365,19 @@ def test_drivers_end_to_end(tmp_path):
                  check=True, env=env, timeout=300)
   assert os.path.exists(os.path.join(swo, 'model_after_1_epochs.pt'))
   assert len(open(os.path.join(swo, 'metrics.txt')).read().split()) == 2
+
+
+def test_empty_batches_through_the_late_entry_points():
+  """B = 0 / n = 0 are no-ops with status OK (the reference's ops accept empty
+  batches): host packing, upload, standalone periodic convolution, epoch end."""
+  from cgs_vmc_b200 import _native
+  out = torch.zeros(0, 1, dtype=torch.int64)
+  _native.pack_configs_host(torch.zeros(0, 36), out)
+  y = _native.conv_periodic(torch.zeros(0, 6, 6, 1, device='cuda'), torch.zeros(3, 3, 1, 4, device='cuda'))
+  assert tuple(y.shape) == (0, 6, 6, 4)
+  z = torch.zeros(0, device='cuda')
+  _native.epoch_end(z, z.clone(), z.clone(), torch.zeros(2, 0, device='cuda'),
+                    torch.zeros(4, dtype=torch.float64, device='cuda'),
+                    torch.zeros(1, dtype=torch.int32, device='cuda'), t=1)
+  with pytest.raises(ValueError):
+    _native.conv_periodic(torch.zeros(2, 6, 6, 2, device='cuda'), torch.zeros(3, 3, 1, 4, device='cuda'))
