@@ -20,6 +20,7 @@
 #include <vector>
 
 #include <immintrin.h>
+#include <unistd.h>
 
 #include "internal.h"
 
@@ -78,6 +79,10 @@ class Pool {
   void run(const Job& job) {
     std::lock_guard<std::mutex> call(call_mu_);
     const int helpers = job.shares - 1;
+    if (owner_pid_ != getpid()) {      // after fork() the child has the bookkeeping but not the threads
+      workers_.clear();
+      owner_pid_ = getpid();
+    }
     if (helpers > 0) {
       while ((int)workers_.size() < helpers) {
         const int id = (int)workers_.size();
@@ -139,6 +144,7 @@ class Pool {
   Job job_;
   std::atomic<uint64_t> generation_{0};
   std::atomic<int> pending_{0};
+  pid_t owner_pid_ = getpid();
 };
 
 Pool& pool() {
