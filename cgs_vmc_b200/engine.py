@@ -4,7 +4,8 @@ This is the host-side glue under the reference-shaped API (graph_builders,
 operators, training): it owns the torch buffers and calls the C-ABI.  Nothing
 here computes on the CPU.
 """
-import types
+import os
+import time
 
 import torch
 
@@ -248,7 +249,6 @@ class HostFedBatchStep(_CapturedStep):
     self.host_staging = [torch.zeros(B, _native.n_words(N), dtype=torch.int64).pin_memory() for _ in range(2)]
     # packing threads: the ranks of one box share its cores (8 ranks x 8 threads on 16 cores
     # measured 98 us per e2e step against 74 us for one rank)
-    import os
     ranks_here = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
     self.pack_threads = max(1, min(8, (os.cpu_count() or 8) // ranks_here))
     self.host_pack_probe = None
@@ -293,7 +293,6 @@ class HostFedBatchStep(_CapturedStep):
   def _probe_host_pack(self, B, N, dev):
     """True when packing a float32 [B, N] batch on the host cores takes less
     time than the extra bytes of its float32 upload on this box."""
-    import time
     host = torch.ones(B, N, dtype=torch.float32).pin_memory()
     dst = torch.empty(B, N, dtype=torch.float32, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
