@@ -164,7 +164,7 @@ size_t walker_smem_bytes(const Image& im, int slots, bool ws, bool do_eloc, int 
 }
 
 // Fills everything but the shared-memory decisions.
-bool base_plan(const cgsvmc_ansatz* a, int64_t B, Plan* pl) {
+bool base_plan(const cgsvmc_ansatz* a, int64_t B, Plan* pl, bool walker) {
   const cgsvmc_ansatz_desc& d = a->desc;
   if (d.kind != CGSVMC_ANSATZ_RBM || d.num_layers != 0) return false;
   if (d.layer_size < 1 || d.layer_size > 256 || d.n_sites > CGSVMC_MAX_SITES) return false;
@@ -181,7 +181,7 @@ bool base_plan(const cgsvmc_ansatz* a, int64_t B, Plan* pl) {
   pl->lpw = (forced_lpw != 16 && pl->kjv <= 5) ? 8 : 16;
   pl->im = make_image(d.n_sites, H, HP);
   pl->nw = n_words(d.n_sites) == 3 ? 4 : n_words(d.n_sites);
-  const int wpw = 32 / pl->lpw, slots = variant_slots(pl->lpw, pl->kjv);
+  const int wpw = 32 / pl->lpw, slots = variant_slots(pl->lpw, pl->kjv, walker);
   pl->slots = slots;
   const int64_t per_sm = std::max<int64_t>(1, (B + a->num_sms - 1) / a->num_sms);
   const int64_t rounds = (per_sm + slots - 1) / slots;
@@ -246,7 +246,7 @@ using namespace rbm2;
 
 bool rbm2_supported(const cgsvmc_ansatz* a, const cgsvmc_ham* h) {
   Plan pl;
-  if (!base_plan(a, 1, &pl)) return false;
+  if (!base_plan(a, 1, &pl, true)) return false;
   const int slots = pl.slots;
   const int nb = h != nullptr ? h->n_bonds : 0;
   if (nb >= 32768) return false;      // list entries keep 15 bits of bond index
@@ -258,7 +258,7 @@ int rbm2_mc_steps(cgsvmc_ansatz* a, uint64_t* packed, int64_t B, int n_steps, ui
                   uint64_t walker0, uint64_t step0, unsigned long long* accept_count,
                   float* log_amp_out, cudaStream_t st) {
   Plan pl;
-  if (!base_plan(a, B, &pl)) { set_error("rbm2: unsupported ansatz"); return CGSVMC_ERR_UNSUPPORTED; }
+  if (!base_plan(a, B, &pl, false)) { set_error("rbm2: unsupported ansatz"); return CGSVMC_ERR_UNSUPPORTED; }
   const size_t img_bytes = (size_t)pl.im.total * 4;
   pl.ws = img_bytes + 16 <= (size_t)a->max_smem_optin;
   pl.mc_smem = (pl.ws ? img_bytes : 2048) + 16;
@@ -276,7 +276,7 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
                 const float* weights, int K, float* out, double* stats, cudaStream_t st,
                 const Rbm2Sweep* sweep) {
   Plan pl;
-  if (!base_plan(a, B, &pl)) { set_error("rbm2: unsupported ansatz"); return CGSVMC_ERR_UNSUPPORTED; }
+  if (!base_plan(a, B, &pl, true)) { set_error("rbm2: unsupported ansatz"); return CGSVMC_ERR_UNSUPPORTED; }
   const bool do_eloc = h != nullptr;
   const bool mc = sweep != nullptr;
   const int slots = pl.slots;
@@ -344,7 +344,7 @@ int rbm2_walker(cgsvmc_ansatz* a, const cgsvmc_ham* h, const uint64_t* packed, i
   if (do_grad && !fuse_off && pl.grid <= a->num_sms) {
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, a->device);
-    const int threads = variant_slots(pl.lpw, pl.kjv) / (32 / pl.lpw) * 32;
+    const int threads = variant_slots(pl.lpw, pl.kjv, true) / (32 / pl.lpw) * 32;
     fuse = coop != 0 && (size_t)slots * pl.im.HP >= (size_t)(threads / 32) * 96;
   }
   if (fuse && a->grid_sync == nullptr) {

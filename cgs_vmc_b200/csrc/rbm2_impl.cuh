@@ -25,7 +25,8 @@
 // with VW = 32 / LPW lane `sub` holds hidden units j = VW (sub + LPW q) + c,
 // q < KJV = HP / 32, c < VW, so a table row is read with LDS.128 / LDS.64 in
 // phases of one walker (128 contiguous bytes) each -- conflict-free.
-// One persistent CTA per SM (1024 threads when the state fits 64 registers).
+// One persistent CTA per SM (the sampler kernel: 1024 threads when the state
+// fits 64 registers; the walker kernel: always 512 threads / 128 registers).
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -537,11 +538,16 @@ struct SitePicker {
 // ---------------------------------------------------------------------------
 // K2: Metropolis sampler, graph_builders.py:54-89 x n_steps
 // ---------------------------------------------------------------------------
-// CTA size: 1024 threads when the per-lane state fits a 64-register budget.
-template <int LPW, int KJV>
+// CTA size.  The sampler kernel (mc_kernel) takes 1024 threads when the per-lane
+// state fits a 64-register budget (at most 10 hidden units per lane): more
+// walkers in flight per SM.  The walker kernel (estimators + sweep) always takes
+// 512 threads = 128 registers: at 64 registers its small-H variants spilled
+// 200-1000 B and ran 1.3-1.8x slower (6x6, H = 64, 8,192 walkers: 54.4 -> 29.8 us
+// per batch iteration; H = 32: 36.1 -> 25.9 us; profiles/r02Y_rbm2_small_h.jsonl).
+template <int LPW, int KJV, bool WALKER = false>
 struct Geometry {
   static constexpr int VW = 32 / LPW, KJ = VW * KJV, HP = 32 * KJV, WPW = 32 / LPW;
-  static constexpr int THREADS = KJ <= 10 ? 1024 : 512;
+  static constexpr int THREADS = (!WALKER && KJ <= 10) ? 1024 : 512;
   static constexpr int WARPS = THREADS / 32, SLOTS = WARPS * WPW;
 };
 
@@ -1003,9 +1009,9 @@ __device__ __forceinline__ void grid_reduce(const WalkerArgs& A, float* red) {
 // separates the two uses; later batches of the same CTA read 2W from global
 // memory).
 template <int NW, int LPW, int KJV, bool WS, bool MC, bool PT = false>
-__global__ void __launch_bounds__((Geometry<LPW, KJV>::THREADS), 1)
+__global__ void __launch_bounds__((Geometry<LPW, KJV, true>::THREADS), 1)
 walker_kernel(Image im, const float* __restrict__ img_g, WalkerArgs A) {
-  using Geo = Geometry<LPW, KJV>;
+  using Geo = Geometry<LPW, KJV, true>;
   constexpr int WPW = Geo::WPW, KJ = Geo::KJ, VW = Geo::VW, HP = Geo::HP;
   constexpr int SLOTS = Geo::SLOTS, THREADS = Geo::THREADS;
   static_assert(!PT || WS, "the pair-table kernel keeps its tables in shared memory");
@@ -1605,7 +1611,7 @@ int launch_mc_variant(const Plan& pl, const float* img, uint64_t* packed, int64_
 
 template <int NW, int LPW, int KJV>
 int launch_walker_variant(const Plan& pl, const float* img, const WalkerArgs& A, cudaStream_t st) {
-  constexpr int THREADS = Geometry<LPW, KJV>::THREADS;
+  constexpr int THREADS = Geometry<LPW, KJV, true>::THREADS;
   const bool mc = A.packed_rw != nullptr;
 #define RBM2_LAUNCH_WALKER(WSV, MCV, PTV)                                         \
   do {                                                                            \
@@ -1633,9 +1639,9 @@ int launch_walker_variant(const Plan& pl, const float* img, const WalkerArgs& A,
 }
 
 // walkers per CTA batch of a variant (host-side planning)
-inline int variant_slots(int lpw, int kjv) {
+inline int variant_slots(int lpw, int kjv, bool walker) {
   const int kj = (32 / lpw) * kjv;
-  return ((kj <= 10 ? 1024 : 512) / 32) * (32 / lpw);
+  return (((!walker && kj <= 10) ? 1024 : 512) / 32) * (32 / lpw);
 }
 
 #define RBM2_VARIANT_SWITCH(NWV, CALL)                       \
