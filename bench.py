@@ -401,9 +401,15 @@ def time_workload(w, steps, warmup, flush, world, dev, clock_index=None, force_p
   w.step()                                 # the rebuilding variant of the step, once
   flush.zero_()
   w.epoch_end()
+  tail = steps % epoch_len               # a shorter last epoch gets its own captured launch
+  tail_epoch = per_epoch and tail >= 2 and w.prepare_epoch(tail)
   if per_epoch:
     for _ in range(2):                     # and of the epoch launch
       w.run_epoch(epoch_len)
+      flush.zero_()
+      w.epoch_end()
+    if tail_epoch:
+      w.run_epoch(tail)
       flush.zero_()
       w.epoch_end()
   w.launches = 0
@@ -420,7 +426,7 @@ def time_workload(w, steps, warmup, flush, world, dev, clock_index=None, force_p
   k = 0
   while k < steps:
     n = min(epoch_len, steps - k)
-    if per_epoch and n == epoch_len:
+    if per_epoch and (n == epoch_len or (tail_epoch and n == tail)):
       m0, m1 = ev(), ev()
       m0.record()
       w.run_epoch(n)
