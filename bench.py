@@ -530,8 +530,10 @@ def roofline_for(w, t_step, n_act, pk):
                      'frac': flop / t_step / 1e12 / fp32_peak,
                      'peak_source': 'derived: 148 SM x 128 FP32 lanes x 2 x sm_max_mhz'},
             'what': what, 'kernel_ms': t_step * 1e3, 'n_active_bonds_mean': n_act,
-            'note': 'at 1024 walkers (8 tiles of 128 for the sampler) the step is launch- and latency-bound; '
-                    'profiles/ holds the 65536-walker numbers where the tensor path is 2.5-3.4x the SIMT path'}
+            'note': 'at 1024 walkers the step is latency-bound: the sweep runs on the warp-per-walker kernel '
+                    '(fc_warp.cu, FP32 SIMT, 7 warps per SM; floor = one shared-memory weight read per warp), '
+                    'local energy and gradient on tcgen05 tiles of 128 items; profiles/ holds the 65536-walker '
+                    'numbers where the tensor path is 2.5-3.4x the SIMT path'}
   return {'kernel': 'conv_tc.cu tcgen05 kernels (sampler, local energy) + conv_tc_grad.cu tcgen05 gradient sums',
           'bound': 'tensor', 'achieved': flop / t_step / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
           'frac': flop / t_step / 1e12 / peak, 'traffic': None,
