@@ -69,10 +69,20 @@ def allreduce_sums(sums, stats, out_sums=None, out_stats=None):
   return out_sums, out_stats
 
 
+_PAYLOADS = {}
+
+
 def allreduce_payload(sums, stats):
   """The all-reduced FLOAT64 payload [K * P + 4] itself (cgsvmc_epoch_end reads
-  it directly: no unpacking pass)."""
-  payload = pack_sums(sums, stats)
+  it directly: no unpacking pass).  The returned buffer is reused by the next
+  call with the same shapes."""
+  n = sums.numel()
+  key = (n, stats.numel(), sums.device)
+  payload = _PAYLOADS.get(key)
+  if payload is None:          # one buffer per shape: two converting copies, no allocation per epoch
+    payload = _PAYLOADS[key] = torch.empty(n + stats.numel(), dtype=torch.float64, device=sums.device)
+  payload[:n].copy_(sums.reshape(-1))
+  payload[n:].copy_(stats)
   if world_size() > 1:
     dist.all_reduce(payload, op=dist.ReduceOp.SUM)
   return payload
